@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def scans2d():
+    """Bundled 2-D LiDAR scans of the reference (tests/golden/scans2d.npz, see make_fixtures.py)."""
+    import numpy as np
+    z = np.load(os.path.join(ROOT, "tests", "golden", "scans2d.npz"))
+    pts, off, ids = z["points"], z["offsets"], z["ids"]
+    return {int(i): pts[off[k]:off[k + 1]].copy() for k, i in enumerate(ids)}
