@@ -1,0 +1,155 @@
+/*
+ * icp_b200.h — C ABI of the B200-native ICP iteration loop (libicp_b200.so).
+ *
+ * Drop-in boundary for tier4/icp_rust's estimation API.  Each entry point names the
+ * reference interface it replaces (file:line relative to the icp_rust repository); the Rust
+ * `extern "C"` block a maintainer adds to src/lib.rs is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - Points are array-of-structs f64 exactly as `&[Vector2]` / `&[Vector3]` are laid out
+ *    (src/types.rs:4-12): x0 y0 x1 y1 ... or x0 y0 z0 x1 ...
+ *  - A `Transform` (src/transform.rs:6-10, no #[repr(C)]) crosses the boundary as 6 doubles
+ *    [r00 r01 r10 r11 tx ty]: the full 2x2 rotation matrix, row-major, then the translation.
+ *  - Batches are ragged: pair b owns points [off[b], off[b+1]) of the concatenated array.
+ *  - Every function returns an icp_b200_status.  Nothing aborts; where the reference would
+ *    panic (empty target: src/lib.rs:122,165; NaN: src/stats.rs:12) the pair's status says so
+ *    and its output transform equals its initial transform.
+ *  - There is no CPU fallback: without a CUDA device every compute entry returns
+ *    ICP_B200_ERR_NO_DEVICE / ICP_B200_ERR_CUDA.
+ *  - Threading: a context owns one device, its streams and scratch memory.  Calls on ONE context
+ *    must be serialised by the caller; different contexts (also on the same device) are
+ *    independent and may be used from different threads.
+ */
+#ifndef ICP_B200_H
+#define ICP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICP_B200_ABI_VERSION 1
+
+typedef enum {
+    ICP_B200_OK = 0,
+    ICP_B200_ERR_INVALID_ARGUMENT = 1,
+    ICP_B200_ERR_CUDA = 2,
+    ICP_B200_ERR_NO_DEVICE = 3,
+    ICP_B200_ERR_EMPTY_TARGET = 4, /* a pair had no target points but source points (reference panics) */
+    ICP_B200_ERR_NON_FINITE = 5,   /* a pair held NaN/Inf coordinates or transform (reference panics on NaN) */
+    ICP_B200_ERR_TOO_LARGE = 6,    /* a scan exceeds what the device kernels of this build hold */
+    ICP_B200_ERR_OUT_OF_MEMORY = 7
+} icp_b200_status;
+
+/* per-pair status values written to icp_b200_batch.out_status */
+#define ICP_B200_PAIR_OK 0
+#define ICP_B200_PAIR_EMPTY_TARGET 1
+#define ICP_B200_PAIR_TOO_LARGE 2
+#define ICP_B200_PAIR_NON_FINITE 3
+
+/* break reasons of the inner IRLS loop, src/lib.rs:66-82 (upper half of out_inner words) */
+#define ICP_B200_BREAK_CAP 0   /* 200 iterations exhausted */
+#define ICP_B200_BREAK_NONE 1  /* weighted_gauss_newton_update returned None */
+#define ICP_B200_BREAK_DELTA 2 /* delta.dot(delta) < 1e-6 */
+#define ICP_B200_BREAK_ERROR 3 /* huber_error increased */
+
+#define ICP_B200_CORR_NONE 0
+#define ICP_B200_CORR_LAST 1   /* out_corr[off_src[b] + i]: index chosen in the last outer iteration */
+#define ICP_B200_CORR_ALL 2    /* out_corr[off_src[b]*max_iter + it*n_b + i] */
+
+typedef struct icp_b200_context icp_b200_context;
+typedef struct icp_b200_target icp_b200_target;
+
+/* One batched call = `batch` independent Icp2d::estimate / Icp3d::estimate calls
+ * (src/lib.rs:105-110, 148-153).  batch == 1 reproduces the reference call exactly. */
+typedef struct {
+    uint32_t dim;            /* 2 -> Icp2d, 3 -> Icp3d (NN in xyz, solve in xy: src/lib.rs:148-173) */
+    uint32_t batch;          /* number of scan pairs B */
+    uint32_t max_iter;       /* `max_iter` argument of estimate (outer iterations, no early exit) */
+    int32_t corr_mode;       /* ICP_B200_CORR_* */
+    const double *src;       /* `src: &[VectorD]` of every pair, concatenated */
+    const uint32_t *src_off; /* [B+1] */
+    const double *dst;       /* `dst` given to Icp2d::new / Icp3d::new, concatenated; ignored by
+                                icp_b200_target_estimate_batch */
+    const uint32_t *dst_off; /* [B+1] */
+    const double *init_T;    /* [B*6] `initial_transform` */
+    double *out_T;           /* [B*6] returned `Transform` */
+    uint32_t *out_inner;     /* nullable [B*max_iter]: accepted IRLS updates | break reason << 16 */
+    int32_t *out_corr;       /* nullable, see ICP_B200_CORR_* */
+    uint64_t *out_corr_hash; /* nullable [B]: order-independent checksum of every outer
+                                iteration's correspondences (definition in DESIGN.md) */
+    int32_t *out_status;     /* nullable [B]: ICP_B200_PAIR_* */
+} icp_b200_batch;
+
+/* counters of the most recent compute call on a context */
+typedef struct {
+    uint32_t kernel_launches;  /* kernels of this library launched by the call */
+    float kernel_ms;           /* device time of those kernels, CUDA events on the launching stream */
+    uint64_t h2d_bytes;        /* bytes the call copied host -> device */
+    uint64_t d2h_bytes;        /* bytes the call copied device -> host */
+    uint32_t grid_ctas, block_threads, smem_bytes; /* launch shape of the ICP kernel */
+} icp_b200_call_info;
+
+int icp_b200_abi_version(void);
+const char *icp_b200_status_string(int status);
+int icp_b200_device_count(int *count);
+
+/* A context binds one CUDA device.  `device` is the CUDA ordinal. */
+int icp_b200_create(int device, icp_b200_context **out);
+void icp_b200_destroy(icp_b200_context *ctx);
+int icp_b200_last_call_info(const icp_b200_context *ctx, icp_b200_call_info *info);
+const char *icp_b200_last_error(const icp_b200_context *ctx);
+
+/* Icp2d::new(dst).estimate(src, init, max_iter) for every pair; HOST pointers.  Inputs are
+ * copied to the device in chunks overlapped with compute; results are copied back before
+ * the call returns.  Replaces src/lib.rs:97-130 and src/lib.rs:139-173. */
+int icp_b200_estimate_batch(icp_b200_context *ctx, const icp_b200_batch *batch);
+
+/* Same with DEVICE pointers (inputs resident in HBM, outputs written to HBM).  Enqueued on
+ * `stream` (a cudaStream_t, NULL = the context's stream) and synchronised before returning
+ * only if `synchronize` is non-zero. */
+int icp_b200_estimate_batch_device(icp_b200_context *ctx, const icp_b200_batch *batch,
+                                   void *stream, int synchronize);
+
+/* Single-pair wrappers with the reference's argument order:
+ *   Icp2d::new(dst) (src/lib.rs:97) + Icp2d::estimate(src, initial_transform, max_iter)
+ *   (src/lib.rs:105-110); Icp3d twins (src/lib.rs:139, 148-153). */
+int icp_b200_icp2d_estimate(icp_b200_context *ctx, const double *dst_xy, uint32_t n_dst,
+                            const double *src_xy, uint32_t n_src, const double initial_transform[6],
+                            uint32_t max_iter, double out_transform[6]);
+int icp_b200_icp3d_estimate(icp_b200_context *ctx, const double *dst_xyz, uint32_t n_dst,
+                            const double *src_xyz, uint32_t n_src, const double initial_transform[6],
+                            uint32_t max_iter, double out_transform[6]);
+
+/* Reusable target: the `Icp2d<'a>` / `Icp3d<'a>` value itself (src/lib.rs:91-102, 133-144).
+ * Builds the search structure once on the device; any number of estimates and searches may
+ * follow.  `dst` is a HOST pointer and is copied (the reference borrows it for 'a). */
+int icp_b200_target_create(icp_b200_context *ctx, uint32_t dim, const double *dst, uint32_t n_dst,
+                           icp_b200_target **out);
+void icp_b200_target_destroy(icp_b200_target *target);
+
+/* estimate() of every `src` scan against the one shared target; HOST pointers
+ * (batch->dst / dst_off are ignored). */
+int icp_b200_target_estimate_batch(icp_b200_target *target, const icp_b200_batch *batch);
+int icp_b200_target_estimate_batch_device(icp_b200_target *target, const icp_b200_batch *batch,
+                                          void *stream, int synchronize);
+
+/* The correspondence search alone: KdTree::search(&q).0 for q in queries
+ * (src/lib.rs:121,164).  out_index[i] = index into the target's `dst`. */
+int icp_b200_target_search(icp_b200_target *target, const double *queries, uint64_t n_queries,
+                           int32_t *out_index);
+int icp_b200_target_search_device(icp_b200_target *target, const double *queries, uint64_t n_queries,
+                                  int32_t *out_index, void *stream, int synchronize);
+
+/* calc_stddevs over ragged residual sets (src/stats.rs:49-60): out_sigma[b*2 + axis].
+ * HOST pointers; residuals are AoS (x y).  Exposes the device selection for parity tests. */
+int icp_b200_calc_stddevs_batch(icp_b200_context *ctx, const double *residuals_xy,
+                                const uint32_t *off, uint32_t batch, double *out_sigma,
+                                double *out_median);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICP_B200_H */

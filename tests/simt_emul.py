@@ -1,0 +1,66 @@
+"""ctypes binding of the lock-step CTA emulator build of the kernel headers
+(tests/simt/_build/libicp_simt.so).  CPU-only TEST INFRASTRUCTURE; see tests/simt/cpu_simt.h."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt")
+_SO = os.path.join(_HERE, "_build", "libicp_simt.so")
+_lib = None
+_dp = C.POINTER(C.c_double)
+_u32p = C.POINTER(C.c_uint32)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+        _lib = C.CDLL(_SO)
+    return _lib
+
+
+def set_schedule(mode):
+    lib().simt_set_schedule(C.c_int(mode))
+
+
+def calc_stddevs(sets, mode=0, threads=128):
+    """sets: list of (n,2) arrays -> (sigma (B,2), median (B,2)); sigma < 0 means None"""
+    off = np.zeros(len(sets) + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(s) for s in sets])
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.float64).reshape(-1, 2) for s in sets]
+                                               + [np.zeros((1, 2))]))
+    sig = np.zeros((len(sets), 2))
+    med = np.zeros((len(sets), 2))
+    lib().simt_calc_stddevs(flat.ctypes.data_as(_dp), off.ctypes.data_as(_u32p), C.c_uint32(len(sets)),
+                            C.c_int(mode), C.c_int(threads), sig.ctypes.data_as(_dp), med.ctypes.data_as(_dp))
+    return sig, med
+
+
+def icp_fused(srcs, dsts, init_T, max_iter=20, variant=0, grid=1, corr_mode=2, cell_budget=4096):
+    """srcs/dsts: lists of (n,dim) arrays.  Returns dict like oracle.icp_estimate_batch."""
+    B = len(srcs)
+    dim = srcs[0].shape[1]
+    so = np.zeros(B + 1, dtype=np.uint32)
+    do = np.zeros(B + 1, dtype=np.uint32)
+    so[1:] = np.cumsum([len(s) for s in srcs])
+    do[1:] = np.cumsum([len(d) for d in dsts])
+    pad = np.zeros((1, dim))
+    src = np.ascontiguousarray(np.concatenate(list(srcs) + [pad]), dtype=np.float64)
+    dst = np.ascontiguousarray(np.concatenate(list(dsts) + [pad]), dtype=np.float64)
+    T0 = np.ascontiguousarray(np.asarray(init_T, dtype=np.float64).reshape(B, 6))
+    out_T = np.zeros((B, 6))
+    inner = np.zeros((B, max(max_iter, 1)), dtype=np.uint32)
+    ncorr = int(so[-1]) * (max_iter if corr_mode == 2 else 1)
+    corr = np.full(max(ncorr, 1), -1, dtype=np.int32)
+    hashes = np.zeros(B, dtype=np.uint64)
+    status = np.zeros(B, dtype=np.int32)
+    err = lib().simt_icp_fused(
+        C.c_int(dim), C.c_int(variant), C.c_uint(grid), src.ctypes.data_as(_dp), so.ctypes.data_as(_u32p),
+        dst.ctypes.data_as(_dp), do.ctypes.data_as(_u32p), T0.ctypes.data_as(_dp), C.c_uint32(B),
+        C.c_uint32(max_iter), C.c_int(corr_mode), C.c_int(cell_budget), out_T.ctypes.data_as(_dp),
+        inner.ctypes.data_as(_u32p), corr.ctypes.data_as(C.POINTER(C.c_int32)),
+        hashes.ctypes.data_as(C.POINTER(C.c_uint64)), status.ctypes.data_as(C.POINTER(C.c_int32)))
+    return {"T": out_T, "inner": inner[:, :max_iter], "corr": corr, "corr_hash": hashes, "status": status,
+            "err": err, "src_off": so}
