@@ -1,0 +1,706 @@
+// icp_b200.cu — host side of libicp_b200.so: the C ABI of include/icp_b200.h over the sm_100a
+// kernels in this directory.  No CPU compute path exists here: every entry point either launches
+// CUDA kernels or returns an error.
+#include "../../include/icp_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "icp_fused.cuh"
+#include "icp_stats_kernel.cuh"
+#include "icp_target.cuh"
+
+using namespace icp;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+typedef void (*FusedKernel)(FusedParams);
+
+struct Instance {
+    int threads, ppt, minb;
+    FusedKernel k[2][2];  // [dim-2][shared target]
+};
+
+#define ICP_INST(T, P, M)                                                                         \
+    {                                                                                             \
+        T, P, M,                                                                                  \
+        {                                                                                         \
+            {icp_fused_kernel<T, P, 2, false, M>, icp_fused_kernel<T, P, 2, true, M>},            \
+            {icp_fused_kernel<T, P, 3, false, M>, icp_fused_kernel<T, P, 3, true, M>}             \
+        }                                                                                         \
+    }
+
+// capacities (source points per scan): 128, 384, 768, 1152, 2048, 3072
+const Instance kInstances[] = {ICP_INST(64, 2, 8),  ICP_INST(128, 3, 4), ICP_INST(128, 6, 4),
+                               ICP_INST(128, 9, 3), ICP_INST(256, 8, 1), ICP_INST(384, 8, 1)};
+constexpr int kNumInstances = (int)(sizeof(kInstances) / sizeof(kInstances[0]));
+constexpr int kMaxChunks = 64;
+
+int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+struct icp_b200_context {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev[kMaxChunks][2];
+    cudaEvent_t ev_ready = nullptr;
+    bool events_ok = false;
+    DevBuf src, dst, src_off, dst_off, init_T, out_T, out_inner, out_corr, out_hash, out_status;
+    DevBuf counters;       // kMaxChunks work counters + 1 error word
+    DevBuf workspace[2];
+    DevBuf stats_in, stats_off, stats_out;
+    icp_b200_call_info info{};
+    std::string last_error;
+    int cell_budget = 4096;
+    int force_instance = -1;
+};
+
+struct icp_b200_target {
+    icp_b200_context* ctx = nullptr;
+    uint32_t dim = 2;
+    uint32_t m = 0;
+    GridGeom g{};
+    DevBuf pts, x, y, z, idx, cstart, cnt, slot, keys;
+    DevBuf queries, out_idx;
+};
+
+namespace {
+
+int fail(icp_b200_context* ctx, int status, const char* what, cudaError_t e = cudaSuccess)
+{
+    if (ctx) {
+        ctx->last_error = what ? what : "";
+        if (e != cudaSuccess) {
+            ctx->last_error += ": ";
+            ctx->last_error += cudaGetErrorString(e);
+        }
+    }
+    return status;
+}
+
+#define ICP_CUDA(ctx, call)                                                        \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) {                                                  \
+            cudaGetLastError();                                                    \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? ICP_B200_ERR_OUT_OF_MEMORY \
+                                                              : ICP_B200_ERR_CUDA, \
+                        #call, e__);                                               \
+        }                                                                          \
+    } while (0)
+
+int pair_status_to_error(int st)
+{
+    switch (st) {
+        case kPairOk: return ICP_B200_OK;
+        case kPairEmptyTarget: return ICP_B200_ERR_EMPTY_TARGET;
+        case kPairTooLarge: return ICP_B200_ERR_TOO_LARGE;
+        case kPairNonFinite: return ICP_B200_ERR_NON_FINITE;
+        default: return ICP_B200_ERR_CUDA;
+    }
+}
+
+struct LaunchPlan {
+    const Instance* inst = nullptr;
+    FusedLayout layout{};
+    int mcap = 0;
+    int grid = 0;
+    FusedKernel kernel = nullptr;
+};
+
+// Chooses the kernel instance for the largest scan of the batch and sizes its launch.
+int plan_launch(icp_b200_context* ctx, uint32_t dim, bool shared_target, uint32_t max_n, uint32_t max_m,
+                uint32_t pairs, LaunchPlan* plan)
+{
+    const Instance* inst = nullptr;
+    if (ctx->force_instance >= 0 && ctx->force_instance < kNumInstances &&
+        (uint32_t)(kInstances[ctx->force_instance].threads * kInstances[ctx->force_instance].ppt) >= max_n)
+        inst = &kInstances[ctx->force_instance];
+    for (int i = 0; !inst && i < kNumInstances; ++i)
+        if ((uint32_t)(kInstances[i].threads * kInstances[i].ppt) >= max_n) inst = &kInstances[i];
+    if (!inst) return fail(ctx, ICP_B200_ERR_TOO_LARGE, "source scan larger than the largest fused kernel (3072 points)");
+    if (!shared_target && max_m > 65528u)
+        return fail(ctx, ICP_B200_ERR_TOO_LARGE, "per-pair target larger than 65528 points: use icp_b200_target_create");
+    plan->inst = inst;
+    plan->mcap = (int)((max_m + 7u) & ~7u);
+    plan->layout = fused_layout((int)dim, inst->threads * inst->ppt, plan->mcap, ctx->cell_budget, shared_target);
+    if ((int)plan->layout.total > ctx->max_smem_optin)
+        return fail(ctx, ICP_B200_ERR_TOO_LARGE, "scan pair does not fit the shared memory of one SM: use icp_b200_target_create for large targets");
+    plan->kernel = inst->k[dim - 2][shared_target ? 1 : 0];
+    ICP_CUDA(ctx, cudaFuncSetAttribute(plan->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->layout.total));
+    int occ = 0;
+    ICP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, plan->kernel, inst->threads, plan->layout.total));
+    if (occ < 1) return fail(ctx, ICP_B200_ERR_CUDA, "fused kernel cannot be resident (occupancy 0)");
+    long long g = (long long)occ * ctx->sm_count;
+    plan->grid = (int)std::max<long long>(1, std::min<long long>(g, pairs));
+    return ICP_B200_OK;
+}
+
+uint64_t ws_stride_of(const FusedLayout& L) { return ((uint64_t)L.nn_bytes + 255u) & ~255ull; }
+
+int validate_batch(icp_b200_context* ctx, const icp_b200_batch* b, bool shared_target)
+{
+    if (!ctx || !b) return ICP_B200_ERR_INVALID_ARGUMENT;
+    if (b->dim != 2 && b->dim != 3) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "dim must be 2 or 3");
+    if (b->batch == 0) return ICP_B200_OK;
+    if (!b->src_off || !b->init_T || !b->out_T) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null src_off / init_T / out_T");
+    if (!shared_target && !b->dst_off) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null dst_off");
+    if (b->corr_mode < 0 || b->corr_mode > 2) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "bad corr_mode");
+    if (b->corr_mode != ICP_B200_CORR_NONE && !b->out_corr) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "corr_mode set but out_corr is null");
+    return ICP_B200_OK;
+}
+
+// Device-pointer launch of pairs [begin, end) on `stream`.
+int launch_range(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_target* tgt, const LaunchPlan& plan,
+                 uint32_t begin, uint32_t end, int chunk_slot, int ws_slot, cudaStream_t stream)
+{
+    FusedParams p{};
+    p.src = b.src; p.src_off = b.src_off; p.dst = b.dst; p.dst_off = b.dst_off; p.init_T = b.init_T;
+    p.out_T = b.out_T; p.out_inner = b.out_inner; p.out_corr = b.out_corr; p.out_hash = b.out_corr_hash;
+    p.out_status = b.out_status;
+    p.out_error = ctx->counters.as<int32_t>() + kMaxChunks;
+    p.work_counter = ctx->counters.as<uint32_t>() + chunk_slot;
+    p.workspace = ctx->workspace[ws_slot].as<unsigned char>();
+    p.ws_stride = ws_stride_of(plan.layout);
+    p.pair_begin = begin; p.pair_end = end; p.max_iter = b.max_iter; p.corr_mode = b.corr_mode;
+    p.cell_budget = ctx->cell_budget; p.ncap = plan.inst->threads * plan.inst->ppt; p.mcap = plan.mcap;
+    if (tgt) {
+        p.target.x = tgt->x.as<double>(); p.target.y = tgt->y.as<double>(); p.target.z = tgt->z.as<double>();
+        p.target.idx = tgt->idx.as<uint32_t>(); p.target.cstart = tgt->cstart.as<uint32_t>();
+        p.target.g = tgt->g; p.target.m = tgt->m;
+    }
+    const uint32_t pairs = end - begin;
+    const int grid = (int)std::min<uint32_t>((uint32_t)plan.grid, pairs);
+    plan.kernel<<<grid, plan.inst->threads, plan.layout.total, stream>>>(p);
+    ICP_CUDA(ctx, cudaGetLastError());
+    ctx->info.kernel_launches += 1;
+    ctx->info.grid_ctas = (uint32_t)grid;
+    ctx->info.block_threads = (uint32_t)plan.inst->threads;
+    ctx->info.smem_bytes = plan.layout.total;
+    return ICP_B200_OK;
+}
+
+int ensure_events(icp_b200_context* ctx)
+{
+    if (ctx->events_ok) return ICP_B200_OK;
+    for (int i = 0; i < kMaxChunks; ++i)
+        for (int j = 0; j < 2; ++j) ICP_CUDA(ctx, cudaEventCreate(&ctx->ev[i][j]));
+    ICP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
+    ctx->events_ok = true;
+    return ICP_B200_OK;
+}
+
+int estimate_device_impl(icp_b200_context* ctx, const icp_b200_target* tgt, const icp_b200_batch* b, void* stream_v,
+                         int synchronize)
+{
+    const bool shared = tgt != nullptr;
+    int rc = validate_batch(ctx, b, shared);
+    if (rc != ICP_B200_OK || b->batch == 0) return rc;
+    ICP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream[0];
+    ctx->info = icp_b200_call_info{};
+    rc = ensure_events(ctx);
+    if (rc != ICP_B200_OK) return rc;
+
+    uint32_t max_n = b->max_src_points, max_m = shared ? tgt->m : b->max_dst_points;
+    if (max_n == 0 || (!shared && max_m == 0)) {
+        // sizes unknown: read the offset tables back once (documented in the header)
+        std::vector<uint32_t> off(b->batch + 1);
+        ICP_CUDA(ctx, cudaMemcpyAsync(off.data(), b->src_off, off.size() * 4, cudaMemcpyDeviceToHost, stream));
+        ICP_CUDA(ctx, cudaStreamSynchronize(stream));
+        max_n = 0;
+        for (uint32_t i = 0; i < b->batch; ++i) max_n = std::max(max_n, off[i + 1] - off[i]);
+        if (!shared) {
+            ICP_CUDA(ctx, cudaMemcpyAsync(off.data(), b->dst_off, off.size() * 4, cudaMemcpyDeviceToHost, stream));
+            ICP_CUDA(ctx, cudaStreamSynchronize(stream));
+            max_m = 0;
+            for (uint32_t i = 0; i < b->batch; ++i) max_m = std::max(max_m, off[i + 1] - off[i]);
+        }
+        ctx->info.d2h_bytes += (uint64_t)off.size() * 4 * (shared ? 1 : 2);
+    }
+    LaunchPlan plan;
+    rc = plan_launch(ctx, b->dim, shared, max_n, max_m, b->batch, &plan);
+    if (rc != ICP_B200_OK) return rc;
+    ICP_CUDA(ctx, ctx->counters.ensure((kMaxChunks + 1) * 4));
+    ICP_CUDA(ctx, ctx->workspace[0].ensure((size_t)plan.grid * ws_stride_of(plan.layout) + 256));
+    ICP_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, (kMaxChunks + 1) * 4, stream));
+    ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], stream));
+    rc = launch_range(ctx, *b, tgt, plan, 0, b->batch, 0, 0, stream);
+    if (rc != ICP_B200_OK) return rc;
+    ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][1], stream));
+    if (synchronize) {
+        int32_t err = 0;
+        ICP_CUDA(ctx, cudaMemcpyAsync(&err, ctx->counters.as<int32_t>() + kMaxChunks, 4, cudaMemcpyDeviceToHost, stream));
+        ICP_CUDA(ctx, cudaStreamSynchronize(stream));
+        ICP_CUDA(ctx, cudaEventElapsedTime(&ctx->info.kernel_ms, ctx->ev[0][0], ctx->ev[0][1]));
+        if (err != 0) return fail(ctx, pair_status_to_error(err), "at least one scan pair was rejected (see out_status)");
+    }
+    return ICP_B200_OK;
+}
+
+// Host-pointer path: chunked H2D -> kernel -> D2H pipeline over two streams.
+int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b200_batch* hb)
+{
+    const bool shared = tgt != nullptr;
+    int rc = validate_batch(ctx, hb, shared);
+    if (rc != ICP_B200_OK || hb->batch == 0) return rc;
+    ICP_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->info = icp_b200_call_info{};
+    rc = ensure_events(ctx);
+    if (rc != ICP_B200_OK) return rc;
+    const uint32_t B = hb->batch, dim = hb->dim;
+    const uint32_t* so = hb->src_off;
+    const uint32_t* doff = hb->dst_off;
+    uint32_t max_n = 0, max_m = shared ? tgt->m : 0;
+    for (uint32_t i = 0; i < B; ++i) {
+        if (so[i + 1] < so[i]) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "src_off not monotone");
+        max_n = std::max(max_n, so[i + 1] - so[i]);
+        if (!shared) {
+            if (doff[i + 1] < doff[i]) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "dst_off not monotone");
+            max_m = std::max(max_m, doff[i + 1] - doff[i]);
+        }
+    }
+    const uint64_t nsrc = so[B], ndst = shared ? 0 : doff[B];
+    if ((nsrc && !hb->src) || (ndst && !hb->dst)) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null point array");
+    LaunchPlan plan;
+    rc = plan_launch(ctx, dim, shared, max_n, max_m, B, &plan);
+    if (rc != ICP_B200_OK) return rc;
+
+    const uint64_t ncorr = hb->corr_mode == ICP_B200_CORR_ALL ? nsrc * hb->max_iter
+                         : hb->corr_mode == ICP_B200_CORR_LAST ? nsrc : 0;
+    ICP_CUDA(ctx, ctx->src.ensure(std::max<uint64_t>(nsrc, 1) * dim * 8));
+    ICP_CUDA(ctx, ctx->dst.ensure(std::max<uint64_t>(ndst, 1) * dim * 8));
+    ICP_CUDA(ctx, ctx->src_off.ensure((B + 1) * 4));
+    ICP_CUDA(ctx, ctx->dst_off.ensure((B + 1) * 4));
+    ICP_CUDA(ctx, ctx->init_T.ensure((size_t)B * 48));
+    ICP_CUDA(ctx, ctx->out_T.ensure((size_t)B * 48));
+    if (hb->out_inner) ICP_CUDA(ctx, ctx->out_inner.ensure(std::max<size_t>((size_t)B * hb->max_iter, 1) * 4));
+    if (ncorr) ICP_CUDA(ctx, ctx->out_corr.ensure(ncorr * 4));
+    if (hb->out_corr_hash) ICP_CUDA(ctx, ctx->out_hash.ensure((size_t)B * 8));
+    if (hb->out_status) ICP_CUDA(ctx, ctx->out_status.ensure((size_t)B * 4));
+    ICP_CUDA(ctx, ctx->counters.ensure((kMaxChunks + 1) * 4));
+    const uint64_t wss = ws_stride_of(plan.layout);
+    for (int s = 0; s < 2; ++s) ICP_CUDA(ctx, ctx->workspace[s].ensure((size_t)plan.grid * wss + 256));
+
+    icp_b200_batch db = *hb;
+    db.src = ctx->src.as<double>(); db.dst = ctx->dst.as<double>();
+    db.src_off = ctx->src_off.as<uint32_t>(); db.dst_off = ctx->dst_off.as<uint32_t>();
+    db.init_T = ctx->init_T.as<double>(); db.out_T = ctx->out_T.as<double>();
+    db.out_inner = hb->out_inner ? ctx->out_inner.as<uint32_t>() : nullptr;
+    db.out_corr = ncorr ? ctx->out_corr.as<int32_t>() : nullptr;
+    db.out_corr_hash = hb->out_corr_hash ? ctx->out_hash.as<uint64_t>() : nullptr;
+    db.out_status = hb->out_status ? ctx->out_status.as<int32_t>() : nullptr;
+
+    // chunking: enough chunks to overlap copies with compute, each at least one full wave
+    int nchunks = (int)std::min<uint32_t>(kMaxChunks, std::max<uint32_t>(1, B / std::max<uint32_t>(1, (uint32_t)plan.grid * 2)));
+    nchunks = std::min(nchunks, env_int("ICP_B200_CHUNKS", 8));
+    nchunks = std::max(nchunks, 1);
+    const uint32_t per = (B + (uint32_t)nchunks - 1) / (uint32_t)nchunks;
+
+    cudaStream_t s0 = ctx->stream[0], s1 = ctx->stream[1];
+    ICP_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, (kMaxChunks + 1) * 4, s0));
+    ICP_CUDA(ctx, cudaMemcpyAsync(ctx->src_off.p, so, (B + 1) * 4, cudaMemcpyHostToDevice, s0));
+    if (!shared) ICP_CUDA(ctx, cudaMemcpyAsync(ctx->dst_off.p, doff, (B + 1) * 4, cudaMemcpyHostToDevice, s0));
+    ICP_CUDA(ctx, cudaMemcpyAsync(ctx->init_T.p, hb->init_T, (size_t)B * 48, cudaMemcpyHostToDevice, s0));
+    ICP_CUDA(ctx, cudaEventRecord(ctx->ev_ready, s0));
+    ICP_CUDA(ctx, cudaStreamWaitEvent(s1, ctx->ev_ready, 0));
+    ctx->info.h2d_bytes += (uint64_t)(B + 1) * 4 * (shared ? 1 : 2) + (uint64_t)B * 48;
+
+    int used = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const uint32_t b0 = (uint32_t)c * per, b1 = std::min<uint32_t>(B, b0 + per);
+        if (b0 >= b1) break;
+        cudaStream_t st = (c & 1) ? s1 : s0;
+        const uint64_t sp0 = so[b0], sp1 = so[b1];
+        if (sp1 > sp0)
+            ICP_CUDA(ctx, cudaMemcpyAsync(ctx->src.as<double>() + sp0 * dim, hb->src + sp0 * dim, (sp1 - sp0) * dim * 8, cudaMemcpyHostToDevice, st));
+        ctx->info.h2d_bytes += (sp1 - sp0) * dim * 8;
+        if (!shared) {
+            const uint64_t dp0 = doff[b0], dp1 = doff[b1];
+            if (dp1 > dp0)
+                ICP_CUDA(ctx, cudaMemcpyAsync(ctx->dst.as<double>() + dp0 * dim, hb->dst + dp0 * dim, (dp1 - dp0) * dim * 8, cudaMemcpyHostToDevice, st));
+            ctx->info.h2d_bytes += (dp1 - dp0) * dim * 8;
+        }
+        ICP_CUDA(ctx, cudaEventRecord(ctx->ev[c][0], st));
+        rc = launch_range(ctx, db, tgt, plan, b0, b1, c, c & 1, st);
+        if (rc != ICP_B200_OK) return rc;
+        ICP_CUDA(ctx, cudaEventRecord(ctx->ev[c][1], st));
+        ICP_CUDA(ctx, cudaMemcpyAsync(hb->out_T + (size_t)b0 * 6, ctx->out_T.as<double>() + (size_t)b0 * 6, (size_t)(b1 - b0) * 48, cudaMemcpyDeviceToHost, st));
+        ctx->info.d2h_bytes += (uint64_t)(b1 - b0) * 48;
+        if (hb->out_inner && hb->max_iter) {
+            ICP_CUDA(ctx, cudaMemcpyAsync(hb->out_inner + (size_t)b0 * hb->max_iter, ctx->out_inner.as<uint32_t>() + (size_t)b0 * hb->max_iter,
+                                          (size_t)(b1 - b0) * hb->max_iter * 4, cudaMemcpyDeviceToHost, st));
+            ctx->info.d2h_bytes += (uint64_t)(b1 - b0) * hb->max_iter * 4;
+        }
+        if (hb->out_corr_hash) {
+            ICP_CUDA(ctx, cudaMemcpyAsync(hb->out_corr_hash + b0, ctx->out_hash.as<uint64_t>() + b0, (size_t)(b1 - b0) * 8, cudaMemcpyDeviceToHost, st));
+            ctx->info.d2h_bytes += (uint64_t)(b1 - b0) * 8;
+        }
+        if (hb->out_status) {
+            ICP_CUDA(ctx, cudaMemcpyAsync(hb->out_status + b0, ctx->out_status.as<int32_t>() + b0, (size_t)(b1 - b0) * 4, cudaMemcpyDeviceToHost, st));
+            ctx->info.d2h_bytes += (uint64_t)(b1 - b0) * 4;
+        }
+        if (ncorr) {
+            const uint64_t mul = hb->corr_mode == ICP_B200_CORR_ALL ? hb->max_iter : 1;
+            if (sp1 > sp0)
+                ICP_CUDA(ctx, cudaMemcpyAsync(hb->out_corr + sp0 * mul, ctx->out_corr.as<int32_t>() + sp0 * mul, (sp1 - sp0) * mul * 4, cudaMemcpyDeviceToHost, st));
+            ctx->info.d2h_bytes += (sp1 - sp0) * mul * 4;
+        }
+        used = c + 1;
+    }
+    int32_t err = 0;
+    ICP_CUDA(ctx, cudaStreamSynchronize(s1));
+    ICP_CUDA(ctx, cudaMemcpyAsync(&err, ctx->counters.as<int32_t>() + kMaxChunks, 4, cudaMemcpyDeviceToHost, s0));
+    ICP_CUDA(ctx, cudaStreamSynchronize(s0));
+    float total = 0.f;
+    for (int c = 0; c < used; ++c) {
+        float ms = 0.f;
+        ICP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[c][0], ctx->ev[c][1]));
+        total += ms;
+    }
+    ctx->info.kernel_ms = total;
+    if (err != 0) return fail(ctx, pair_status_to_error(err), "at least one scan pair was rejected (see out_status)");
+    return ICP_B200_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int icp_b200_abi_version(void) { return ICP_B200_ABI_VERSION; }
+
+const char* icp_b200_status_string(int status)
+{
+    switch (status) {
+        case ICP_B200_OK: return "ok";
+        case ICP_B200_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case ICP_B200_ERR_CUDA: return "CUDA error";
+        case ICP_B200_ERR_NO_DEVICE: return "no CUDA device";
+        case ICP_B200_ERR_EMPTY_TARGET: return "empty target point set";
+        case ICP_B200_ERR_NON_FINITE: return "non-finite input";
+        case ICP_B200_ERR_TOO_LARGE: return "scan too large for this build";
+        case ICP_B200_ERR_OUT_OF_MEMORY: return "out of device memory";
+        default: return "unknown status";
+    }
+}
+
+int icp_b200_device_count(int* count)
+{
+    if (!count) return ICP_B200_ERR_INVALID_ARGUMENT;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return ICP_B200_ERR_NO_DEVICE;
+    }
+    *count = n;
+    return ICP_B200_OK;
+}
+
+int icp_b200_create(int device, icp_b200_context** out)
+{
+    if (!out) return ICP_B200_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return ICP_B200_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) return ICP_B200_ERR_INVALID_ARGUMENT;
+    icp_b200_context* ctx = new (std::nothrow) icp_b200_context();
+    if (!ctx) return ICP_B200_ERR_OUT_OF_MEMORY;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream[0], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream[1], cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return ICP_B200_ERR_CUDA;
+    }
+    ctx->cell_budget = std::max(16, std::min(65000, env_int("ICP_B200_CELL_BUDGET", 4096)));
+    ctx->force_instance = env_int("ICP_B200_FORCE_INSTANCE", -1);
+    *out = ctx;
+    return ICP_B200_OK;
+}
+
+void icp_b200_destroy(icp_b200_context* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&ctx->src, &ctx->dst, &ctx->src_off, &ctx->dst_off, &ctx->init_T, &ctx->out_T, &ctx->out_inner,
+                      &ctx->out_corr, &ctx->out_hash, &ctx->out_status, &ctx->counters, &ctx->workspace[0],
+                      &ctx->workspace[1], &ctx->stats_in, &ctx->stats_off, &ctx->stats_out};
+    for (DevBuf* b : bufs) b->release();
+    if (ctx->events_ok) {
+        for (int i = 0; i < kMaxChunks; ++i)
+            for (int j = 0; j < 2; ++j) cudaEventDestroy(ctx->ev[i][j]);
+        cudaEventDestroy(ctx->ev_ready);
+    }
+    for (int s = 0; s < 2; ++s)
+        if (ctx->stream[s]) cudaStreamDestroy(ctx->stream[s]);
+    delete ctx;
+}
+
+int icp_b200_last_call_info(const icp_b200_context* ctx, icp_b200_call_info* info)
+{
+    if (!ctx || !info) return ICP_B200_ERR_INVALID_ARGUMENT;
+    *info = ctx->info;
+    return ICP_B200_OK;
+}
+
+const char* icp_b200_last_error(const icp_b200_context* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int icp_b200_estimate_batch(icp_b200_context* ctx, const icp_b200_batch* batch) { return estimate_host_impl(ctx, nullptr, batch); }
+
+int icp_b200_estimate_batch_device(icp_b200_context* ctx, const icp_b200_batch* batch, void* stream, int synchronize)
+{
+    return estimate_device_impl(ctx, nullptr, batch, stream, synchronize);
+}
+
+static int single_pair(icp_b200_context* ctx, uint32_t dim, const double* dst, uint32_t m, const double* src, uint32_t n,
+                       const double* T0, uint32_t max_iter, double* out)
+{
+    if (!ctx || !T0 || !out) return ICP_B200_ERR_INVALID_ARGUMENT;
+    const uint32_t so[2] = {0, n}, dof[2] = {0, m};
+    icp_b200_batch b{};
+    b.dim = dim; b.batch = 1; b.max_iter = max_iter; b.corr_mode = ICP_B200_CORR_NONE;
+    b.src = src; b.src_off = so; b.dst = dst; b.dst_off = dof; b.init_T = T0; b.out_T = out;
+    return estimate_host_impl(ctx, nullptr, &b);
+}
+
+int icp_b200_icp2d_estimate(icp_b200_context* ctx, const double* dst_xy, uint32_t n_dst, const double* src_xy,
+                            uint32_t n_src, const double initial_transform[6], uint32_t max_iter, double out_transform[6])
+{
+    return single_pair(ctx, 2, dst_xy, n_dst, src_xy, n_src, initial_transform, max_iter, out_transform);
+}
+
+int icp_b200_icp3d_estimate(icp_b200_context* ctx, const double* dst_xyz, uint32_t n_dst, const double* src_xyz,
+                            uint32_t n_src, const double initial_transform[6], uint32_t max_iter, double out_transform[6])
+{
+    return single_pair(ctx, 3, dst_xyz, n_dst, src_xyz, n_src, initial_transform, max_iter, out_transform);
+}
+
+// ---------------------------------------------------------------------------------------------
+int icp_b200_target_create(icp_b200_context* ctx, uint32_t dim, const double* dst, uint32_t m, icp_b200_target** out)
+{
+    if (!ctx || !out) return ICP_B200_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (dim != 2 && dim != 3) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "dim must be 2 or 3");
+    if (m && !dst) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null dst");
+    ICP_CUDA(ctx, cudaSetDevice(ctx->device));
+    icp_b200_target* t = new (std::nothrow) icp_b200_target();
+    if (!t) return ICP_B200_ERR_OUT_OF_MEMORY;
+    t->ctx = ctx; t->dim = dim; t->m = m;
+    ctx->info = icp_b200_call_info{};
+    cudaStream_t st = ctx->stream[0];
+    auto bail = [&](int rc) { icp_b200_target_destroy(t); return rc; };
+#define ICP_T(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cudaGetLastError(); return bail(fail(ctx, ICP_B200_ERR_CUDA, #call, e__)); } } while (0)
+    if (m == 0) {  // an empty target is representable; estimating against it reports EMPTY_TARGET
+        t->g = grid_make_geom(0, 0, 0, 0, 0, 0, (int)dim, 1);
+        ICP_T(t->cstart.ensure(8));
+        ICP_T(cudaMemsetAsync(t->cstart.p, 0, 8, st));
+        ICP_T(cudaStreamSynchronize(st));
+        *out = t;
+        return ICP_B200_OK;
+    }
+    for (uint64_t q = 0; q < (uint64_t)m * dim; ++q)
+        if (!(std::fabs(dst[q]) <= kF64Max)) return bail(fail(ctx, ICP_B200_ERR_NON_FINITE, "target holds NaN/Inf"));
+    ICP_T(t->pts.ensure((size_t)m * dim * 8));
+    ICP_T(t->x.ensure((size_t)m * 8));
+    ICP_T(t->y.ensure((size_t)m * 8));
+    if (dim == 3) ICP_T(t->z.ensure((size_t)m * 8));
+    ICP_T(t->idx.ensure((size_t)m * 4));
+    ICP_T(t->slot.ensure((size_t)m * 4));
+    ICP_T(t->keys.ensure(48));
+    ICP_T(cudaMemcpyAsync(t->pts.p, dst, (size_t)m * dim * 8, cudaMemcpyHostToDevice, st));
+    ctx->info.h2d_bytes += (uint64_t)m * dim * 8;
+    unsigned long long keys[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};
+    ICP_T(cudaMemcpyAsync(t->keys.p, keys, 48, cudaMemcpyHostToDevice, st));
+    TargetBuild tb{};
+    tb.pts = t->pts.as<double>(); tb.m = m; tb.bbox_keys = t->keys.as<unsigned long long>();
+    const int blocks = (int)std::min<uint32_t>((m + 255) / 256, (uint32_t)ctx->sm_count * 8);
+    if (dim == 2) target_bbox_kernel<2><<<blocks, 256, 0, st>>>(tb); else target_bbox_kernel<3><<<blocks, 256, 0, st>>>(tb);
+    ICP_T(cudaGetLastError());
+    ICP_T(cudaMemcpyAsync(keys, t->keys.p, 48, cudaMemcpyDeviceToHost, st));
+    ICP_T(cudaStreamSynchronize(st));
+    auto unkey = [](unsigned long long k) {
+        unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+        double d; std::memcpy(&d, &b, 8); return d;
+    };
+    // cell budget: about two cells per point, bounded (cell table stays L2-resident)
+    long long budget = std::max<long long>(64, std::min<long long>((long long)m * env_int("ICP_B200_TARGET_CELLS_PER_POINT", 2), 1ll << 24));
+    t->g = grid_make_geom(unkey(keys[0]), unkey(keys[1]), unkey(keys[2]), unkey(keys[3]), unkey(keys[4]), unkey(keys[5]), (int)dim, (int)budget);
+    const uint32_t ncells = (uint32_t)(t->g.gx * t->g.gy * t->g.gz);
+    ICP_T(t->cnt.ensure((size_t)ncells * 4));
+    ICP_T(t->cstart.ensure((size_t)(ncells + 1) * 4));
+    ICP_T(cudaMemsetAsync(t->cnt.p, 0, (size_t)ncells * 4, st));
+    tb.g = t->g; tb.cnt = t->cnt.as<uint32_t>(); tb.slot = t->slot.as<uint32_t>(); tb.cstart = t->cstart.as<uint32_t>();
+    tb.x = t->x.as<double>(); tb.y = t->y.as<double>(); tb.z = t->z.as<double>(); tb.idx = t->idx.as<uint32_t>();
+    if (dim == 2) target_count_kernel<2><<<blocks, 256, 0, st>>>(tb); else target_count_kernel<3><<<blocks, 256, 0, st>>>(tb);
+    target_scan_kernel<<<1, 1024, 0, st>>>(tb, ncells);
+    if (dim == 2) target_scatter_kernel<2><<<blocks, 256, 0, st>>>(tb); else target_scatter_kernel<3><<<blocks, 256, 0, st>>>(tb);
+    ICP_T(cudaGetLastError());
+    ICP_T(cudaStreamSynchronize(st));
+    ctx->info.kernel_launches = 4;
+#undef ICP_T
+    *out = t;
+    return ICP_B200_OK;
+}
+
+void icp_b200_target_destroy(icp_b200_target* t)
+{
+    if (!t) return;
+    if (t->ctx) cudaSetDevice(t->ctx->device);
+    DevBuf* bufs[] = {&t->pts, &t->x, &t->y, &t->z, &t->idx, &t->cstart, &t->cnt, &t->slot, &t->keys, &t->queries, &t->out_idx};
+    for (DevBuf* b : bufs) b->release();
+    delete t;
+}
+
+int icp_b200_target_estimate_batch(icp_b200_target* t, const icp_b200_batch* batch)
+{
+    if (!t) return ICP_B200_ERR_INVALID_ARGUMENT;
+    if (batch && batch->dim != t->dim) return fail(t->ctx, ICP_B200_ERR_INVALID_ARGUMENT, "batch dim differs from target dim");
+    return estimate_host_impl(t->ctx, t, batch);
+}
+
+int icp_b200_target_estimate_batch_device(icp_b200_target* t, const icp_b200_batch* batch, void* stream, int synchronize)
+{
+    if (!t) return ICP_B200_ERR_INVALID_ARGUMENT;
+    if (batch && batch->dim != t->dim) return fail(t->ctx, ICP_B200_ERR_INVALID_ARGUMENT, "batch dim differs from target dim");
+    return estimate_device_impl(t->ctx, t, batch, stream, synchronize);
+}
+
+int icp_b200_target_search_device(icp_b200_target* t, const double* queries, uint64_t nq, int32_t* out_index, void* stream_v,
+                                  int synchronize)
+{
+    if (!t) return ICP_B200_ERR_INVALID_ARGUMENT;
+    icp_b200_context* ctx = t->ctx;
+    if (nq == 0) return ICP_B200_OK;
+    if (!queries || !out_index) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null queries / out_index");
+    if (t->m == 0) return fail(ctx, ICP_B200_ERR_EMPTY_TARGET, "search on an empty target");
+    ICP_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_events(ctx);
+    if (rc != ICP_B200_OK) return rc;
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : ctx->stream[0];
+    TargetView tv{};
+    tv.x = t->x.as<double>(); tv.y = t->y.as<double>(); tv.z = t->z.as<double>();
+    tv.idx = t->idx.as<uint32_t>(); tv.cstart = t->cstart.as<uint32_t>(); tv.g = t->g; tv.m = t->m;
+    const int threads = 256;
+    const long long want = (long long)((nq + threads - 1) / threads);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)ctx->sm_count * 8));
+    ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], st));
+    if (t->dim == 2) nn_search_kernel<2><<<grid, threads, 0, st>>>(tv, queries, nq, out_index);
+    else nn_search_kernel<3><<<grid, threads, 0, st>>>(tv, queries, nq, out_index);
+    ICP_CUDA(ctx, cudaGetLastError());
+    ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][1], st));
+    ctx->info.kernel_launches += 1;
+    ctx->info.grid_ctas = (uint32_t)grid; ctx->info.block_threads = threads; ctx->info.smem_bytes = 0;
+    if (synchronize) {
+        ICP_CUDA(ctx, cudaStreamSynchronize(st));
+        ICP_CUDA(ctx, cudaEventElapsedTime(&ctx->info.kernel_ms, ctx->ev[0][0], ctx->ev[0][1]));
+    }
+    return ICP_B200_OK;
+}
+
+int icp_b200_target_search(icp_b200_target* t, const double* queries, uint64_t nq, int32_t* out_index)
+{
+    if (!t) return ICP_B200_ERR_INVALID_ARGUMENT;
+    icp_b200_context* ctx = t->ctx;
+    if (nq == 0) return ICP_B200_OK;
+    if (!queries || !out_index) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null queries / out_index");
+    ICP_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->info = icp_b200_call_info{};
+    ICP_CUDA(ctx, t->queries.ensure(nq * t->dim * 8));
+    ICP_CUDA(ctx, t->out_idx.ensure(nq * 4));
+    cudaStream_t st = ctx->stream[0];
+    ICP_CUDA(ctx, cudaMemcpyAsync(t->queries.p, queries, nq * t->dim * 8, cudaMemcpyHostToDevice, st));
+    int rc = icp_b200_target_search_device(t, t->queries.as<double>(), nq, t->out_idx.as<int32_t>(), st, 0);
+    if (rc != ICP_B200_OK) return rc;
+    ICP_CUDA(ctx, cudaMemcpyAsync(out_index, t->out_idx.p, nq * 4, cudaMemcpyDeviceToHost, st));
+    ICP_CUDA(ctx, cudaStreamSynchronize(st));
+    ICP_CUDA(ctx, cudaEventElapsedTime(&ctx->info.kernel_ms, ctx->ev[0][0], ctx->ev[0][1]));
+    ctx->info.h2d_bytes = nq * t->dim * 8;
+    ctx->info.d2h_bytes = nq * 4;
+    return ICP_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int icp_b200_calc_stddevs_batch(icp_b200_context* ctx, const double* residuals_xy, const uint32_t* off, uint32_t batch,
+                                double* out_sigma, double* out_median)
+{
+    if (!ctx) return ICP_B200_ERR_INVALID_ARGUMENT;
+    if (batch == 0) return ICP_B200_OK;
+    if (!off || !out_sigma) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null off / out_sigma");
+    ICP_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->info = icp_b200_call_info{};
+    int cap = 1;
+    for (uint32_t b = 0; b < batch; ++b) cap = std::max(cap, (int)(off[b + 1] - off[b]));
+    const uint32_t smem = stats_smem_bytes(cap);
+    if ((int)smem > ctx->max_smem_optin) return fail(ctx, ICP_B200_ERR_TOO_LARGE, "residual set does not fit shared memory");
+    const uint64_t total = off[batch];
+    if (total && !residuals_xy) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null residuals");
+    ICP_CUDA(ctx, ctx->stats_in.ensure(std::max<uint64_t>(total, 1) * 16));
+    ICP_CUDA(ctx, ctx->stats_off.ensure((batch + 1) * 4));
+    ICP_CUDA(ctx, ctx->stats_out.ensure((size_t)batch * 32));
+    cudaStream_t st = ctx->stream[0];
+    if (total) ICP_CUDA(ctx, cudaMemcpyAsync(ctx->stats_in.p, residuals_xy, total * 16, cudaMemcpyHostToDevice, st));
+    ICP_CUDA(ctx, cudaMemcpyAsync(ctx->stats_off.p, off, (batch + 1) * 4, cudaMemcpyHostToDevice, st));
+    StatsParams p{};
+    p.residuals = ctx->stats_in.as<double>(); p.off = ctx->stats_off.as<uint32_t>();
+    p.out_sigma = ctx->stats_out.as<double>(); p.out_median = ctx->stats_out.as<double>() + (size_t)batch * 2;
+    p.B = batch; p.cap = cap; p.mode = env_int("ICP_B200_STATS_MODE", 1);
+    ICP_CUDA(ctx, cudaFuncSetAttribute(calc_stddevs_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<uint32_t>(batch, (uint32_t)ctx->sm_count * 4);
+    calc_stddevs_kernel<128><<<grid, 128, smem, st>>>(p);
+    ICP_CUDA(ctx, cudaGetLastError());
+    ICP_CUDA(ctx, cudaMemcpyAsync(out_sigma, p.out_sigma, (size_t)batch * 16, cudaMemcpyDeviceToHost, st));
+    if (out_median) ICP_CUDA(ctx, cudaMemcpyAsync(out_median, p.out_median, (size_t)batch * 16, cudaMemcpyDeviceToHost, st));
+    ICP_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->info.kernel_launches = 1;
+    return ICP_B200_OK;
+}
+
+}  // extern "C"

@@ -69,6 +69,8 @@ typedef struct {
     uint32_t batch;          /* number of scan pairs B */
     uint32_t max_iter;       /* `max_iter` argument of estimate (outer iterations, no early exit) */
     int32_t corr_mode;       /* ICP_B200_CORR_* */
+    uint32_t max_src_points; /* largest src scan of the batch; 0 = let the library find out (the */
+    uint32_t max_dst_points; /* device-pointer entries then read the offset tables back once)    */
     const double *src;       /* `src: &[VectorD]` of every pair, concatenated */
     const uint32_t *src_off; /* [B+1] */
     const double *dst;       /* `dst` given to Icp2d::new / Icp3d::new, concatenated; ignored by
