@@ -190,6 +190,22 @@ class Context:
             rc = self._L.icp_b200_target_estimate_batch_device(target._h, C.byref(b), stream, 1 if synchronize else 0)
         return self._check(rc)
 
+    def estimate_batch_host_ptrs(self, ptrs: dict, B, max_iter, dim=2, corr_mode=CORR_NONE, target=None):
+        """icp_b200_estimate_batch on caller-owned HOST buffers given as addresses (e.g. pinned torch
+        tensors): same keys as estimate_batch_device.  Copies in, computes, copies results back and
+        returns when they have landed."""
+        b = Batch()
+        b.dim, b.batch, b.max_iter, b.corr_mode = dim, B, max_iter, corr_mode
+        for k in ("src", "src_off", "dst", "dst_off", "init_T", "out_T", "out_inner", "out_corr", "out_corr_hash",
+                  "out_status"):
+            v = ptrs.get(k)
+            setattr(b, k, v if v else None)
+        if target is None:
+            rc = self._L.icp_b200_estimate_batch(self._h, C.byref(b))
+        else:
+            rc = self._L.icp_b200_target_estimate_batch(target._h, C.byref(b))
+        return self._check(rc)
+
     # ------------------------------------------------------------------ stats hook
     def calc_stddevs_batch(self, sets):
         """stats::calc_stddevs (stats.rs:49-60) of each (n,2) residual set -> (sigma, median), (B,2) each;
@@ -248,6 +264,11 @@ class Target:
         out = np.zeros(q.shape[0], dtype=np.int32)
         self.ctx._check(self.ctx._L.icp_b200_target_search(self._h, q.ctypes.data, q.shape[0], out.ctypes.data))
         return out
+
+    def search_device(self, queries_ptr: int, n_queries: int, out_index_ptr: int, stream=None, synchronize=True):
+        """Same search on DEVICE buffers (addresses), enqueued on `stream`."""
+        self.ctx._check(self.ctx._L.icp_b200_target_search_device(self._h, queries_ptr, n_queries, out_index_ptr,
+                                                                  stream, 1 if synchronize else 0))
 
     def estimate_batch(self, src, src_off, init_T, max_iter=20, **kw):
         return self.ctx.estimate_batch(src, src_off, None, None, init_T, max_iter, dim=self.dim, target=self, **kw)

@@ -13,7 +13,7 @@
 #include <string>
 #include <vector>
 
-#include "icp_fused.cuh"
+#include "icp_instances.h"
 #include "icp_stats_kernel.cuh"
 #include "icp_target.cuh"
 
@@ -45,25 +45,10 @@ struct DevBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-typedef void (*FusedKernel)(FusedParams);
-
-struct Instance {
-    int threads, ppt, minb;
-    FusedKernel k[2][2];  // [dim-2][shared target]
-};
-
-#define ICP_INST(T, P, M)                                                                         \
-    {                                                                                             \
-        T, P, M,                                                                                  \
-        {                                                                                         \
-            {icp_fused_kernel<T, P, 2, false, M>, icp_fused_kernel<T, P, 2, true, M>},            \
-            {icp_fused_kernel<T, P, 3, false, M>, icp_fused_kernel<T, P, 3, true, M>}             \
-        }                                                                                         \
-    }
-
-// capacities (source points per scan): 128, 384, 768, 1152, 2048, 3072
-const Instance kInstances[] = {ICP_INST(64, 2, 8),  ICP_INST(128, 3, 4), ICP_INST(128, 6, 4),
-                               ICP_INST(128, 9, 3), ICP_INST(256, 8, 1), ICP_INST(384, 8, 1)};
+// kernel instances live in their own translation units (icp_fused_inst.cu, one per capacity) so
+// that they compile in parallel; capacities (source points per scan): 128, 384, 768, 1152, 2048, 3072
+const Instance* const kInstances[] = {&kFusedInstance0, &kFusedInstance1, &kFusedInstance2,
+                                      &kFusedInstance3, &kFusedInstance4, &kFusedInstance5};
 constexpr int kNumInstances = (int)(sizeof(kInstances) / sizeof(kInstances[0]));
 constexpr int kMaxChunks = 64;
 
@@ -152,10 +137,10 @@ int plan_launch(icp_b200_context* ctx, uint32_t dim, bool shared_target, uint32_
 {
     const Instance* inst = nullptr;
     if (ctx->force_instance >= 0 && ctx->force_instance < kNumInstances &&
-        (uint32_t)(kInstances[ctx->force_instance].threads * kInstances[ctx->force_instance].ppt) >= max_n)
-        inst = &kInstances[ctx->force_instance];
+        (uint32_t)(kInstances[ctx->force_instance]->threads * kInstances[ctx->force_instance]->ppt) >= max_n)
+        inst = kInstances[ctx->force_instance];
     for (int i = 0; !inst && i < kNumInstances; ++i)
-        if ((uint32_t)(kInstances[i].threads * kInstances[i].ppt) >= max_n) inst = &kInstances[i];
+        if ((uint32_t)(kInstances[i]->threads * kInstances[i]->ppt) >= max_n) inst = kInstances[i];
     if (!inst) return fail(ctx, ICP_B200_ERR_TOO_LARGE, "source scan larger than the largest fused kernel (3072 points)");
     if (!shared_target && max_m > 65528u)
         return fail(ctx, ICP_B200_ERR_TOO_LARGE, "per-pair target larger than 65528 points: use icp_b200_target_create");

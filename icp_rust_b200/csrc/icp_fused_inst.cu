@@ -1,0 +1,15 @@
+// icp_fused_inst.cu — one capacity of the fused per-pair ICP kernel (icp_fused.cuh), four
+// specialisations: {2-D, 3-D} x {per-pair target in shared memory, shared target in HBM}.
+#include "icp_instances.h"
+
+#define ICP_CAT_(a, b) a##b
+#define ICP_CAT(a, b) ICP_CAT_(a, b)
+
+namespace icp {
+extern const Instance ICP_CAT(kFusedInstance, ICP_INST_ID) = {
+    ICP_INST_THREADS, ICP_INST_PPT, ICP_INST_MINB,
+    {{icp_fused_kernel<ICP_INST_THREADS, ICP_INST_PPT, 2, false, ICP_INST_MINB>,
+      icp_fused_kernel<ICP_INST_THREADS, ICP_INST_PPT, 2, true, ICP_INST_MINB>},
+     {icp_fused_kernel<ICP_INST_THREADS, ICP_INST_PPT, 3, false, ICP_INST_MINB>,
+      icp_fused_kernel<ICP_INST_THREADS, ICP_INST_PPT, 3, true, ICP_INST_MINB>}}};
+}  // namespace icp

@@ -13,7 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #define ICP_DEV __device__ __forceinline__
-#define ICP_DEV_NOINLINE __device__ __noinline__
+#define ICP_DEV_NOINLINE static __device__ __noinline__
 #define ICP_HD __host__ __device__ __forceinline__
 #define ICP_GLOBAL __global__
 #define ICP_SHARED_DYN(name) extern __shared__ __align__(16) unsigned char name[]

@@ -1,0 +1,270 @@
+"""Parity of the sm_100a CUDA path (through the C ABI of include/icp_b200.h) with the CPU oracle.
+Bar: correspondence indices, inner iteration counts / break reasons and transforms BIT-EXACT
+(the north star only asks 1e-9 for transforms; the kernels reproduce the reference's operation
+order, so equality is what is asserted)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from tests import refdata as R
+
+pytestmark = pytest.mark.gpu
+
+I6 = np.array([1., 0., 0., 1., 0., 0.])
+
+
+@pytest.fixture(scope="module")
+def icp():
+    import icp_rust_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def ctx(icp):
+    c = icp.Context(0)
+    yield c
+    c.close()
+
+
+def _cat(arrs, dim):
+    off = np.zeros(len(arrs) + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(a) for a in arrs])
+    flat = np.concatenate([np.asarray(a, dtype=np.float64).reshape(-1, dim) for a in arrs] + [np.zeros((0, dim))])
+    return flat, off
+
+
+def _run(ctx, icp, srcs, dsts, T0s, max_iter, dim=2, **kw):
+    src, so = _cat(srcs, dim)
+    dst, do = _cat(dsts, dim)
+    g = ctx.estimate_batch(src, so, dst, do, np.array(T0s).reshape(-1, 6), max_iter, dim=dim,
+                           corr_mode=icp.CORR_ALL, **kw)
+    g["src_off"] = so
+    return g
+
+
+def _check_vs_oracle(g, srcs, dsts, T0s, max_iter, nn_mode=oracle.NN_KDTREE):
+    so = g["src_off"]
+    for b in range(len(srcs)):
+        o = oracle.icp_estimate(srcs[b], dsts[b], T0s[b], max_iter, nn_mode=nn_mode, corr_mode=oracle.CORR_ALL)
+        n = len(srcs[b])
+        gc = g["corr"][int(so[b]) * max_iter:int(so[b]) * max_iter + n * max_iter].reshape(max_iter, n)
+        assert np.array_equal(gc, o["corr"]), f"pair {b}: correspondence indices differ"
+        assert np.array_equal(g["inner"][b], o["inner"]), f"pair {b}: inner iteration counts differ"
+        assert np.array_equal(g["T"][b], o["T"]), f"pair {b}: transform differs by {np.abs(g['T'][b] - o['T']).max()}"
+        assert int(g["corr_hash"][b]) == int(o["corr_hash"])
+        assert g["status"][b] == 0
+
+
+# ------------------------------------------------------------------------------------------------
+def test_native_library_is_the_cuda_build(icp, ctx):
+    assert os.path.exists(icp._lib.CUDA_SO)
+    assert icp.cuda_lib().icp_b200_abi_version() == 1
+
+
+def test_calc_stddevs_exact(ctx):  # stats.rs:49-60 on the device selection
+    rng = np.random.default_rng(5)
+    sets = [rng.normal(0, 3, (n, 2)) for n in (1, 2, 3, 10, 11, 64, 665, 666, 1080, 1081, 3000)]
+    sets.append(np.zeros((50, 2)))
+    sets.append(np.repeat(rng.normal(0, 1, (5, 2)), 40, axis=0))
+    sets.append(rng.normal(0, 1e-300, (33, 2)))
+    sets.append(rng.normal(0, 1e150, (34, 2)))
+    sets.append(np.array(R.MEASUREMENTS_30))
+    for vals, exp in R.MEDIAN_CASES + R.MAD_CASES:
+        if exp is not None:
+            sets.append(np.stack([vals, vals], axis=1))
+    for mode in ("0", "1"):
+        os.environ["ICP_B200_STATS_MODE"] = mode
+        sig, med = ctx.calc_stddevs_batch(sets)
+        for k, s in enumerate(sets):
+            assert np.array_equal(sig[k], oracle.calc_stddevs(s)), (mode, k)
+            for a in range(2):
+                assert med[k, a] == oracle.median(s[:, a])
+    os.environ.pop("ICP_B200_STATS_MODE")
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_l_shape_reference_test(ctx, icp, dim):  # lib.rs:510-551 / 554-595
+    true_T = oracle.transform_new(R.L_TRUE_PARAM)
+    init = oracle.transform_new(np.array(R.L_TRUE_PARAM) + np.array(R.L_NOISE_PARAM))
+    if dim == 2:
+        src = R.L_SHAPE_2D
+        dst = np.array([oracle.transform_apply(true_T, p) for p in src])
+        est = icp.Icp2d.new(dst, ctx).estimate(src, icp.Transform.from_array(init), 20)
+    else:
+        src = R.L_SHAPE_3D
+        dst = np.array([oracle.transform_xy(true_T, p) for p in src])
+        est = icp.Icp3d.new(dst, ctx).estimate(src, icp.Transform.from_array(init), 20)
+    for p, q in zip(src, dst):
+        assert np.linalg.norm(est.transform(p[:2]) - q[:2]) < 1e-3
+    o = oracle.icp_estimate(src, dst, init, 20)
+    assert np.array_equal(est.to_array(), o["T"])
+    g = _run(ctx, icp, [src], [dst], [init], 20, dim=dim)
+    _check_vs_oracle(g, [src], [dst], [init], 20)
+
+
+def test_bundled_scans_chain(ctx, icp, scans2d):
+    """examples/scan2d.rs:62-88: src = 001 fixed, dst = 002.., warm start, 20 iterations."""
+    src = scans2d[1]
+    T = I6.copy()
+    for k in range(2, 12):
+        g = _run(ctx, icp, [src], [scans2d[k]], [T], 20)
+        _check_vs_oracle(g, [src], [scans2d[k]], [T], 20)
+        T = g["T"][0].copy()
+
+
+def test_bundled_scans_batch_with_origin_duplicates(ctx, icp, scans2d):
+    ids = [2, 3, 50, 99, 100, 150, 209]     # >= 099 hold duplicated (0,0) points: index ties
+    srcs = [scans2d[k - 1] for k in ids]
+    dsts = [scans2d[k] for k in ids]
+    T0 = [I6] * len(ids)
+    g = _run(ctx, icp, srcs, dsts, T0, 20)
+    _check_vs_oracle(g, srcs, dsts, T0, 20)
+    # the tie is real: some query of pair 099 picked an origin duplicate, and it is the lowest index
+    d = scans2d[99]
+    dup = np.flatnonzero((d == 0).all(axis=1))
+    assert len(dup) >= 2
+    so = g["src_off"]
+    c = g["corr"][int(so[3]) * 20:int(so[3]) * 20 + len(srcs[3]) * 20]
+    assert dup[0] in c and not np.isin(dup[1:], c).any()
+
+
+@pytest.mark.parametrize("instance", [3, 4, 5])
+def test_synthetic_pairs_every_large_instance(icp, instance):
+    """config 2 shape (1080 beams, mm units, 3 mm noise, 1 % invalid returns), 20 iterations,
+    on each kernel instance able to hold it."""
+    os.environ["ICP_B200_FORCE_INSTANCE"] = str(instance)
+    try:
+        c = icp.Context(0)
+    finally:
+        os.environ.pop("ICP_B200_FORCE_INSTANCE")
+    B = 24
+    src, dst, off, _ = icp.synth_scan_pairs(B, beams=1080, first_pair=1000 * instance)
+    T0 = np.tile(I6, (B, 1))
+    g = c.estimate_batch(src, off, dst, off, T0, 20, corr_mode=icp.CORR_ALL)
+    assert c.call_info()["block_threads"] * [2, 3, 6, 9, 8, 8][instance] >= 1080
+    g["src_off"] = off
+    srcs = [src[off[b]:off[b + 1]] for b in range(B)]
+    dsts = [dst[off[b]:off[b + 1]] for b in range(B)]
+    _check_vs_oracle(g, srcs, dsts, list(T0), 20)
+    c.close()
+
+
+@pytest.mark.parametrize("beams", [100, 300, 700])
+def test_small_instances(ctx, icp, beams):
+    B = 16
+    src, dst, off, _ = icp.synth_scan_pairs(B, beams=beams, first_pair=77)
+    T0 = np.tile(I6, (B, 1))
+    g = ctx.estimate_batch(src, off, dst, off, T0, 8, corr_mode=icp.CORR_ALL)
+    g["src_off"] = off
+    _check_vs_oracle(g, [src[off[b]:off[b + 1]] for b in range(B)], [dst[off[b]:off[b + 1]] for b in range(B)],
+                     list(T0), 8)
+
+
+def test_ragged_and_degenerate_batch(ctx, icp, scans2d):
+    rng = np.random.default_rng(3)
+    a = rng.normal(0, 100, (40, 2))
+    srcs = [a, a[:1], np.zeros((0, 2)), a, np.zeros((30, 2)), scans2d[1], a[:2], R.ZERO_X_SRC]
+    dsts = [a.copy(), a, a, a[:1], np.zeros((30, 2)), scans2d[0], a[5:9],
+            np.array([oracle.transform_apply(oracle.transform_new([0., 0.01, 0.]), p) for p in R.ZERO_X_SRC])]
+    T0 = [I6] * len(srcs)
+    g = _run(ctx, icp, srcs, dsts, T0, 6)
+    _check_vs_oracle(g, srcs, dsts, T0, 6, nn_mode=oracle.NN_BRUTE)
+    assert np.array_equal(g["T"][0], I6)                      # sigma == 0 -> None -> identity
+    assert (g["reason"][0] == icp.BREAK_NONE).all()
+    assert (g["reason"][2] == icp.BREAK_NONE).all()          # empty source: check_input_size
+
+
+def test_status_codes_instead_of_panics(ctx, icp):
+    rng = np.random.default_rng(4)
+    a = rng.normal(0, 100, (20, 2))
+    bad = a.copy()
+    bad[3, 1] = np.nan
+    srcs = [a, bad, a, a]
+    dsts = [np.zeros((0, 2)), a, a, a + 0.5]
+    T0 = [I6, I6, np.array([1., 0., 0., 1., np.inf, 0.]), I6]
+    g = _run(ctx, icp, srcs, dsts, T0, 2, raise_on_pair_error=False)
+    assert list(g["status"]) == [icp.PAIR_EMPTY_TARGET, icp.PAIR_NON_FINITE, icp.PAIR_NON_FINITE, icp.PAIR_OK]
+    assert g["rc"] == icp.ERR_NON_FINITE
+    for b in range(3):
+        assert np.array_equal(g["T"][b], T0[b], equal_nan=True)
+    with pytest.raises(icp.IcpError):
+        _run(ctx, icp, srcs, dsts, T0, 2)
+    big = rng.normal(0, 100, (3073, 2))
+    with pytest.raises(icp.IcpError) as e:
+        _run(ctx, icp, [big], [big], [I6], 1)
+    assert e.value.status == icp.ERR_TOO_LARGE
+    # max_iter == 0 returns the initial transform (lib.rs:112 runs zero times)
+    g = _run(ctx, icp, [a], [a + 1.0], [oracle.transform_new([1., 2., 0.3])], 0)
+    assert np.array_equal(g["T"][0], oracle.transform_new([1., 2., 0.3]))
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [2, 3])
+def test_target_search_matches_brute_force(ctx, icp, dim):  # KdTree::search, lib.rs:121,164
+    rng = np.random.default_rng(11)
+    m = 20000
+    dst = rng.normal(0, 1000, (m, dim))
+    if dim == 3:
+        dst[:, 2] *= 0.05
+    dst[500:520] = dst[100]           # duplicated points: lowest index must win
+    dst[7000] = dst[6000]
+    q = np.concatenate([rng.normal(0, 1100, (4000, dim)), dst[95:105], dst[6995:7005],
+                        rng.uniform(-1e5, 1e5, (64, dim)), np.zeros((1, dim))])
+    t = icp.Target(dst, ctx)
+    got = t.search(q)
+    exp = oracle.nn_search(dst, q, oracle.NN_BRUTE)
+    assert np.array_equal(got, exp)
+    assert np.array_equal(oracle.nn_search(dst, q, oracle.NN_KDTREE), exp)
+    t.close()
+
+
+def test_target_search_bundled_scan_ties(ctx, icp, scans2d):
+    d = scans2d[120]
+    t = icp.Target(d, ctx)
+    q = np.concatenate([scans2d[119], np.zeros((3, 2)), [[1e-3, -1e-3]]])
+    assert np.array_equal(t.search(q), oracle.nn_search(d, q, oracle.NN_BRUTE))
+    t.close()
+
+
+def test_shared_target_estimate(ctx, icp):
+    """config 3 in small: one shared map, many scans, each against the whole map."""
+    m = icp.synth_map(20000, seed=7)
+    scans, off, T0 = icp.synth_map_scans(12, beams=360, seed=7)
+    t = icp.Target(m, ctx)
+    g = t.estimate_batch(scans, off, T0, 6, corr_mode=icp.CORR_ALL)
+    g["src_off"] = off
+    srcs = [scans[off[b]:off[b + 1]] for b in range(12)]
+    _check_vs_oracle(g, srcs, [m] * 12, list(T0), 6)
+    t.close()
+
+
+# ------------------------------------------------------------------------------------------------
+def test_full_size_config2_properties(ctx, icp):
+    """BASELINE.json config 2 at full size (4096 pairs x 1080 points x 20 iterations):
+    (1) a seeded sample of pairs equals the oracle bit for bit; (2) results do not depend on how
+    the batch is split or ordered (same pair -> same bits); (3) the estimate recovers the
+    generator's true transform to scan-noise accuracy."""
+    B = 4096
+    src, dst, off, true_T = icp.synth_scan_pairs(B, beams=1080)
+    T0 = np.tile(I6, (B, 1))
+    g = ctx.estimate_batch(src, off, dst, off, T0, 20)
+    assert (g["status"] == 0).all() and np.isfinite(g["T"]).all()
+    sample = np.random.default_rng(0).choice(B, 48, replace=False)
+    for b in sample:
+        o = oracle.icp_estimate(src[off[b]:off[b + 1]], dst[off[b]:off[b + 1]], T0[b], 20, nn_mode=oracle.NN_KDTREE)
+        assert np.array_equal(g["T"][b], o["T"]) and np.array_equal(g["inner"][b], o["inner"])
+        assert int(g["corr_hash"][b]) == int(o["corr_hash"])
+    # split / order independence
+    perm = np.random.default_rng(1).permutation(B)[:512]
+    s2 = np.concatenate([src[off[b]:off[b + 1]] for b in perm])
+    d2 = np.concatenate([dst[off[b]:off[b + 1]] for b in perm])
+    off2 = (np.arange(513, dtype=np.uint64) * 1080).astype(np.uint32)
+    g2 = ctx.estimate_batch(s2, off2, d2, off2, T0[:512], 20)
+    assert np.array_equal(g2["T"], g["T"][perm]) and np.array_equal(g2["corr_hash"], g["corr_hash"][perm])
+    assert np.array_equal(g2["inner"], g["inner"][perm])
+    # accuracy against the generator's truth (mm / rad)
+    err_t = np.abs(g["T"][:, 4:] - true_T[:, 4:]).max(axis=1)
+    err_r = np.abs(g["T"][:, 2] - true_T[:, 2])
+    assert np.median(err_t) < 5.0 and np.median(err_r) < 2e-3

@@ -1,0 +1,125 @@
+"""CPU-only checks of the KERNEL SOURCES: icp_rust_b200/csrc/*.cuh compiled with g++ against the
+lock-step CTA emulator (tests/simt/) and compared with the oracle.  This validates barrier
+placement, the exact selection and the ordered accumulation without a GPU; the -m gpu tests
+repeat the comparison on the real sm_100a build through the C ABI."""
+import numpy as np
+import pytest
+
+import oracle
+from tests import refdata as R
+from tests import simt_emul as E
+
+I6 = np.array([1., 0., 0., 1., 0., 0.])
+
+
+def _oracle_ref(srcs, dsts, T0s, max_iter):
+    out = []
+    for s, d, t in zip(srcs, dsts, T0s):
+        out.append(oracle.icp_estimate(s, d, t, max_iter, nn_mode=oracle.NN_BRUTE, corr_mode=oracle.CORR_ALL))
+    return out
+
+
+def _compare(g, refs, srcs, max_iter):
+    so = g["src_off"]
+    for b, o in enumerate(refs):
+        n = len(srcs[b])
+        gc = g["corr"][int(so[b]) * max_iter:int(so[b]) * max_iter + n * max_iter].reshape(max_iter, n)
+        assert np.array_equal(gc, o["corr"]), f"pair {b}: correspondences differ"
+        assert np.array_equal(g["inner"][b], o["inner"]), f"pair {b}: inner iteration counts differ"
+        assert np.array_equal(g["T"][b], o["T"]), f"pair {b}: transform differs"
+        assert int(g["corr_hash"][b]) == int(o["corr_hash"]), f"pair {b}: hash differs"
+
+
+@pytest.mark.parametrize("threads", [32, 128, 256])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_calc_stddevs_exact(threads, mode):
+    rng = np.random.default_rng(5)
+    sets = [rng.normal(0, 3, (n, 2)) for n in (1, 2, 3, 10, 11, 64, 665, 666, 1080)]
+    sets.append(np.zeros((50, 2)))                              # MAD == 0
+    sets.append(np.repeat(rng.normal(0, 1, (5, 2)), 40, axis=0))  # heavy duplicates
+    sets.append(rng.normal(0, 1e-300, (33, 2)))                 # denormal-scale
+    sets.append(rng.normal(0, 1e150, (34, 2)))
+    sets.append(np.array(R.MEASUREMENTS_30))
+    sig, med = E.calc_stddevs(sets, mode=mode, threads=threads)
+    for k, s in enumerate(sets):
+        exp = oracle.calc_stddevs(s)
+        assert np.array_equal(sig[k], exp), (k, sig[k], exp)
+        for a in range(2):
+            assert med[k, a] == oracle.median(s[:, a])
+
+
+def test_calc_stddevs_reference_vectors():
+    # stats.rs:69-102 medians / MADs through the device selection
+    for vals, exp in R.MEDIAN_CASES:
+        if exp is None:
+            continue
+        s = np.stack([vals, vals], axis=1)
+        _, med = E.calc_stddevs([s])
+        assert med[0, 0] == exp and med[0, 1] == exp
+    for vals, exp in R.MAD_CASES:
+        s = np.stack([vals, vals], axis=1)
+        sig, _ = E.calc_stddevs([s])
+        assert sig[0, 0] == 1.482602218505602 * exp
+
+
+def _l_shape_case(dim):
+    true_T = oracle.transform_new(R.L_TRUE_PARAM)
+    init = oracle.transform_new(np.array(R.L_TRUE_PARAM) + np.array(R.L_NOISE_PARAM))
+    if dim == 2:
+        src = R.L_SHAPE_2D
+        dst = np.array([oracle.transform_apply(true_T, p) for p in src])
+    else:
+        src = R.L_SHAPE_3D
+        dst = np.array([oracle.transform_xy(true_T, p) for p in src])
+    return src, dst, init, true_T
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("variant", [2, 3])
+def test_fused_l_shape(dim, variant):  # lib.rs:510-595
+    src, dst, init, true_T = _l_shape_case(dim)
+    g = E.icp_fused([src], [dst], [init], max_iter=20, variant=variant)
+    _compare(g, _oracle_ref([src], [dst], [init], 20), [src], 20)
+    for p, q in zip(src, dst):
+        got = oracle.transform_apply(g["T"][0], p[:2])
+        assert np.linalg.norm(got - q[:2]) < 1e-3
+
+
+@pytest.mark.parametrize("schedule", [0, 1, 7])
+def test_fused_real_scans(scans2d, schedule):
+    E.set_schedule(schedule)
+    try:
+        srcs = [scans2d[1], scans2d[98]]
+        dsts = [scans2d[2], scans2d[99]]   # 099 holds duplicated (0,0) points: index ties
+        T0 = [I6, I6]
+        g = E.icp_fused(srcs, dsts, T0, max_iter=3, variant=1, grid=2)
+        _compare(g, _oracle_ref(srcs, dsts, T0, 3), srcs, 3)
+    finally:
+        E.set_schedule(0)
+
+
+def test_fused_degenerate_pairs():
+    rng = np.random.default_rng(3)
+    a = rng.normal(0, 100, (40, 2))
+    srcs = [a, a[:1], np.zeros((0, 2)), a, np.zeros((30, 2))]
+    dsts = [a.copy(), a, a, a[:1], np.zeros((30, 2))]  # identical clouds: sigma == 0 -> None
+    T0 = [I6] * 5
+    g = E.icp_fused(srcs, dsts, T0, max_iter=4, variant=2, grid=1)
+    _compare(g, _oracle_ref(srcs, dsts, T0, 4), srcs, 4)
+    assert np.array_equal(g["T"][0], I6)
+    assert (g["inner"][0] >> 16 == oracle.BREAK_NONE).all()
+
+
+def test_fused_status_codes():
+    rng = np.random.default_rng(4)
+    a = rng.normal(0, 100, (20, 2))
+    bad = a.copy()
+    bad[3, 1] = np.nan
+    srcs = [a, bad, a]
+    dsts = [np.zeros((0, 2)), a, a]
+    T0 = [I6, I6, np.array([1., 0., 0., 1., np.inf, 0.])]
+    g = E.icp_fused(srcs, dsts, T0, max_iter=2, variant=2)
+    assert list(g["status"]) == [1, 3, 3]
+    assert g["err"] == 3
+    for b in range(3):
+        assert np.array_equal(g["T"][b], T0[b], equal_nan=True)
