@@ -19,6 +19,8 @@ import numpy as np
 from ._lib import Batch, CallInfo, MissingNativeLibrary, cuda_lib, synth_lib, EXPORTS  # noqa: F401
 
 CORR_NONE, CORR_LAST, CORR_ALL = 0, 1, 2
+FLAG_ORDERED_SUMS = 1  # ICP_B200_FLAG_ORDERED_SUMS: reference-order sums, bit-identical transforms
+ABI_VERSION = 2
 BREAK_CAP, BREAK_NONE, BREAK_DELTA, BREAK_ERROR = 0, 1, 2, 3
 PAIR_OK, PAIR_EMPTY_TARGET, PAIR_TOO_LARGE, PAIR_NON_FINITE = 0, 1, 2, 3
 ERR_EMPTY_TARGET, ERR_NON_FINITE, ERR_TOO_LARGE = 4, 5, 6
@@ -122,7 +124,7 @@ class Context:
 
     # ------------------------------------------------------------------ batched estimate (host arrays)
     def estimate_batch(self, src, src_off, dst, dst_off, init_T, max_iter=20, *, dim=None, corr_mode=CORR_NONE,
-                       want_inner=True, want_hash=True, target=None, raise_on_pair_error=True):
+                       want_inner=True, want_hash=True, target=None, raise_on_pair_error=True, ordered=False):
         """B independent `IcpD::new(dst_b).estimate(src_b, init_b, max_iter)` calls.
         src/dst: concatenated (P, dim) float64; *_off: (B+1,) uint32.  Returns a dict."""
         src = np.ascontiguousarray(src, dtype=np.float64)
@@ -143,6 +145,7 @@ class Context:
             corr = np.full(max(nsrc, 1), -1, dtype=np.int32)
         b = Batch()
         b.dim, b.batch, b.max_iter, b.corr_mode = dim, B, max_iter, corr_mode
+        b.flags = FLAG_ORDERED_SUMS if ordered else 0
         b.src = src.ctypes.data if src.size else None
         b.src_off = src_off.ctypes.data
         if target is None:
@@ -174,12 +177,13 @@ class Context:
 
     # ------------------------------------------------------------------ device-resident batch
     def estimate_batch_device(self, ptrs: dict, B, max_iter, dim=2, corr_mode=CORR_NONE, max_src=0, max_dst=0,
-                              stream=None, synchronize=True, target=None):
+                              stream=None, synchronize=True, target=None, ordered=False):
         """ptrs: device addresses (ints) for src, src_off, dst, dst_off, init_T, out_T and optionally
         out_inner, out_corr, out_corr_hash, out_status.  Used with torch tensors' data_ptr()."""
         b = Batch()
         b.dim, b.batch, b.max_iter, b.corr_mode = dim, B, max_iter, corr_mode
         b.max_src_points, b.max_dst_points = max_src, max_dst
+        b.flags = FLAG_ORDERED_SUMS if ordered else 0
         for k in ("src", "src_off", "dst", "dst_off", "init_T", "out_T", "out_inner", "out_corr", "out_corr_hash",
                   "out_status"):
             v = ptrs.get(k)
@@ -190,12 +194,13 @@ class Context:
             rc = self._L.icp_b200_target_estimate_batch_device(target._h, C.byref(b), stream, 1 if synchronize else 0)
         return self._check(rc)
 
-    def estimate_batch_host_ptrs(self, ptrs: dict, B, max_iter, dim=2, corr_mode=CORR_NONE, target=None):
+    def estimate_batch_host_ptrs(self, ptrs: dict, B, max_iter, dim=2, corr_mode=CORR_NONE, target=None, ordered=False):
         """icp_b200_estimate_batch on caller-owned HOST buffers given as addresses (e.g. pinned torch
         tensors): same keys as estimate_batch_device.  Copies in, computes, copies results back and
         returns when they have landed."""
         b = Batch()
         b.dim, b.batch, b.max_iter, b.corr_mode = dim, B, max_iter, corr_mode
+        b.flags = FLAG_ORDERED_SUMS if ordered else 0
         for k in ("src", "src_off", "dst", "dst_off", "init_T", "out_T", "out_inner", "out_corr", "out_corr_hash",
                   "out_status"):
             v = ptrs.get(k)
@@ -295,7 +300,7 @@ class _IcpBase:
         T0 = _as_T6(initial_transform)
         if self._target is not None:
             res = self._target.estimate_batch(src, np.array([0, len(src)], dtype=np.uint32), T0[None], max_iter,
-                                              want_inner=False, want_hash=False)
+                                              want_inner=False, want_hash=False, ordered=True)
             return Transform.from_array(res["T"][0])
         out = np.zeros(6)
         L = self.ctx._L

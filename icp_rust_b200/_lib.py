@@ -20,7 +20,7 @@ class Batch(C.Structure):
         ("max_src_points", C.c_uint32), ("max_dst_points", C.c_uint32),
         ("src", C.c_void_p), ("src_off", C.c_void_p), ("dst", C.c_void_p), ("dst_off", C.c_void_p),
         ("init_T", C.c_void_p), ("out_T", C.c_void_p), ("out_inner", C.c_void_p), ("out_corr", C.c_void_p),
-        ("out_corr_hash", C.c_void_p), ("out_status", C.c_void_p),
+        ("out_corr_hash", C.c_void_p), ("out_status", C.c_void_p), ("flags", C.c_uint32),
     ]
 
 

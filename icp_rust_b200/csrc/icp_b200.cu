@@ -45,10 +45,12 @@ struct DevBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-// kernel instances live in their own translation units (icp_fused_inst.cu, one per capacity) so
-// that they compile in parallel; capacities (source points per scan): 128, 384, 768, 1152, 2048, 3072
-const Instance* const kInstances[] = {&kFusedInstance0, &kFusedInstance1, &kFusedInstance2,
-                                      &kFusedInstance3, &kFusedInstance4, &kFusedInstance5};
+// kernel instances live in their own translation units (icp_fused_inst.cu, list in the
+// Makefile) so that they compile in parallel
+const Instance* const kInstances[] = {&kFusedInstance0, &kFusedInstance1, &kFusedInstance2, &kFusedInstance3,
+                                      &kFusedInstance4, &kFusedInstance5, &kFusedInstance6, &kFusedInstance7,
+                                      &kFusedInstance8, &kFusedInstance9, &kFusedInstance10, &kFusedInstance11,
+                                      &kFusedInstance12, &kFusedInstance13};
 constexpr int kNumInstances = (int)(sizeof(kInstances) / sizeof(kInstances[0]));
 constexpr int kMaxChunks = 64;
 
@@ -132,21 +134,21 @@ struct LaunchPlan {
 };
 
 // Chooses the kernel instance for the largest scan of the batch and sizes its launch.
-int plan_launch(icp_b200_context* ctx, uint32_t dim, bool shared_target, uint32_t max_n, uint32_t max_m,
+int plan_launch(icp_b200_context* ctx, uint32_t dim, bool shared_target, bool ordered, uint32_t max_n, uint32_t max_m,
                 uint32_t pairs, LaunchPlan* plan)
 {
     const Instance* inst = nullptr;
-    if (ctx->force_instance >= 0 && ctx->force_instance < kNumInstances &&
-        (uint32_t)(kInstances[ctx->force_instance]->threads * kInstances[ctx->force_instance]->ppt) >= max_n)
+    auto fits = [&](const Instance* c) { return c->ordered == ordered && (uint32_t)(c->threads * c->ppt) >= max_n; };
+    if (ctx->force_instance >= 0 && ctx->force_instance < kNumInstances && fits(kInstances[ctx->force_instance]))
         inst = kInstances[ctx->force_instance];
     for (int i = 0; !inst && i < kNumInstances; ++i)
-        if ((uint32_t)(kInstances[i]->threads * kInstances[i]->ppt) >= max_n) inst = kInstances[i];
+        if (fits(kInstances[i])) inst = kInstances[i];
     if (!inst) return fail(ctx, ICP_B200_ERR_TOO_LARGE, "source scan larger than the largest fused kernel (3072 points)");
     if (!shared_target && max_m > 65528u)
         return fail(ctx, ICP_B200_ERR_TOO_LARGE, "per-pair target larger than 65528 points: use icp_b200_target_create");
     plan->inst = inst;
     plan->mcap = (int)((max_m + 7u) & ~7u);
-    plan->layout = fused_layout((int)dim, inst->threads * inst->ppt, plan->mcap, ctx->cell_budget, shared_target);
+    plan->layout = fused_layout((int)dim, inst->threads * inst->ppt, plan->mcap, ctx->cell_budget, shared_target, ordered);
     if ((int)plan->layout.total > ctx->max_smem_optin)
         return fail(ctx, ICP_B200_ERR_TOO_LARGE, "scan pair does not fit the shared memory of one SM: use icp_b200_target_create for large targets");
     plan->kernel = inst->k[dim - 2][shared_target ? 1 : 0];
@@ -169,6 +171,7 @@ int validate_batch(icp_b200_context* ctx, const icp_b200_batch* b, bool shared_t
     if (!b->src_off || !b->init_T || !b->out_T) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null src_off / init_T / out_T");
     if (!shared_target && !b->dst_off) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null dst_off");
     if (b->corr_mode < 0 || b->corr_mode > 2) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "bad corr_mode");
+    if (b->flags & ~(uint32_t)ICP_B200_FLAG_ORDERED_SUMS) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "unknown flag bits");
     if (b->corr_mode != ICP_B200_CORR_NONE && !b->out_corr) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "corr_mode set but out_corr is null");
     return ICP_B200_OK;
 }
@@ -187,6 +190,7 @@ int launch_range(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_
     p.ws_stride = ws_stride_of(plan.layout);
     p.pair_begin = begin; p.pair_end = end; p.max_iter = b.max_iter; p.corr_mode = b.corr_mode;
     p.cell_budget = ctx->cell_budget; p.ncap = plan.inst->threads * plan.inst->ppt; p.mcap = plan.mcap;
+    p.sm_count = (uint32_t)ctx->sm_count;
     if (tgt) {
         p.target.x = tgt->x.as<double>(); p.target.y = tgt->y.as<double>(); p.target.z = tgt->z.as<double>();
         p.target.idx = tgt->idx.as<uint32_t>(); p.target.cstart = tgt->cstart.as<uint32_t>();
@@ -242,7 +246,7 @@ int estimate_device_impl(icp_b200_context* ctx, const icp_b200_target* tgt, cons
         ctx->info.d2h_bytes += (uint64_t)off.size() * 4 * (shared ? 1 : 2);
     }
     LaunchPlan plan;
-    rc = plan_launch(ctx, b->dim, shared, max_n, max_m, b->batch, &plan);
+    rc = plan_launch(ctx, b->dim, shared, (b->flags & ICP_B200_FLAG_ORDERED_SUMS) != 0, max_n, max_m, b->batch, &plan);
     if (rc != ICP_B200_OK) return rc;
     ICP_CUDA(ctx, ctx->counters.ensure((kMaxChunks + 1) * 4));
     ICP_CUDA(ctx, ctx->workspace[0].ensure((size_t)plan.grid * ws_stride_of(plan.layout) + 256));
@@ -286,7 +290,7 @@ int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b2
     const uint64_t nsrc = so[B], ndst = shared ? 0 : doff[B];
     if ((nsrc && !hb->src) || (ndst && !hb->dst)) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null point array");
     LaunchPlan plan;
-    rc = plan_launch(ctx, dim, shared, max_n, max_m, B, &plan);
+    rc = plan_launch(ctx, dim, shared, (hb->flags & ICP_B200_FLAG_ORDERED_SUMS) != 0, max_n, max_m, B, &plan);
     if (rc != ICP_B200_OK) return rc;
 
     const uint64_t ncorr = hb->corr_mode == ICP_B200_CORR_ALL ? nsrc * hb->max_iter
@@ -493,6 +497,7 @@ static int single_pair(icp_b200_context* ctx, uint32_t dim, const double* dst, u
     icp_b200_batch b{};
     b.dim = dim; b.batch = 1; b.max_iter = max_iter; b.corr_mode = ICP_B200_CORR_NONE;
     b.src = src; b.src_off = so; b.dst = dst; b.dst_off = dof; b.init_T = T0; b.out_T = out;
+    b.flags = ICP_B200_FLAG_ORDERED_SUMS;  // one pair: latency is launch-bound anyway, keep the reference's exact sums
     return estimate_host_impl(ctx, nullptr, &b);
 }
 
@@ -664,7 +669,8 @@ int icp_b200_calc_stddevs_batch(icp_b200_context* ctx, const double* residuals_x
     int cap = 1;
     for (uint32_t b = 0; b < batch; ++b) cap = std::max(cap, (int)(off[b + 1] - off[b]));
     const uint32_t smem = stats_smem_bytes(cap);
-    if ((int)smem > ctx->max_smem_optin) return fail(ctx, ICP_B200_ERR_TOO_LARGE, "residual set does not fit shared memory");
+    if ((int)smem > ctx->max_smem_optin || cap > kStatsThreads * kStatsPpt)
+        return fail(ctx, ICP_B200_ERR_TOO_LARGE, "residual set larger than 3072 points");
     const uint64_t total = off[batch];
     if (total && !residuals_xy) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null residuals");
     ICP_CUDA(ctx, ctx->stats_in.ensure(std::max<uint64_t>(total, 1) * 16));
@@ -677,9 +683,9 @@ int icp_b200_calc_stddevs_batch(icp_b200_context* ctx, const double* residuals_x
     p.residuals = ctx->stats_in.as<double>(); p.off = ctx->stats_off.as<uint32_t>();
     p.out_sigma = ctx->stats_out.as<double>(); p.out_median = ctx->stats_out.as<double>() + (size_t)batch * 2;
     p.B = batch; p.cap = cap; p.mode = env_int("ICP_B200_STATS_MODE", 1);
-    ICP_CUDA(ctx, cudaFuncSetAttribute(calc_stddevs_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ICP_CUDA(ctx, cudaFuncSetAttribute(calc_stddevs_kernel<kStatsThreads, kStatsPpt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)std::min<uint32_t>(batch, (uint32_t)ctx->sm_count * 4);
-    calc_stddevs_kernel<128><<<grid, 128, smem, st>>>(p);
+    calc_stddevs_kernel<kStatsThreads, kStatsPpt><<<grid, kStatsThreads, smem, st>>>(p);
     ICP_CUDA(ctx, cudaGetLastError());
     ICP_CUDA(ctx, cudaMemcpyAsync(out_sigma, p.out_sigma, (size_t)batch * 16, cudaMemcpyDeviceToHost, st));
     if (out_median) ICP_CUDA(ctx, cudaMemcpyAsync(out_median, p.out_median, (size_t)batch * 16, cudaMemcpyDeviceToHost, st));

@@ -86,8 +86,8 @@ constexpr int kSelCap = 32;              // gathered keys ranked by one warp
 
 struct SelBinSpec {
     int mode;        // 0 = FAST (value-uniform), 1 = RADIX
-    double lo;       // FAST: value of the left edge of bin 1
-    double scale;    // FAST: bins per unit
+    float lo;        // FAST: value of the left edge of bin 1
+    float scale;     // FAST: bins per unit
     uint64_t pfx;    // RADIX: required value of key >> (shift + 8)   (unused when shift == 56)
     int shift;       // RADIX: digit = (key >> shift) & 0xff
 };
@@ -108,12 +108,16 @@ struct SelShared {
     double out_lo[2], out_hi[2];
 };
 
+// FAST bins in binary32: conversion, subtraction of a constant, multiplication by a positive
+// constant, clamping and floor are each monotone non-decreasing, so the composition is a
+// monotone map of the binary64 key — all that exactness needs.  (A key range too fine for
+// binary32 merely crowds one bin; the caller then falls back to RADIX.)
 ICP_DEV int sel_bin(const SelBinSpec& s, double v)
 {
     if (s.mode == 0) {
-        double t = (v - s.lo) * s.scale;
-        t = fmin(fmax(t, -1.0), (double)kSelBins);
-        return __double2int_rd(t) + 1;  // 0 .. kSelBins+1
+        float t = (__double2float_rn(v) - s.lo) * s.scale;
+        t = fminf(fmaxf(t, -1.0f), (float)kSelBins);
+        return __float2int_rd(t) + 1;  // 0 .. kSelBins+1
     }
     uint64_t key = f64_order_key(v);
     if (s.shift < 56) {
@@ -229,19 +233,43 @@ ICP_DEV void sel_start_radix(SelAxisState& st, int which)
     st.phase = which;
 }
 
-// Medians of the two key columns.  n >= 1.  est_valid[a] enables the FAST map for axis a with
-// value range [est_lo[a], est_lo[a] + kSelBins / est_scale[a]).
+// FAST-map parameters from an estimate of centre and spread of the keys: kSelBins bins over
+// [lo, lo + width).  Returns false when the binary32 map would be degenerate.
+ICP_DEV bool sel_fast_params(double lo, double width, float* lo32, float* scale32)
+{
+    const double sc = (double)kSelBins / width;
+    *lo32 = __double2float_rn(lo);
+    *scale32 = __double2float_rn(sc);
+    return width > 0.0 && sc < 1e30 && sc > 1e-30 && fabs(lo) < 1e30;
+}
+
+// Key sources: where block_median2 reads the (x, y) value pair of point i = tid + kk * THREADS.
+struct KeysInShared {            // AoS double2 array in shared memory
+    const double2* v;
+    ICP_DEV_MEMBER double2 get(int /*kk*/, int i) const { return v[i]; }
+};
+template <int PPT>
+struct KeysInRegisters {         // the calling thread's own points, held in registers
+    const double2* v;            // v[kk]
+    ICP_DEV_MEMBER double2 get(int kk, int /*i*/) const { return v[kk]; }
+};
+
+// Medians of the two key columns.  n >= 1, n <= THREADS * PPT.  est_valid[a] enables the FAST map
+// for axis a with value range [est_lo[a], est_lo[a] + kSelBins / est_scale[a]).
 // On return med[a] = median as stats.rs:11-28 defines it ((b + c) / 2 for even n).
 // `hist_parity` names the histogram buffer that is already zeroed on entry; on exit the
 // returned parity names a zeroed buffer again.  Must be called by all threads of the CTA.
-template <int THREADS>
-ICP_DEV int block_median2(SelShared* sh, const double* r2, int n, int absdev, const double centre[2],
-                          const bool est_valid[2], const double est_lo[2], const double est_scale[2],
+//
+// Round structure (two barriers in the common case): histogram pass | barrier | EVERY warp
+// locates the wanted bins from the shared histogram (identical results, no broadcast needed) |
+// gather the bins' keys into a short list | barrier | every warp ranks the list.
+template <int THREADS, int PPT, class KeySrc>
+ICP_DEV int block_median2(SelShared* sh, const KeySrc& keys, int n, int absdev, const double centre[2],
+                          const bool est_valid[2], const float est_lo[2], const float est_scale[2],
                           int hist_parity, double med[2])
 {
     const int tid = (int)threadIdx.x;
     const int lane = lane_id();
-    const int warp = warp_id();
     const bool need_hi = (n % 2) == 0;
     const uint32_t k = need_hi ? (uint32_t)(n / 2 - 1) : (uint32_t)(n / 2);
     SelAxisState st[2];
@@ -258,34 +286,42 @@ ICP_DEV int block_median2(SelShared* sh, const double* r2, int n, int absdev, co
             st[a].phase = 0;
         } else {
             sel_start_radix(st[a], 0);
-            st[a].spec.lo = 0.;
-            st[a].spec.scale = 0.;
+            st[a].spec.lo = 0.f;
+            st[a].spec.scale = 0.f;
         }
     }
     int par = hist_parity;
-    const double2* r2v = reinterpret_cast<const double2*>(r2);
     while (st[0].phase != 2 || st[1].phase != 2) {
         uint32_t* h0 = sh->hist[par][0];
         uint32_t* h1 = sh->hist[par][1];
         // ---- histogram pass (also clears the other buffer and the list counters)
         for (int q = tid; q < 2 * kSelHistPad; q += THREADS) (&sh->hist[par ^ 1][0][0])[q] = 0u;
         if (tid < 2) sh->lcnt[tid] = 0u;
+        uint32_t bins[PPT];   // this round's bin of each of the thread's keys: axis 0 | axis 1 << 16
         {
             uint32_t under0 = 0, over0 = 0, under1 = 0, over1 = 0;
-            for (int i = tid; i < n; i += THREADS) {
-                double2 rr = r2v[i];
-                if (st[0].phase != 2) {
-                    int b = sel_bin(st[0].spec, sel_key(rr.x, absdev, centre[0]));
-                    if (b == 0) ++under0;
-                    else if (b == kSelBins + 1) ++over0;
-                    else atomicAdd(&h0[b], 1u);
+#pragma unroll
+            for (int kk = 0; kk < PPT; ++kk) {
+                const int i = tid + kk * THREADS;
+                uint32_t packed = 0xffffffffu;
+                if (i < n) {
+                    const double2 rr = keys.get(kk, i);
+                    int b0 = 0xffff, b1 = 0xffff;
+                    if (st[0].phase != 2) {
+                        b0 = sel_bin(st[0].spec, sel_key(rr.x, absdev, centre[0]));
+                        if (b0 == 0) ++under0;
+                        else if (b0 == kSelBins + 1) ++over0;
+                        else atomicAdd(&h0[b0], 1u);
+                    }
+                    if (st[1].phase != 2) {
+                        b1 = sel_bin(st[1].spec, sel_key(rr.y, absdev, centre[1]));
+                        if (b1 == 0) ++under1;
+                        else if (b1 == kSelBins + 1) ++over1;
+                        else atomicAdd(&h1[b1], 1u);
+                    }
+                    packed = (uint32_t)b0 | ((uint32_t)b1 << 16);
                 }
-                if (st[1].phase != 2) {
-                    int b = sel_bin(st[1].spec, sel_key(rr.y, absdev, centre[1]));
-                    if (b == 0) ++under1;
-                    else if (b == kSelBins + 1) ++over1;
-                    else atomicAdd(&h1[b], 1u);
-                }
+                bins[kk] = packed;
             }
             under0 = warp_sum_u32(under0);
             over0 = warp_sum_u32(over0);
@@ -299,49 +335,37 @@ ICP_DEV int block_median2(SelShared* sh, const double* r2, int n, int absdev, co
             }
         }
         __syncthreads();
-        // ---- locate (warp a serves axis a)
-        if (warp < 2) {
-            for (int a = (THREADS >= 64 ? warp : 0); a < 2; a += (THREADS >= 64 ? 2 : 1)) {
-                if (st[a].phase == 2) continue;
-                const bool both = (st[a].spec.mode == 0) && need_hi;
-                const uint32_t kq = k + (uint32_t)(st[a].phase == 1 ? 1 : 0);
-                SelDecision d = sel_locate(sh->hist[par][a], kq, both, st[a].spec);
-                if (lane == 0) sh->dec[a] = d;
-            }
-        }
-        __syncthreads();
-        SelDecision d0 = sh->dec[0], d1 = sh->dec[1];
-        const bool g0 = st[0].phase != 2 && d0.action == 0;
-        const bool g1 = st[1].phase != 2 && d1.action == 0;
+        // ---- locate: every warp, both axes, identical decisions
+        SelDecision d0, d1;
+        d0.action = -1; d0.b_lo = d0.b_hi = 0; d0.below = d0.count = 0;
+        d1 = d0;
+        if (st[0].phase != 2)
+            d0 = sel_locate(h0, k + (uint32_t)(st[0].phase == 1 ? 1 : 0), (st[0].spec.mode == 0) && need_hi, st[0].spec);
+        if (st[1].phase != 2)
+            d1 = sel_locate(h1, k + (uint32_t)(st[1].phase == 1 ? 1 : 0), (st[1].spec.mode == 0) && need_hi, st[1].spec);
+        const bool g0 = d0.action == 0;
+        const bool g1 = d1.action == 0;
+        double fin_lo[2] = {0., 0.}, fin_hi[2] = {0., 0.};
         if (g0 || g1) {
-            // ---- gather the target bins
-            for (int i = tid; i < n; i += THREADS) {
-                double2 rr = r2v[i];
-                if (g0) {
-                    double v = sel_key(rr.x, absdev, centre[0]);
-                    int b = sel_bin(st[0].spec, v);
-                    if (b >= d0.b_lo && b <= d0.b_hi) sh->list[0][atomicAdd(&sh->lcnt[0], 1u)] = v;
-                }
-                if (g1) {
-                    double v = sel_key(rr.y, absdev, centre[1]);
-                    int b = sel_bin(st[1].spec, v);
-                    if (b >= d1.b_lo && b <= d1.b_hi) sh->list[1][atomicAdd(&sh->lcnt[1], 1u)] = v;
+            // ---- gather the target bins (cached bin numbers; keys are re-read only on a hit)
+#pragma unroll
+            for (int kk = 0; kk < PPT; ++kk) {
+                const int i = tid + kk * THREADS;
+                const int b0 = (int)(bins[kk] & 0xffffu), b1 = (int)(bins[kk] >> 16);
+                const bool hit0 = g0 && b0 >= d0.b_lo && b0 <= d0.b_hi;   // 0xffff marks "no key"
+                const bool hit1 = g1 && b1 >= d1.b_lo && b1 <= d1.b_hi;
+                if (hit0 || hit1) {
+                    const double2 rr = keys.get(kk, i);
+                    if (hit0) sh->list[0][atomicAdd(&sh->lcnt[0], 1u)] = sel_key(rr.x, absdev, centre[0]);
+                    if (hit1) sh->list[1][atomicAdd(&sh->lcnt[1], 1u)] = sel_key(rr.y, absdev, centre[1]);
                 }
             }
             __syncthreads();
-            if (warp < 2) {
-                for (int a = (THREADS >= 64 ? warp : 0); a < 2; a += (THREADS >= 64 ? 2 : 1)) {
-                    if (!(a == 0 ? g0 : g1)) continue;
-                    const SelDecision d = a == 0 ? d0 : d1;
-                    const uint32_t kq = k + (uint32_t)(st[a].phase == 1 ? 1 : 0);
-                    double v0, v1;
-                    sel_finish(sh->list[a], d.count, kq - d.below, &v0, &v1);
-                    if (lane == 0) {
-                        sh->out_lo[a] = v0;
-                        sh->out_hi[a] = v1;
-                    }
-                }
-            }
+            // ---- rank the lists: every warp, identical results
+            if (g0) sel_finish(sh->list[0], d0.count, k + (uint32_t)(st[0].phase == 1 ? 1 : 0) - d0.below, &fin_lo[0], &fin_hi[0]);
+            if (g1) sel_finish(sh->list[1], d1.count, k + (uint32_t)(st[1].phase == 1 ? 1 : 0) - d1.below, &fin_lo[1], &fin_hi[1]);
+        } else {
+            // no barrier separated this round's histogram readers from the next round's clearing
             __syncthreads();
         }
         // ---- uniform state update
@@ -351,7 +375,7 @@ ICP_DEV int block_median2(SelShared* sh, const double* r2, int n, int absdev, co
             const SelDecision d = a == 0 ? d0 : d1;
             const uint32_t kq = k + (uint32_t)(st[a].phase == 1 ? 1 : 0);
             if (d.action == 0) {
-                const double v0 = sh->out_lo[a], v1 = sh->out_hi[a];
+                const double v0 = fin_lo[a], v1 = fin_hi[a];
                 const bool hi_inside = (kq - d.below) + 1 < d.count;
                 if (st[a].phase == 0) {
                     st[a].v_lo = v0;
@@ -391,6 +415,32 @@ ICP_DEV int block_median2(SelShared* sh, const double* r2, int n, int absdev, co
 #pragma unroll
     for (int a = 0; a < 2; ++a) med[a] = need_hi ? (st[a].v_lo + st[a].v_hi) / 2. : st[a].v_lo;
     return par;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sums 16 values per lane across the warp with 16 (instead of 80) 64-bit exchanges: at every
+// butterfly step the partners split the value set, each keeping (and summing) one half.  On
+// return every lane holds the warp total of value number warp_reduce16_owner(lane) in v[0];
+// lanes 2t and 2t+1 hold the same value.  The summation tree is fixed: results do not depend on
+// scheduling.
+ICP_DEV int warp_reduce16_owner(int lane)
+{
+    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+ICP_DEV void warp_reduce16(double v[16])
+{
+    const int lane = lane_id();
+#pragma unroll
+    for (int half = 8, msk = 16; half >= 1; half >>= 1, msk >>= 1) {
+        const bool upper = (lane & msk) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+            const double send = upper ? v[j] : v[j + half];
+            const double keep = upper ? v[j + half] : v[j];
+            v[j] = keep + shfl_xor_f64(send, msk);
+        }
+    }
+    v[0] = v[0] + shfl_xor_f64(v[0], 1);
 }
 
 }  // namespace icp

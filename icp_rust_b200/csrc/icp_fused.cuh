@@ -17,14 +17,25 @@
 //             source order (i ascending, row 0 then row 1) by dedicated lanes so that every
 //             sum carries the same roundings as the reference's fold -> 3x3 solve, break
 //             tests, SE(2) exponential, compose.  No host round trip.
-// Shared memory is one region used as {sorted target, cell table} during search and as
-// {r, c, b, rho} row arrays during IRLS.
+// Two reduction modes (template parameter ORDERED):
+//   ORDERED = false  the normal-equation sums are reduced with warp shuffles in a fixed,
+//             schedule-independent order (per-thread partials over the thread's points in
+//             ascending order, xor-butterfly across lanes, warps added in warp order).  Weights,
+//             Jacobian rows and terms never leave registers; the sorted target stays resident in
+//             shared memory for the whole pair.  Results differ from the reference's sequential
+//             fold only by summation rounding (~1e-16 relative): iteration counts and
+//             correspondences match unless a break test falls within that distance of its
+//             threshold, transforms agree to far better than 1e-9.
+//   ORDERED = true   every sum carries the same roundings as the reference's fold: transforms are
+//             bit-identical to the oracle by construction.  Shared memory is one region used as
+//             {sorted target, cell table} during search and as {r, c, b, rho} row arrays during
+//             IRLS (the target is re-staged from an L2-resident per-CTA slab each outer iteration).
 #pragma once
 #include "icp_grid.cuh"
 
 namespace icp {
 
-constexpr int kChainUnroll = 8;  // rows arrays are zero-padded to a multiple of this many points
+constexpr int kChainUnroll = 8;  // rows arrays are zero-padded to a multiple of 2x this many points
 constexpr int kMaxWarps = 32;
 
 enum PairStatus : int32_t {
@@ -46,13 +57,14 @@ struct FusedLayout {
 
 struct FusedCtl {
     double sums[16];
-    double red[kMaxWarps][6];
+    double red[kMaxWarps][16];
     uint64_t hash_part[kMaxWarps];
     uint32_t warp_tot[kMaxWarps];
     uint32_t pair;
 };
 
 ICP_HD uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
+ICP_HD uint32_t align128(uint32_t v) { return (v + 127u) & ~127u; }
 
 // Shared target (Icp2d::new analogue kept on the device, reused by many estimates)
 struct TargetView {
@@ -65,7 +77,7 @@ struct TargetView {
     uint32_t m;
 };
 
-ICP_HD FusedLayout fused_layout(int dim, int ncap, int mcap, int cell_budget, bool shared_target)
+ICP_HD FusedLayout fused_layout(int dim, int ncap, int mcap, int cell_budget, bool shared_target, bool ordered)
 {
     FusedLayout L;
     uint32_t o = 0;
@@ -76,16 +88,28 @@ ICP_HD FusedLayout fused_layout(int dim, int ncap, int mcap, int cell_budget, bo
     L.nn_idx = o; o = align16(o + 2u * (uint32_t)mcap);
     L.nn_cell = o; o = align16(o + 2u * (uint32_t)(cell_budget + 1));
     L.nn_bytes = o;
+    o = align128(o);
+    const uint32_t bt0 = o;
     L.bt_cnt = o; o = align16(o + 4u * (uint32_t)cell_budget);
     L.bt_cell = o; o = align16(o + 2u * (uint32_t)mcap);
     L.bt_slot = o; o = align16(o + 2u * (uint32_t)mcap);
-    uint32_t nn_total = o;
-    o = 0;
-    L.gn_r = o; o = align16(o + 16u * (uint32_t)ncap);
-    L.gn_c = o; o = align16(o + 16u * (uint32_t)ncap);
-    L.gn_b = o; o = align16(o + 16u * (uint32_t)ncap);
-    L.gn_rho = o; o = align16(o + 8u * (uint32_t)ncap);
-    L.gn_const = o; o = align16(o + 8u * 6u * 2u * (uint32_t)kChainUnroll);
+    const uint32_t nn_total = o;
+    // IRLS row arrays, one double2 (row 0, row 1) per point.
+    //  ordered: r, b, c, rho and the constant table overlay the whole search region; the chain
+    //           warp reads them with 128-bit loads whose lanes address different arrays at the
+    //           same point index, so the arrays sit at different 16-byte phases of the 128-byte
+    //           bank line: r +0, b +16, K0 +32, K1 +48 (c is read alone).
+    //  tree:    only r is kept, overlaying the build temporaries; the search arrays stay resident.
+    o = ordered ? 0u : bt0;
+    L.gn_r = o; o = align128(o + 16u * (uint32_t)ncap);
+    if (ordered) {
+        L.gn_b = o + 16u; o = align128(L.gn_b + 16u * (uint32_t)ncap);
+        L.gn_c = o; o = align128(o + 16u * (uint32_t)ncap);
+        L.gn_rho = o; o = align128(o + 8u * (uint32_t)ncap);
+        L.gn_const = o + 32u; o = align128(L.gn_const + 16u + 2u * 16u * (uint32_t)kChainUnroll);
+    } else {
+        L.gn_b = L.gn_c = L.gn_rho = L.gn_const = o;
+    }
     L.u_bytes = o > nn_total ? o : nn_total;
     L.off_sel = L.u_bytes;
     L.off_ctl = align16(L.off_sel + (uint32_t)sizeof(SelShared));
@@ -114,6 +138,7 @@ struct FusedParams {
     int corr_mode;              // 0 none, 1 last iteration, 2 all iterations
     int cell_budget;
     int ncap, mcap;             // capacities the layout was built for
+    uint32_t sm_count;          // SMs of the device (residency-slot estimate for warp-role rotation)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -213,83 +238,162 @@ ICP_DEV GridGeom cta_build_grid(const double* dst, int m, unsigned char* U, cons
 }
 
 // ---------------------------------------------------------------------------------------------
-// Sequential accumulation (lib.rs:242-255 and lib.rs:45-50).  Lane L of the chain warp owns one
-// accumulator and adds its terms in the reference's order.  Term of row (i, j):
+// Sequential accumulation (lib.rs:242-255 and lib.rs:45-50).  Lane L < 12 of the chain warp owns
+// one accumulator (9 of jtj, 3 of jtr) and adds its terms in the reference's order.  Term of
+// row (i, j):
 //     (X * Y) * Z   with  X = c_ij = w_ij * g_j,   Y = J_ij[a],   Z = J_ij[b] or r_ij
-// J_ij = [R_j0, R_j1, b_ij].  Point-dependent factors are read from the row arrays (stride two
-// doubles per point); uniform factors come from a table whose entries repeat, so that every
-// lane executes the same loads with the same immediates.
+// J_ij = [R_j0, R_j1, b_ij].  Rows 0 and 1 of a point are one double2, so each factor is one
+// 128-bit shared load per point; uniform factors (R_j0, R_j1) come from a small table whose
+// entries repeat per unrolled point, so that every lane executes the same loads with the same
+// immediates and only the base pointer differs.  Lanes >= 12 mirror lane 0 (same addresses,
+// result discarded).
 struct ChainPtrs {
-    const double *x0, *y0, *z0, *x1, *y1, *z1;
-    int ix0, iy0, iz0, ix1, iy1, iz1;   // pointer advance per block of kChainUnroll points
+    smem_ref x, y, z;   // shared-memory references to double2 arrays
+    int iy, iz;         // advance (in double2) per kChainStage points; x always advances
 };
 
-ICP_DEV double chain_run(ChainPtrs p, int nblocks)
+constexpr int kChainStage = 4;   // points per pipeline stage
+
+// Three-stage software pipeline over stages of kChainStage points: while stage k's dependent
+// additions retire, stage k+1's (independent) products are formed and stage k+2's operands are
+// loaded, so the loop runs at the latency of the DADD chain alone.  Kept out of line so that it
+// gets its own register allocation instead of competing with the per-point state the calling
+// kernel keeps in registers.  nstages >= 2.
+ICP_DEV_NOINLINE double chain_run(ChainPtrs p, int nstages)
 {
+    constexpr int S = kChainStage;
     double acc = 0.0;
-    for (int blk = 0; blk < nblocks; ++blk) {
+    double2 lx[S], ly[S], lz[S];
+    double t[2 * S];
 #pragma unroll
-        for (int u = 0; u < kChainUnroll; ++u) {
-            acc = acc + (p.x0[2 * u] * p.y0[2 * u]) * p.z0[2 * u];
-            acc = acc + (p.x1[2 * u] * p.y1[2 * u]) * p.z1[2 * u];
+    for (int u = 0; u < S; ++u) {
+        const double2 x = smem_ld2(p.x, u), y = smem_ld2(p.y, u), z = smem_ld2(p.z, u);
+        t[2 * u] = (x.x * y.x) * z.x;
+        t[2 * u + 1] = (x.y * y.y) * z.y;
+    }
+    p.x = smem_adv2(p.x, S); p.y = smem_adv2(p.y, p.iy); p.z = smem_adv2(p.z, p.iz);
+#pragma unroll
+    for (int u = 0; u < S; ++u) { lx[u] = smem_ld2(p.x, u); ly[u] = smem_ld2(p.y, u); lz[u] = smem_ld2(p.z, u); }
+    for (int st = 2; st < nstages; ++st) {
+        p.x = smem_adv2(p.x, S); p.y = smem_adv2(p.y, p.iy); p.z = smem_adv2(p.z, p.iz);
+        double tn[2 * S];
+#pragma unroll
+        for (int u = 0; u < S; ++u) {
+            tn[2 * u] = (lx[u].x * ly[u].x) * lz[u].x;
+            tn[2 * u + 1] = (lx[u].y * ly[u].y) * lz[u].y;
+            lx[u] = smem_ld2(p.x, u); ly[u] = smem_ld2(p.y, u); lz[u] = smem_ld2(p.z, u);
+            acc = acc + t[2 * u];
+            acc = acc + t[2 * u + 1];
         }
-        p.x0 += p.ix0; p.y0 += p.iy0; p.z0 += p.iz0;
-        p.x1 += p.ix1; p.y1 += p.iy1; p.z1 += p.iz1;
+#pragma unroll
+        for (int u = 0; u < 2 * S; ++u) t[u] = tn[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 2 * S; ++u) acc = acc + t[u];
+#pragma unroll
+    for (int u = 0; u < S; ++u) {
+        acc = acc + (lx[u].x * ly[u].x) * lz[u].x;
+        acc = acc + (lx[u].y * ly[u].y) * lz[u].y;
     }
     return acc;
 }
 
-ICP_DEV ChainPtrs chain_role(int lane, const double* r2, const double* c2, const double* b2,
-                             const double* ktab)
+// sum of the Huber cost terms in source order (lib.rs:45-50); n2 = number of double2 entries
+// (a multiple of kChainUnroll)
+ICP_DEV_NOINLINE double cost_run(smem_ref rp, int n2)
 {
-    // ktab[k][2*kChainUnroll], k: 0..3 = R00 R01 R10 R11, 4 = 1.0, 5 = 0.0
-    constexpr int KS = 2 * kChainUnroll;
-    constexpr int VAR = 2 * kChainUnroll;
-    ChainPtrs p;
-    auto jac = [&](int j, int col, const double** ptr, int* inc) {
-        if (col < 2) { *ptr = ktab + (2 * j + col) * KS; *inc = 0; }
-        else { *ptr = b2 + j; *inc = VAR; }
-    };
-    if (lane < 12) {
-        const int a = (lane < 9) ? lane / 3 : lane - 9;
-        p.x0 = c2; p.x1 = c2 + 1; p.ix0 = VAR; p.ix1 = VAR;
-        jac(0, a, &p.y0, &p.iy0);
-        jac(1, a, &p.y1, &p.iy1);
-        if (lane < 9) {
-            const int b = lane % 3;
-            jac(0, b, &p.z0, &p.iz0);
-            jac(1, b, &p.z1, &p.iz1);
-        } else {
-            p.z0 = r2; p.z1 = r2 + 1; p.iz0 = VAR; p.iz1 = VAR;
+    double e = 0.0;
+    double2 v[kChainUnroll];
+#pragma unroll
+    for (int u = 0; u < kChainUnroll; ++u) v[u] = smem_ld2(rp, u);
+    for (int i = kChainUnroll; i < n2; i += kChainUnroll) {
+        rp = smem_adv2(rp, kChainUnroll);
+#pragma unroll
+        for (int u = 0; u < kChainUnroll; ++u) {
+            const double2 w = v[u];
+            v[u] = smem_ld2(rp, u);
+            e = e + w.x;
+            e = e + w.y;
         }
-    } else {
-        p.x0 = p.x1 = ktab + 5 * KS;
-        p.y0 = p.y1 = p.z0 = p.z1 = ktab + 4 * KS;
-        p.ix0 = p.ix1 = p.iy0 = p.iy1 = p.iz0 = p.iz1 = 0;
     }
+#pragma unroll
+    for (int u = 0; u < kChainUnroll; ++u) {
+        e = e + v[u].x;
+        e = e + v[u].y;
+    }
+    return e;
+}
+
+// ktab: K0[kChainStage] = (R00, R10) repeated, then (after a 16-byte phase shift) K1 = (R01, R11)
+constexpr int kChainK1 = kChainUnroll + 1;   // offset of K1 in double2 units
+
+ICP_DEV ChainPtrs chain_role(int lane, const double2* r2, const double2* c2, const double2* b2,
+                             const double2* ktab)
+{
+    ChainPtrs p;
+    const int l = lane < 12 ? lane : 0;
+    const int a = (l < 9) ? l / 3 : l - 9;
+    const int b = (l < 9) ? l % 3 : 3;
+    p.x = smem_ref_of(c2);
+    if (a < 2) { p.y = smem_ref_of(ktab + a * kChainK1); p.iy = 0; } else { p.y = smem_ref_of(b2); p.iy = kChainStage; }
+    if (b < 2) { p.z = smem_ref_of(ktab + b * kChainK1); p.iz = 0; }
+    else { p.z = smem_ref_of((b == 2) ? b2 : r2); p.iz = kChainStage; }
     return p;
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int THREADS, int PPT, int DIM, bool SHARED_TARGET, int MINB>
+// calc_stddevs (stats.rs:49-60) over the CTA's residuals: per-axis median, then the median of
+// |r - median|, sigma = 1.4826 * MAD (stats.rs:39-47).  est_med / est_sigma carry the previous
+// evaluation's result in and this one's out: they only steer the (exact) selection's bin map.
+// One inlined copy of the selection runs both stages.
+template <int THREADS, int PPT, class KeySrc>
+ICP_DEV int cta_calc_stddevs(SelShared* sel, const KeySrc& ks, int n, double est_med[2], double est_sigma[2],
+                             int hist_par, double sigma[2])
+{
+    double med[2] = {0., 0.}, out[2] = {0., 0.};
+#pragma unroll 1
+    for (int stage = 0; stage < 2; ++stage) {
+        bool ev[2];
+        float elo[2], esc[2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+            ev[a] = stage == 0 ? sel_fast_params(est_med[a] - 3.0 * est_sigma[a], 6.0 * est_sigma[a], &elo[a], &esc[a])
+                               : sel_fast_params(0.0, 3.0 * est_sigma[a], &elo[a], &esc[a]);
+        hist_par = block_median2<THREADS, PPT>(sel, ks, n, stage, med, ev, elo, esc, hist_par, out);
+        if (stage == 0) { med[0] = out[0]; med[1] = out[1]; }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        sigma[a] = kPpf34 * out[a];
+        est_med[a] = med[a];
+        est_sigma[a] = sigma[a];
+    }
+    return hist_par;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int THREADS, int PPT, int DIM, bool SHARED_TARGET, int MINB, bool ORDERED>
 ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
 {
     constexpr int NW = THREADS / 32;
     constexpr int NCAP = THREADS * PPT;
-    static_assert(NCAP % kChainUnroll == 0, "row arrays are padded to the chain unroll");
+    static_assert(NCAP % (2 * kChainUnroll) == 0, "row arrays are padded to twice the chain unroll");
     ICP_SHARED_DYN(smem);
-    const FusedLayout L = fused_layout(DIM, NCAP, p.mcap, p.cell_budget, SHARED_TARGET);
+    const FusedLayout L = fused_layout(DIM, NCAP, p.mcap, p.cell_budget, SHARED_TARGET, ORDERED);
     unsigned char* U = smem;
     SelShared* sel = reinterpret_cast<SelShared*>(smem + L.off_sel);
     FusedCtl* ctl = reinterpret_cast<FusedCtl*>(smem + L.off_ctl);
     double* r2 = reinterpret_cast<double*>(U + L.gn_r);
-    double* c2 = reinterpret_cast<double*>(U + L.gn_c);
-    double* b2 = reinterpret_cast<double*>(U + L.gn_b);
     double* rho = reinterpret_cast<double*>(U + L.gn_rho);
-    double* ktab = reinterpret_cast<double*>(U + L.gn_const);
-    double2* r2v = reinterpret_cast<double2*>(r2);
-    double2* c2v = reinterpret_cast<double2*>(c2);
-    double2* b2v = reinterpret_cast<double2*>(b2);
+    double2* r2v = reinterpret_cast<double2*>(U + L.gn_r);
+    double2* c2v = reinterpret_cast<double2*>(U + L.gn_c);
+    double2* b2v = reinterpret_cast<double2*>(U + L.gn_b);
+    double2* ktab = reinterpret_cast<double2*>(U + L.gn_const);
+    // chain / cost-sum warps rotate with the CTA's residency slot so that co-resident CTAs put
+    // their serial phases on different SM sub-partitions (warp w issues on sub-partition w % 4)
+    const int slot = (int)(blockIdx.x / (p.sm_count > 0 ? p.sm_count : 1u));
+    const int chain_warp = slot % NW;
+    const int cost_warp = (slot + 1) % NW;
 
     const int tid = (int)threadIdx.x, lane = lane_id(), warp = warp_id();
     unsigned char* slab = p.workspace + (size_t)blockIdx.x * p.ws_stride;
@@ -350,8 +454,9 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
         if (!SHARED_TARGET) {
             if (m > 0) {
                 geom = cta_build_grid<THREADS, DIM>(dst, m, U, L, ctl, p.cell_budget);
-                for (uint32_t o = (uint32_t)tid * 16u; o < L.nn_bytes; o += THREADS * 16u)
-                    *reinterpret_cast<uint4*>(slab + o) = *reinterpret_cast<const uint4*>(U + o);
+                if (ORDERED)
+                    for (uint32_t o = (uint32_t)tid * 16u; o < L.nn_bytes; o += THREADS * 16u)
+                        *reinterpret_cast<uint4*>(slab + o) = *reinterpret_cast<const uint4*>(U + o);
             }
         } else {
             geom = p.target.g;
@@ -359,12 +464,12 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
 
         double est_med[2] = {0., 0.}, est_sigma[2] = {0., 0.};
         uint64_t H = 0;  // meaningful in thread 0
-        const int npad = ((n + kChainUnroll - 1) / kChainUnroll) * kChainUnroll;
+        const int npad = ((n + 2 * kChainUnroll - 1) / (2 * kChainUnroll)) * (2 * kChainUnroll);
         const uint64_t corr_base = (uint64_t)p.src_off[pair] * (p.corr_mode == 2 ? p.max_iter : 1u);
 
         for (uint32_t it = 0; it < p.max_iter; ++it) {
             // ---- stage the sorted target (the union region was overwritten by the IRLS rows)
-            if (!SHARED_TARGET && it > 0 && m > 0) {
+            if (ORDERED && !SHARED_TARGET && it > 0 && m > 0) {
                 for (uint32_t o = (uint32_t)tid * 16u; o < L.nn_bytes; o += THREADS * 16u)
                     *reinterpret_cast<uint4*>(U + o) = *reinterpret_cast<const uint4*>(slab + o);
                 __syncthreads();
@@ -372,44 +477,77 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
             // ---- transform (lib.rs:113-116) + correspondence search (lib.rs:118-124)
             double sx[PPT], sy[PPT], dx[PPT], dy[PPT];
             uint64_t hpart = 0;
+            auto search_one = [&](int i, double qx, double qy, double* ox, double* oy) {
+                const double pz = (DIM == 3) ? src[(size_t)i * DIM + 2] : 0.0;  // transform_xy keeps z (lib.rs:52-57)
+                int idx;
+                if (SHARED_TARGET) {
+                    GridView<DIM, uint32_t, uint32_t> gv;
+                    gv.x = p.target.x; gv.y = p.target.y; gv.z = p.target.z;
+                    gv.idx = p.target.idx; gv.cstart = p.target.cstart; gv.g = geom;
+                    NnResult<DIM, uint32_t, uint32_t> r = grid_nn_search(gv, qx, qy, pz);
+                    *ox = gv.x[r.pos]; *oy = gv.y[r.pos];
+                    idx = r.idx;
+                } else {
+                    GridView<DIM, uint16_t, uint16_t> gv;
+                    gv.x = reinterpret_cast<const double*>(U + L.nn_x);
+                    gv.y = reinterpret_cast<const double*>(U + L.nn_y);
+                    gv.z = reinterpret_cast<const double*>(U + L.nn_z);
+                    gv.idx = reinterpret_cast<const uint16_t*>(U + L.nn_idx);
+                    gv.cstart = reinterpret_cast<const uint16_t*>(U + L.nn_cell);
+                    gv.g = geom;
+                    NnResult<DIM, uint16_t, uint16_t> r = grid_nn_search(gv, qx, qy, pz);
+                    *ox = gv.x[r.pos]; *oy = gv.y[r.pos];
+                    idx = r.idx;
+                }
+                hpart += mix64(((uint64_t)(uint32_t)i << 32) | (uint64_t)(uint32_t)idx);
+                if (p.out_corr) {
+                    if (p.corr_mode == 2) p.out_corr[corr_base + (uint64_t)it * (uint64_t)n + (uint64_t)i] = idx;
+                    else if (p.corr_mode == 1 && it + 1 == p.max_iter) p.out_corr[corr_base + (uint64_t)i] = idx;
+                }
+            };
+            if (ORDERED) {
 #pragma unroll
-            for (int k = 0; k < PPT; ++k) {
-                const int i = tid + k * THREADS;
-                sx[k] = 0.; sy[k] = 0.; dx[k] = 0.; dy[k] = 0.;
-                if (i < n) {
-                    const double px = src[(size_t)i * DIM + 0], py = src[(size_t)i * DIM + 1];
-                    const double pz = (DIM == 3) ? src[(size_t)i * DIM + 2] : 0.0;
-                    transform_apply(T, px, py, &sx[k], &sy[k]);   // transform_xy keeps z (lib.rs:52-57)
-                    int idx;
-                    if (SHARED_TARGET) {
-                        GridView<DIM, uint32_t, uint32_t> gv;
-                        gv.x = p.target.x; gv.y = p.target.y; gv.z = p.target.z;
-                        gv.idx = p.target.idx; gv.cstart = p.target.cstart; gv.g = geom;
-                        NnResult<DIM, uint32_t, uint32_t> r = grid_nn_search(gv, sx[k], sy[k], pz);
-                        dx[k] = gv.x[r.pos]; dy[k] = gv.y[r.pos];
-                        idx = r.idx;
-                    } else {
-                        GridView<DIM, uint16_t, uint16_t> gv;
-                        gv.x = reinterpret_cast<const double*>(U + L.nn_x);
-                        gv.y = reinterpret_cast<const double*>(U + L.nn_y);
-                        gv.z = reinterpret_cast<const double*>(U + L.nn_z);
-                        gv.idx = reinterpret_cast<const uint16_t*>(U + L.nn_idx);
-                        gv.cstart = reinterpret_cast<const uint16_t*>(U + L.nn_cell);
-                        gv.g = geom;
-                        NnResult<DIM, uint16_t, uint16_t> r = grid_nn_search(gv, sx[k], sy[k], pz);
-                        dx[k] = gv.x[r.pos]; dy[k] = gv.y[r.pos];
-                        idx = r.idx;
+                for (int k = 0; k < PPT; ++k) {
+                    const int i = tid + k * THREADS;
+                    sx[k] = 0.; sy[k] = 0.; dx[k] = 0.; dy[k] = 0.;
+                    if (i < n) {
+                        transform_apply(T, src[(size_t)i * DIM + 0], src[(size_t)i * DIM + 1], &sx[k], &sy[k]);
+                        search_one(i, sx[k], sy[k], &dx[k], &dy[k]);
                     }
-                    hpart += mix64(((uint64_t)(uint32_t)i << 32) | (uint64_t)(uint32_t)idx);
-                    if (p.out_corr) {
-                        if (p.corr_mode == 2) p.out_corr[corr_base + (uint64_t)it * (uint64_t)n + (uint64_t)i] = idx;
-                        else if (p.corr_mode == 1 && it + 1 == p.max_iter) p.out_corr[corr_base + (uint64_t)i] = idx;
+                }
+            } else {
+                // one (not PPT) inlined copy of the search: queries go through a shared scratch
+                // slot per point (the thread's own), the matched target point comes back the same way
+#pragma unroll
+                for (int k = 0; k < PPT; ++k) {
+                    const int i = tid + k * THREADS;
+                    sx[k] = 0.; sy[k] = 0.; dx[k] = 0.; dy[k] = 0.;
+                    if (i < n) {
+                        transform_apply(T, src[(size_t)i * DIM + 0], src[(size_t)i * DIM + 1], &sx[k], &sy[k]);
+                        double2 q;
+                        q.x = sx[k]; q.y = sy[k];
+                        r2v[i] = q;
+                    }
+                }
+#pragma unroll 1
+                for (int i = tid; i < n; i += THREADS) {
+                    const double2 q = r2v[i];
+                    double2 d;
+                    search_one(i, q.x, q.y, &d.x, &d.y);
+                    r2v[i] = d;
+                }
+#pragma unroll
+                for (int k = 0; k < PPT; ++k) {
+                    const int i = tid + k * THREADS;
+                    if (i < n) {
+                        const double2 d = r2v[i];
+                        dx[k] = d.x; dy[k] = d.y;
                     }
                 }
             }
             hpart = warp_sum_u64(hpart);
             if (lane == 0) ctl->hash_part[warp] = hpart;
-            __syncthreads();  // search done: the union region becomes the IRLS row arrays
+            __syncthreads();  // search done (ordered: the union region becomes the IRLS row arrays)
             if (tid == 0) {
                 uint64_t h = 0;
                 for (int w = 0; w < NW; ++w) h += ctl->hash_part[w];
@@ -424,100 +562,144 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                 why = kBreakNone;  // check_input_size (lib.rs:186-189,225-228)
             } else {
                 for (int inner = 0; inner < kInnerMaxIter; ++inner) {
-                    // residuals (lib.rs:230-234)
+                    double sigma[2];
+                    double jtj[9], jtr[3], error;
+                    if (ORDERED) {
+                        // residuals (lib.rs:230-234)
 #pragma unroll
-                    for (int k = 0; k < PPT; ++k) {
-                        const int i = tid + k * THREADS;
-                        if (i < npad) {
-                            double2 rr;
-                            rr.x = 0.; rr.y = 0.;
-                            if (i < n) {
-                                double tx_, ty_;
-                                transform_apply(Ti, sx[k], sy[k], &tx_, &ty_);
-                                rr.x = tx_ - dx[k];
-                                rr.y = ty_ - dy[k];
+                        for (int k = 0; k < PPT; ++k) {
+                            const int i = tid + k * THREADS;
+                            if (i < npad) {
+                                double2 rr;
+                                rr.x = 0.; rr.y = 0.;
+                                if (i < n) {
+                                    double tx_, ty_;
+                                    transform_apply(Ti, sx[k], sy[k], &tx_, &ty_);
+                                    rr.x = tx_ - dx[k];
+                                    rr.y = ty_ - dy[k];
+                                }
+                                r2v[i] = rr;
                             }
-                            r2v[i] = rr;
                         }
-                    }
-                    for (int q = tid; q < 6 * 2 * kChainUnroll; q += THREADS) {
-                        const int kk = q / (2 * kChainUnroll);
-                        ktab[q] = kk == 0 ? Ti.r00 : kk == 1 ? Ti.r01 : kk == 2 ? Ti.r10
-                                : kk == 3 ? Ti.r11 : kk == 4 ? 1.0 : 0.0;
-                    }
-                    __syncthreads();
-                    // calc_stddevs (stats.rs:49-60): per-axis median, then median of |r - median|
-                    double med[2], mad[2], sigma[2];
-                    {
-                        bool ev[2];
-                        double elo[2], esc[2];
-                        const double zero2[2] = {0., 0.};
-#pragma unroll
-                        for (int a = 0; a < 2; ++a) {
-                            esc[a] = (double)kSelBins / (6.0 * est_sigma[a]);
-                            elo[a] = est_med[a] - 3.0 * est_sigma[a];
-                            ev[a] = est_sigma[a] > 0.0 && esc[a] < 1e300 && fabs(elo[a]) < 1e300;
+                        if (tid < 2 * kChainUnroll) {
+                            double2 kv;
+                            if (tid < kChainUnroll) { kv.x = Ti.r00; kv.y = Ti.r10; }
+                            else { kv.x = Ti.r01; kv.y = Ti.r11; }
+                            ktab[tid < kChainUnroll ? tid : tid - kChainUnroll + kChainK1] = kv;
                         }
-                        hist_par = block_median2<THREADS>(sel, r2, n, 0, zero2, ev, elo, esc, hist_par, med);
+                        __syncthreads();
+                        // calc_stddevs (stats.rs:49-60): per-axis median, then median of |r - median|
+                        KeysInShared ks;
+                        ks.v = r2v;
+                        hist_par = cta_calc_stddevs<THREADS, PPT>(sel, ks, n, est_med, est_sigma, hist_par, sigma);
+                        // row weights (lib.rs:245-250), Jacobian third column (lib.rs:176-184),
+                        // Huber cost terms (lib.rs:47-48)
+                        const double g0 = 1. / sigma[0], g1 = 1. / sigma[1];
 #pragma unroll
-                        for (int a = 0; a < 2; ++a) {
-                            esc[a] = (double)kSelBins / (3.0 * est_sigma[a]);
-                            elo[a] = 0.0;
+                        for (int k = 0; k < PPT; ++k) {
+                            const int i = tid + k * THREADS;
+                            if (i < npad) {
+                                double2 cc, bb;
+                                double rh = 0.;
+                                cc.x = 0.; cc.y = 0.; bb.x = 0.; bb.y = 0.;
+                                if (i < n) {
+                                    const double2 rr = r2v[i];
+                                    if (sigma[0] != 0.) cc.x = huber_drho_of_residual(rr.x) * g0;
+                                    if (sigma[1] != 0.) cc.y = huber_drho_of_residual(rr.y) * g1;
+                                    const double a0 = -sy[k], a1 = sx[k];
+                                    bb.x = Ti.r00 * a0 + Ti.r01 * a1;
+                                    bb.y = Ti.r10 * a0 + Ti.r11 * a1;
+                                    rh = huber_rho(rr.x * rr.x + rr.y * rr.y);
+                                }
+                                c2v[i] = cc;
+                                b2v[i] = bb;
+                                rho[i] = rh;
+                            }
                         }
-                        hist_par = block_median2<THREADS>(sel, r2, n, 1, med, ev, elo, esc, hist_par, mad);
-#pragma unroll
-                        for (int a = 0; a < 2; ++a) {
-                            sigma[a] = kPpf34 * mad[a];   // stats.rs:39-47
-                            est_med[a] = med[a];
-                            est_sigma[a] = sigma[a];
+                        __syncthreads();
+                        // ordered accumulation
+                        if (warp == chain_warp) {
+                            const double s = chain_run(chain_role(lane, r2v, c2v, b2v, ktab), npad / kChainStage);
+                            if (lane < 12) ctl->sums[lane] = s;
                         }
-                    }
-                    // row weights (lib.rs:245-250), Jacobian third column (lib.rs:176-184),
-                    // Huber cost terms (lib.rs:47-48)
-                    const double g0 = 1. / sigma[0], g1 = 1. / sigma[1];
+                        if (warp == cost_warp) {
+                            const double e = cost_run(smem_ref_of(reinterpret_cast<const double2*>(rho)), npad / 2);
+                            if (lane == 0) ctl->sums[12] = e;
+                        }
+                        __syncthreads();
 #pragma unroll
-                    for (int k = 0; k < PPT; ++k) {
-                        const int i = tid + k * THREADS;
-                        if (i < npad) {
-                            double2 cc, bb;
-                            double rh = 0.;
-                            cc.x = 0.; cc.y = 0.; bb.x = 0.; bb.y = 0.;
+                        for (int q = 0; q < 9; ++q) jtj[q] = ctl->sums[q];
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) jtr[q] = ctl->sums[9 + q];
+                        error = ctl->sums[12];
+                    } else {
+                        // residuals (lib.rs:230-234) stay in registers
+                        double2 rr[PPT];
+#pragma unroll
+                        for (int k = 0; k < PPT; ++k) {
+                            double tx_, ty_;
+                            transform_apply(Ti, sx[k], sy[k], &tx_, &ty_);
+                            rr[k].x = tx_ - dx[k];
+                            rr[k].y = ty_ - dy[k];
+                        }
+                        KeysInRegisters<PPT> ks;
+                        ks.v = rr;
+                        hist_par = cta_calc_stddevs<THREADS, PPT>(sel, ks, n, est_med, est_sigma, hist_par, sigma);
+                        // row weights (lib.rs:245-250), Jacobian (lib.rs:176-184), Huber cost (lib.rs:47-48)
+                        // and their sums, reduced as a fixed tree: per-thread partials over the
+                        // thread's points (ascending), split butterfly across lanes, warps in order
+                        const double g0 = 1. / sigma[0], g1 = 1. / sigma[1];
+                        double acc[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) acc[q] = 0.;
+#pragma unroll
+                        for (int k = 0; k < PPT; ++k) {
+                            const int i = tid + k * THREADS;
                             if (i < n) {
-                                const double2 rr = r2v[i];
-                                if (sigma[0] != 0.) cc.x = huber_drho(rr.x * rr.x) * g0;
-                                if (sigma[1] != 0.) cc.y = huber_drho(rr.y * rr.y) * g1;
                                 const double a0 = -sy[k], a1 = sx[k];
-                                bb.x = Ti.r00 * a0 + Ti.r01 * a1;
-                                bb.y = Ti.r10 * a0 + Ti.r11 * a1;
-                                rh = huber_rho(rr.x * rr.x + rr.y * rr.y);
+                                const double J0[3] = {Ti.r00, Ti.r01, Ti.r00 * a0 + Ti.r01 * a1};
+                                const double J1[3] = {Ti.r10, Ti.r11, Ti.r10 * a0 + Ti.r11 * a1};
+                                if (sigma[0] != 0.) {
+                                    const double c = huber_drho_of_residual(rr[k].x) * g0;
+#pragma unroll
+                                    for (int a = 0; a < 3; ++a) {
+                                        const double pa = c * J0[a];
+#pragma unroll
+                                        for (int b = 0; b < 3; ++b) acc[3 * a + b] = acc[3 * a + b] + pa * J0[b];
+                                        acc[9 + a] = acc[9 + a] + pa * rr[k].x;
+                                    }
+                                }
+                                if (sigma[1] != 0.) {
+                                    const double c = huber_drho_of_residual(rr[k].y) * g1;
+#pragma unroll
+                                    for (int a = 0; a < 3; ++a) {
+                                        const double pa = c * J1[a];
+#pragma unroll
+                                        for (int b = 0; b < 3; ++b) acc[3 * a + b] = acc[3 * a + b] + pa * J1[b];
+                                        acc[9 + a] = acc[9 + a] + pa * rr[k].y;
+                                    }
+                                }
+                                acc[12] = acc[12] + huber_rho(rr[k].x * rr[k].x + rr[k].y * rr[k].y);
                             }
-                            c2v[i] = cc;
-                            b2v[i] = bb;
-                            rho[i] = rh;
                         }
-                    }
-                    __syncthreads();
-                    // ordered accumulation
-                    if (warp == 0) {
-                        const double s = chain_run(chain_role(lane, r2, c2, b2, ktab), npad / kChainUnroll);
-                        if (lane < 12) ctl->sums[lane] = s;
-                    }
-                    if (warp == (NW > 1 ? 1 : 0)) {
-                        double e = 0.0;
-                        for (int i = 0; i < npad; i += kChainUnroll) {
+                        warp_reduce16(acc);
+                        // (the previous evaluation's readers of ctl->red have passed the barriers of
+                        // this evaluation's selection before anyone writes here)
+                        if ((lane & 1) == 0) ctl->red[warp][warp_reduce16_owner(lane)] = acc[0];
+                        __syncthreads();
+                        double tot = 0.;
+                        if (lane < 16) {
+                            tot = ctl->red[0][lane];
+                            for (int w = 1; w < NW; ++w) tot = tot + ctl->red[w][lane];
+                        }
 #pragma unroll
-                            for (int u = 0; u < kChainUnroll; ++u) e = e + rho[i + u];
-                        }
-                        if (lane == 0) ctl->sums[12] = e;
+                        for (int q = 0; q < 9; ++q) jtj[q] = shfl_f64(tot, q);
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) jtr[q] = shfl_f64(tot, 9 + q);
+                        error = shfl_f64(tot, 12);
                     }
-                    __syncthreads();
                     // solve + break tests + update: every thread, identically (lib.rs:67-81)
-                    double jtj[9], jtr[3], delta[3];
-#pragma unroll
-                    for (int q = 0; q < 9; ++q) jtj[q] = ctl->sums[q];
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) jtr[q] = ctl->sums[9 + q];
-                    const double error = ctl->sums[12];
+                    double delta[3];
                     if (!solve_normal_equations(jtj, jtr, delta)) { why = kBreakNone; break; }
                     if ((delta[0] * delta[0] + delta[1] * delta[1]) + delta[2] * delta[2] < kDeltaNormThreshold) {
                         why = kBreakDelta;

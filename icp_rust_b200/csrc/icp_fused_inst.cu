@@ -4,12 +4,11 @@
 
 #define ICP_CAT_(a, b) a##b
 #define ICP_CAT(a, b) ICP_CAT_(a, b)
+#define ICP_K(DIM, SHARED) \
+    icp_fused_kernel<ICP_INST_THREADS, ICP_INST_PPT, DIM, SHARED, ICP_INST_MINB, (ICP_INST_ORDERED != 0)>
 
 namespace icp {
 extern const Instance ICP_CAT(kFusedInstance, ICP_INST_ID) = {
-    ICP_INST_THREADS, ICP_INST_PPT, ICP_INST_MINB,
-    {{icp_fused_kernel<ICP_INST_THREADS, ICP_INST_PPT, 2, false, ICP_INST_MINB>,
-      icp_fused_kernel<ICP_INST_THREADS, ICP_INST_PPT, 2, true, ICP_INST_MINB>},
-     {icp_fused_kernel<ICP_INST_THREADS, ICP_INST_PPT, 3, false, ICP_INST_MINB>,
-      icp_fused_kernel<ICP_INST_THREADS, ICP_INST_PPT, 3, true, ICP_INST_MINB>}}};
+    ICP_INST_THREADS, ICP_INST_PPT, ICP_INST_MINB, (ICP_INST_ORDERED != 0),
+    {{ICP_K(2, false), ICP_K(2, true)}, {ICP_K(3, false), ICP_K(3, true)}}};
 }  // namespace icp

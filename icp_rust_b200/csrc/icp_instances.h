@@ -1,5 +1,5 @@
 // icp_instances.h — table of the compiled fused-kernel instances (one translation unit each,
-// icp_fused_inst.cu built with -DICP_INST_ID/THREADS/PPT/MINB).
+// icp_fused_inst.cu built with -DICP_INST_ID/THREADS/PPT/MINB/ORDERED; list in the Makefile).
 #pragma once
 #include "icp_fused.cuh"
 
@@ -9,10 +9,15 @@ typedef void (*FusedKernel)(FusedParams);
 
 struct Instance {
     int threads, ppt, minb;
+    bool ordered;         // reference-order sums (bit-exact) vs warp-tree reductions
     FusedKernel k[2][2];  // [dim-2][shared target]
 };
 
-extern const Instance kFusedInstance0, kFusedInstance1, kFusedInstance2, kFusedInstance3,
-    kFusedInstance4, kFusedInstance5;
+#define ICP_DECLARE_INSTANCE(id) extern const Instance kFusedInstance##id;
+ICP_DECLARE_INSTANCE(0) ICP_DECLARE_INSTANCE(1) ICP_DECLARE_INSTANCE(2) ICP_DECLARE_INSTANCE(3)
+ICP_DECLARE_INSTANCE(4) ICP_DECLARE_INSTANCE(5) ICP_DECLARE_INSTANCE(6) ICP_DECLARE_INSTANCE(7)
+ICP_DECLARE_INSTANCE(8) ICP_DECLARE_INSTANCE(9) ICP_DECLARE_INSTANCE(10) ICP_DECLARE_INSTANCE(11)
+ICP_DECLARE_INSTANCE(12) ICP_DECLARE_INSTANCE(13)
+#undef ICP_DECLARE_INSTANCE
 
 }  // namespace icp

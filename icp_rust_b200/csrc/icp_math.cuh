@@ -195,6 +195,20 @@ ICP_DEV double huber_drho(double e)
     return kHuberK / sqrt(e);
 }
 
+// huber_drho(r * r) for a residual component r (lib.rs:250).  In radix 2 with round-to-nearest,
+// sqrt(fl(r*r)) == |r| exactly whenever r*r neither underflows nor overflows (Boldo, "Stupid is
+// as stupid does: taking the square root of the square of a floating-point number", 2015), so
+// the square root is skipped: k / sqrt(e) == k / |r|.  The branch e <= k*k already covers the
+// underflow side; an overflowing e keeps the literal formula.
+ICP_DEV double huber_drho_of_residual(double r)
+{
+    const double k2 = kHuberK * kHuberK;
+    const double e = r * r;
+    if (e <= k2) return 1.;
+    if (e > kF64Max) return kHuberK / sqrt(e);
+    return kHuberK / fabs(r);
+}
+
 // ---------------------------------------------------------------------------------------------
 // src/transform.rs:22-24: rot * p + t (nalgebra gemv sums columns in ascending order)
 ICP_DEV void transform_apply(const Transform& T, double x, double y, double* ox, double* oy)

@@ -17,12 +17,15 @@ struct StatsParams {
                                //    result as the estimate (exercises the value-uniform map)
 };
 
+constexpr int kStatsThreads = 128;
+constexpr int kStatsPpt = 24;   // keys per thread the selection can hold: sets of up to 3072 points
+
 ICP_HD uint32_t stats_smem_bytes(int cap)
 {
     return (uint32_t)(16u * (uint32_t)cap + 16u + sizeof(SelShared));
 }
 
-template <int THREADS>
+template <int THREADS, int PPT>
 ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, 1) calc_stddevs_kernel(StatsParams p)
 {
     ICP_SHARED_DYN(smem);
@@ -45,25 +48,22 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, 1) calc_stddevs_kernel(StatsParams p)
         __syncthreads();
         int par = 0;
         double med[2], mad[2];
+        KeysInShared ks;
+        ks.v = reinterpret_cast<const double2*>(r2);
         bool ev[2] = {false, false};
-        double elo[2] = {0., 0.}, esc[2] = {0., 0.};
+        float elo[2] = {0.f, 0.f}, esc[2] = {0.f, 0.f};
         const double zero2[2] = {0., 0.};
-        par = block_median2<THREADS>(sel, r2, n, 0, zero2, ev, elo, esc, par, med);
-        par = block_median2<THREADS>(sel, r2, n, 1, med, ev, elo, esc, par, mad);
+        par = block_median2<THREADS, PPT>(sel, ks, n, 0, zero2, ev, elo, esc, par, med);
+        par = block_median2<THREADS, PPT>(sel, ks, n, 1, med, ev, elo, esc, par, mad);
         if (p.mode == 1) {
             double med2[2], mad2[2];
             for (int a = 0; a < 2; ++a) {
                 const double s = kPpf34 * mad[a];
-                esc[a] = (double)kSelBins / (6.0 * s);
-                elo[a] = med[a] - 3.0 * s;
-                ev[a] = s > 0.0 && esc[a] < 1e300 && fabs(elo[a]) < 1e300;
+                ev[a] = sel_fast_params(med[a] - 3.0 * s, 6.0 * s, &elo[a], &esc[a]);
             }
-            par = block_median2<THREADS>(sel, r2, n, 0, zero2, ev, elo, esc, par, med2);
-            for (int a = 0; a < 2; ++a) {
-                esc[a] = (double)kSelBins / (3.0 * kPpf34 * mad[a]);
-                elo[a] = 0.0;
-            }
-            par = block_median2<THREADS>(sel, r2, n, 1, med2, ev, elo, esc, par, mad2);
+            par = block_median2<THREADS, PPT>(sel, ks, n, 0, zero2, ev, elo, esc, par, med2);
+            for (int a = 0; a < 2; ++a) ev[a] = ev[a] && sel_fast_params(0.0, 3.0 * kPpf34 * mad[a], &elo[a], &esc[a]);
+            par = block_median2<THREADS, PPT>(sel, ks, n, 1, med2, ev, elo, esc, par, mad2);
             for (int a = 0; a < 2; ++a) { med[a] = med2[a]; mad[a] = mad2[a]; }
         }
         if (tid < 2) {

@@ -14,10 +14,22 @@
 #include <stdint.h>
 #define ICP_DEV __device__ __forceinline__
 #define ICP_DEV_NOINLINE static __device__ __noinline__
+#define ICP_DEV_MEMBER __device__ __forceinline__
 #define ICP_HD __host__ __device__ __forceinline__
 #define ICP_GLOBAL __global__
-#define ICP_SHARED_DYN(name) extern __shared__ __align__(16) unsigned char name[]
+#define ICP_SHARED_DYN(name) extern __shared__ __align__(128) unsigned char name[]
 #define ICP_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
+// Shared-memory reference to a double2 array that keeps its address space across an out-of-line
+// call (a plain pointer would degrade to generic loads there).
+typedef uint32_t smem_ref;
+static __device__ __forceinline__ smem_ref smem_ref_of(const double2* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+static __device__ __forceinline__ smem_ref smem_adv2(smem_ref r, int n) { return r + 16u * (uint32_t)n; }
+static __device__ __forceinline__ double2 smem_ld2(smem_ref r, int idx)
+{
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(r + 16u * (uint32_t)idx));
+    return v;
+}
 #endif
 
 #define ICP_FULL_MASK 0xffffffffu

@@ -144,6 +144,11 @@ inline const uint32_t* warp_exchange(uint32_t v)
 // ------------------------------------------------------------------ CUDA surface used by the kernels
 #define ICP_DEV static inline
 #define ICP_DEV_NOINLINE static inline
+#define ICP_DEV_MEMBER inline
+typedef const double2* smem_ref;
+static inline smem_ref smem_ref_of(const double2* p) { return p; }
+static inline smem_ref smem_adv2(smem_ref r, int n) { return r + n; }
+static inline double2 smem_ld2(smem_ref r, int idx) { return r[idx]; }
 #define ICP_HD static inline
 #define ICP_GLOBAL static inline
 #define ICP_SHARED_DYN(name) unsigned char* name = simt::st().cta->smem.data()
@@ -218,6 +223,10 @@ static inline unsigned long long atomicMax(unsigned long long* p, unsigned long 
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __double2int_rd(double v) { return (int)std::floor(v); }
+static inline float __double2float_rn(double v) { return (float)v; }
+static inline int __float2int_rd(float v) { return (int)std::floor(v); }
+using std::fmaxf;
+using std::fminf;
 static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
 using std::cbrt;

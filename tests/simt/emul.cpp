@@ -10,10 +10,11 @@
 using namespace icp;
 
 template <int THREADS, int PPT, int DIM>
-static void run_fused(FusedParams p, unsigned grid)
+static void run_fused(FusedParams p, unsigned grid, bool ordered)
 {
-    const FusedLayout L = fused_layout(DIM, THREADS * PPT, p.mcap, p.cell_budget, false);
-    simt::launch(grid, THREADS, L.total, [&] { icp_fused_kernel<THREADS, PPT, DIM, false, 1>(p); });
+    const FusedLayout L = fused_layout(DIM, THREADS * PPT, p.mcap, p.cell_budget, false, ordered);
+    if (ordered) simt::launch(grid, THREADS, L.total, [&] { icp_fused_kernel<THREADS, PPT, DIM, false, 1, true>(p); });
+    else simt::launch(grid, THREADS, L.total, [&] { icp_fused_kernel<THREADS, PPT, DIM, false, 1, false>(p); });
 }
 
 extern "C" int simt_set_schedule(int mode)
@@ -26,7 +27,7 @@ extern "C" int simt_set_schedule(int mode)
 // 2 -> 64 x 2 (tiny), 3 -> 32 x 4 (single warp).
 extern "C" int simt_icp_fused(int dim, int variant, unsigned grid, const double* src, const uint32_t* src_off,
                               const double* dst, const uint32_t* dst_off, const double* init_T, uint32_t B,
-                              uint32_t max_iter, int corr_mode, int cell_budget, double* out_T, uint32_t* out_inner,
+                              uint32_t max_iter, int corr_mode, int cell_budget, int ordered, double* out_T, uint32_t* out_inner,
                               int32_t* out_corr, uint64_t* out_hash, int32_t* out_status)
 {
     uint32_t counter = 0;
@@ -39,21 +40,21 @@ extern "C" int simt_icp_fused(int dim, int variant, unsigned grid, const double*
     p.out_T = out_T; p.out_inner = out_inner; p.out_corr = out_corr; p.out_hash = out_hash;
     p.out_status = out_status; p.out_error = &err; p.work_counter = &counter;
     p.pair_begin = 0; p.pair_end = B; p.max_iter = max_iter; p.corr_mode = corr_mode;
-    p.cell_budget = cell_budget; p.mcap = mcap;
-    const FusedLayout L = fused_layout(dim, 128 * 9, mcap, cell_budget, false);
+    p.cell_budget = cell_budget; p.mcap = mcap; p.sm_count = 1;
+    const FusedLayout L = fused_layout(dim, 128 * 9, mcap, cell_budget, false, true);
     std::vector<unsigned char> ws((size_t)grid * (L.nn_bytes + 64));
     p.workspace = ws.data();
     p.ws_stride = L.nn_bytes + 64 - ((L.nn_bytes + 64) % 16);
     if (dim == 2) {
-        if (variant == 0) { p.ncap = 384; run_fused<128, 3, 2>(p, grid); }
-        else if (variant == 1) { p.ncap = 1152; run_fused<128, 9, 2>(p, grid); }
-        else if (variant == 2) { p.ncap = 128; run_fused<64, 2, 2>(p, grid); }
-        else { p.ncap = 128; run_fused<32, 4, 2>(p, grid); }
+        if (variant == 0) { p.ncap = 384; run_fused<128, 3, 2>(p, grid, ordered != 0); }
+        else if (variant == 1) { p.ncap = 1152; run_fused<128, 9, 2>(p, grid, ordered != 0); }
+        else if (variant == 2) { p.ncap = 128; run_fused<64, 2, 2>(p, grid, ordered != 0); }
+        else { p.ncap = 128; run_fused<32, 4, 2>(p, grid, ordered != 0); }
     } else {
-        if (variant == 0) { p.ncap = 384; run_fused<128, 3, 3>(p, grid); }
-        else if (variant == 1) { p.ncap = 1152; run_fused<128, 9, 3>(p, grid); }
-        else if (variant == 2) { p.ncap = 128; run_fused<64, 2, 3>(p, grid); }
-        else { p.ncap = 128; run_fused<32, 4, 3>(p, grid); }
+        if (variant == 0) { p.ncap = 384; run_fused<128, 3, 3>(p, grid, ordered != 0); }
+        else if (variant == 1) { p.ncap = 1152; run_fused<128, 9, 3>(p, grid, ordered != 0); }
+        else if (variant == 2) { p.ncap = 128; run_fused<64, 2, 3>(p, grid, ordered != 0); }
+        else { p.ncap = 128; run_fused<32, 4, 3>(p, grid, ordered != 0); }
     }
     return err;
 }
@@ -67,9 +68,9 @@ extern "C" int simt_calc_stddevs(const double* residuals, const uint32_t* off, u
     p.residuals = residuals; p.off = off; p.out_sigma = out_sigma; p.out_median = out_median;
     p.B = B; p.cap = cap; p.mode = mode;
     const unsigned grid = B < 4 ? (B ? B : 1) : 4;
-    if (threads == 32) simt::launch(grid, 32, stats_smem_bytes(cap), [&] { calc_stddevs_kernel<32>(p); });
-    else if (threads == 256) simt::launch(grid, 256, stats_smem_bytes(cap), [&] { calc_stddevs_kernel<256>(p); });
-    else simt::launch(grid, 128, stats_smem_bytes(cap), [&] { calc_stddevs_kernel<128>(p); });
+    if (threads == 32) simt::launch(grid, 32, stats_smem_bytes(cap), [&] { calc_stddevs_kernel<32, 40>(p); });
+    else if (threads == 256) simt::launch(grid, 256, stats_smem_bytes(cap), [&] { calc_stddevs_kernel<256, 8>(p); });
+    else simt::launch(grid, 128, stats_smem_bytes(cap), [&] { calc_stddevs_kernel<128, kStatsPpt>(p); });
     return 0;
 }
 

@@ -38,7 +38,7 @@ def calc_stddevs(sets, mode=0, threads=128):
     return sig, med
 
 
-def icp_fused(srcs, dsts, init_T, max_iter=20, variant=0, grid=1, corr_mode=2, cell_budget=4096):
+def icp_fused(srcs, dsts, init_T, max_iter=20, variant=0, grid=1, corr_mode=2, cell_budget=4096, ordered=True):
     """srcs/dsts: lists of (n,dim) arrays.  Returns dict like oracle.icp_estimate_batch."""
     B = len(srcs)
     dim = srcs[0].shape[1]
@@ -59,7 +59,8 @@ def icp_fused(srcs, dsts, init_T, max_iter=20, variant=0, grid=1, corr_mode=2, c
     err = lib().simt_icp_fused(
         C.c_int(dim), C.c_int(variant), C.c_uint(grid), src.ctypes.data_as(_dp), so.ctypes.data_as(_u32p),
         dst.ctypes.data_as(_dp), do.ctypes.data_as(_u32p), T0.ctypes.data_as(_dp), C.c_uint32(B),
-        C.c_uint32(max_iter), C.c_int(corr_mode), C.c_int(cell_budget), out_T.ctypes.data_as(_dp),
+        C.c_uint32(max_iter), C.c_int(corr_mode), C.c_int(cell_budget), C.c_int(1 if ordered else 0),
+        out_T.ctypes.data_as(_dp),
         inner.ctypes.data_as(_u32p), corr.ctypes.data_as(C.POINTER(C.c_int32)),
         hashes.ctypes.data_as(C.POINTER(C.c_uint64)), status.ctypes.data_as(C.POINTER(C.c_int32)))
     return {"T": out_T, "inner": inner[:, :max_iter], "corr": corr, "corr_hash": hashes, "status": status,
