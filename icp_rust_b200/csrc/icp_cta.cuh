@@ -9,6 +9,7 @@
 
 namespace icp {
 
+// @region warp_utils
 ICP_DEV int lane_id() { return (int)(threadIdx.x & 31u); }
 ICP_DEV int warp_id() { return (int)(threadIdx.x >> 5); }
 
@@ -101,10 +102,12 @@ struct SelDecision {   // written by the locating warp, read by every thread
 };
 
 struct SelShared {
-    uint32_t hist[2][2][kSelHistPad];   // [buffer parity][axis][bin]
+    // [buffer parity][bin]: count of axis 0 in the low half-word, of axis 1 in the high half-word
+    // (at most 65535 keys per axis, so the halves never carry into each other)
+    uint32_t hist[2][kSelHistPad];
     uint32_t lcnt[2];
     double list[2][kSelCap];
-    SelDecision dec[2];
+    SelDecision dec[2];          // written by the axis' service warp, read by every thread
     double out_lo[2], out_hi[2];
 };
 
@@ -112,6 +115,7 @@ struct SelShared {
 // constant, clamping and floor are each monotone non-decreasing, so the composition is a
 // monotone map of the binary64 key — all that exactness needs.  (A key range too fine for
 // binary32 merely crowds one bin; the caller then falls back to RADIX.)
+// @region sel_bin
 ICP_DEV int sel_bin(const SelBinSpec& s, double v)
 {
     if (s.mode == 0) {
@@ -135,18 +139,37 @@ ICP_DEV double sel_key(double r, int absdev, double centre)
 
 // Locate the bin holding rank `k` (0-based) and, if need_hi, rank k+1, in hist[0..kSelHist).
 // Executed by one full warp; every lane returns the same decision.
-ICP_DEV SelDecision sel_locate(const uint32_t* hist, uint32_t k, bool need_hi, const SelBinSpec& spec)
+// @region sel_locate
+struct SelScan {       // one lane's share of the packed histogram and its warp prefix sums
+    uint32_t c[9];     // packed counts of bins lane*9 .. lane*9+8
+    uint32_t incl;     // packed inclusive prefix over lanes
+    uint32_t tot;
+};
+
+ICP_DEV SelScan sel_scan(const uint32_t* hist)
 {
     const int lane = lane_id();
-    uint32_t c[9];
-    uint32_t tot = 0;
+    SelScan sc;
+    sc.tot = 0;
 #pragma unroll
     for (int q = 0; q < 9; ++q) {
-        c[q] = hist[lane * 9 + q];  // padded with zeros beyond kSelHist
-        tot += c[q];
+        sc.c[q] = hist[lane * 9 + q];  // padded with zeros beyond kSelHist
+        sc.tot += sc.c[q];
     }
-    uint32_t incl = warp_inclusive_scan_u32(tot);
-    uint32_t excl = incl - tot;
+    sc.incl = warp_inclusive_scan_u32(sc.tot);
+    return sc;
+}
+
+ICP_DEV SelDecision sel_locate(const SelScan& sc, int axis, uint32_t k, bool need_hi, const SelBinSpec& spec)
+{
+    const int lane = lane_id();
+    const int sh = axis * 16;
+    uint32_t c[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) c[q] = (sc.c[q] >> sh) & 0xffffu;
+    const uint32_t tot = (sc.tot >> sh) & 0xffffu;
+    const uint32_t incl = (sc.incl >> sh) & 0xffffu;
+    const uint32_t excl = incl - tot;
     SelDecision d;
     // rank k
     uint32_t vote = __ballot_sync(ICP_FULL_MASK, incl > k);
@@ -200,6 +223,7 @@ ICP_DEV SelDecision sel_locate(const uint32_t* hist, uint32_t k, bool need_hi, c
 
 // Rank the gathered list (cnt <= kSelCap entries) with one warp: returns the entries of rank
 // kp and kp+1 (the latter only meaningful when kp+1 < cnt).
+// @region sel_finish
 ICP_DEV void sel_finish(const double* list, uint32_t cnt, uint32_t kp, double* v0, double* v1)
 {
     const int lane = lane_id();
@@ -219,6 +243,7 @@ ICP_DEV void sel_finish(const double* list, uint32_t cnt, uint32_t kp, double* v
 }
 
 // Per-axis selection state, kept redundantly (and identically) by every thread of the CTA.
+// @region sel_state
 struct SelAxisState {
     SelBinSpec spec;
     int phase;       // 0 = searching rank k (+k+1 when FAST), 1 = searching rank k+1 (RADIX), 2 = done
@@ -260,9 +285,10 @@ struct KeysInRegisters {         // the calling thread's own points, held in reg
 // `hist_parity` names the histogram buffer that is already zeroed on entry; on exit the
 // returned parity names a zeroed buffer again.  Must be called by all threads of the CTA.
 //
-// Round structure (two barriers in the common case): histogram pass | barrier | EVERY warp
-// locates the wanted bins from the shared histogram (identical results, no broadcast needed) |
-// gather the bins' keys into a short list | barrier | every warp ranks the list.
+// Round structure: histogram pass | barrier | warp a locates axis a's bins in the shared histogram |
+// barrier | all threads gather those bins' keys (cached bin numbers) into a short list | barrier |
+// warp a ranks list a | barrier.  The CTA is instruction-issue bound with two or three CTAs per SM,
+// so the serial steps are done once (by one warp per axis) rather than redundantly by every warp.
 template <int THREADS, int PPT, class KeySrc>
 ICP_DEV int block_median2(SelShared* sh, const KeySrc& keys, int n, int absdev, const double centre[2],
                           const bool est_valid[2], const float est_lo[2], const float est_scale[2],
@@ -292,10 +318,10 @@ ICP_DEV int block_median2(SelShared* sh, const KeySrc& keys, int n, int absdev, 
     }
     int par = hist_parity;
     while (st[0].phase != 2 || st[1].phase != 2) {
-        uint32_t* h0 = sh->hist[par][0];
-        uint32_t* h1 = sh->hist[par][1];
+        uint32_t* h = sh->hist[par];
+// @region sel_hist_pass
         // ---- histogram pass (also clears the other buffer and the list counters)
-        for (int q = tid; q < 2 * kSelHistPad; q += THREADS) (&sh->hist[par ^ 1][0][0])[q] = 0u;
+        for (int q = tid; q < kSelHistPad; q += THREADS) sh->hist[par ^ 1][q] = 0u;
         if (tid < 2) sh->lcnt[tid] = 0u;
         uint32_t bins[PPT];   // this round's bin of each of the thread's keys: axis 0 | axis 1 << 16
         {
@@ -311,13 +337,13 @@ ICP_DEV int block_median2(SelShared* sh, const KeySrc& keys, int n, int absdev, 
                         b0 = sel_bin(st[0].spec, sel_key(rr.x, absdev, centre[0]));
                         if (b0 == 0) ++under0;
                         else if (b0 == kSelBins + 1) ++over0;
-                        else atomicAdd(&h0[b0], 1u);
+                        else atomicAdd(&h[b0], 1u);
                     }
                     if (st[1].phase != 2) {
                         b1 = sel_bin(st[1].spec, sel_key(rr.y, absdev, centre[1]));
                         if (b1 == 0) ++under1;
                         else if (b1 == kSelBins + 1) ++over1;
-                        else atomicAdd(&h1[b1], 1u);
+                        else atomicAdd(&h[b1], 0x10000u);
                     }
                     packed = (uint32_t)b0 | ((uint32_t)b1 << 16);
                 }
@@ -328,25 +354,32 @@ ICP_DEV int block_median2(SelShared* sh, const KeySrc& keys, int n, int absdev, 
             under1 = warp_sum_u32(under1);
             over1 = warp_sum_u32(over1);
             if (lane == 0) {
-                if (under0) atomicAdd(&h0[0], under0);
-                if (over0) atomicAdd(&h0[kSelBins + 1], over0);
-                if (under1) atomicAdd(&h1[0], under1);
-                if (over1) atomicAdd(&h1[kSelBins + 1], over1);
+                if (under0 | under1) atomicAdd(&h[0], under0 | (under1 << 16));
+                if (over0 | over1) atomicAdd(&h[kSelBins + 1], over0 | (over1 << 16));
             }
         }
         __syncthreads();
-        // ---- locate: every warp, both axes, identical decisions
-        SelDecision d0, d1;
-        d0.action = -1; d0.b_lo = d0.b_hi = 0; d0.below = d0.count = 0;
-        d1 = d0;
-        if (st[0].phase != 2)
-            d0 = sel_locate(h0, k + (uint32_t)(st[0].phase == 1 ? 1 : 0), (st[0].spec.mode == 0) && need_hi, st[0].spec);
-        if (st[1].phase != 2)
-            d1 = sel_locate(h1, k + (uint32_t)(st[1].phase == 1 ? 1 : 0), (st[1].spec.mode == 0) && need_hi, st[1].spec);
-        const bool g0 = d0.action == 0;
-        const bool g1 = d1.action == 0;
+// @region sel_locate_call
+        // ---- locate: warp a serves axis a (a single-warp CTA serves both)
+        {
+            const int warp = warp_id();
+            if (warp < 2) {
+                const SelScan sc = sel_scan(h);
+                for (int a = (THREADS >= 64 ? warp : 0); a < 2; a += (THREADS >= 64 ? 2 : 1)) {
+                    if (st[a].phase == 2) continue;
+                    const SelDecision d = sel_locate(sc, a, k + (uint32_t)(st[a].phase == 1 ? 1 : 0),
+                                                     (st[a].spec.mode == 0) && need_hi, st[a].spec);
+                    if (lane == 0) sh->dec[a] = d;
+                }
+            }
+        }
+        __syncthreads();
+        SelDecision d0 = sh->dec[0], d1 = sh->dec[1];
+        const bool g0 = st[0].phase != 2 && d0.action == 0;
+        const bool g1 = st[1].phase != 2 && d1.action == 0;
         double fin_lo[2] = {0., 0.}, fin_hi[2] = {0., 0.};
         if (g0 || g1) {
+// @region sel_gather
             // ---- gather the target bins (cached bin numbers; keys are re-read only on a hit)
 #pragma unroll
             for (int kk = 0; kk < PPT; ++kk) {
@@ -361,13 +394,25 @@ ICP_DEV int block_median2(SelShared* sh, const KeySrc& keys, int n, int absdev, 
                 }
             }
             __syncthreads();
-            // ---- rank the lists: every warp, identical results
-            if (g0) sel_finish(sh->list[0], d0.count, k + (uint32_t)(st[0].phase == 1 ? 1 : 0) - d0.below, &fin_lo[0], &fin_hi[0]);
-            if (g1) sel_finish(sh->list[1], d1.count, k + (uint32_t)(st[1].phase == 1 ? 1 : 0) - d1.below, &fin_lo[1], &fin_hi[1]);
-        } else {
-            // no barrier separated this round's histogram readers from the next round's clearing
+// @region sel_finish_call
+            // ---- rank the lists: warp a serves axis a
+            {
+                const int warp = warp_id();
+                if (warp < 2) {
+                    for (int a = (THREADS >= 64 ? warp : 0); a < 2; a += (THREADS >= 64 ? 2 : 1)) {
+                        if (!(a == 0 ? g0 : g1)) continue;
+                        const SelDecision d = a == 0 ? d0 : d1;
+                        double v0, v1;
+                        sel_finish(sh->list[a], d.count, k + (uint32_t)(st[a].phase == 1 ? 1 : 0) - d.below, &v0, &v1);
+                        if (lane == 0) { sh->out_lo[a] = v0; sh->out_hi[a] = v1; }
+                    }
+                }
+            }
             __syncthreads();
+#pragma unroll
+            for (int a = 0; a < 2; ++a) { fin_lo[a] = sh->out_lo[a]; fin_hi[a] = sh->out_hi[a]; }
         }
+// @region sel_state_update
         // ---- uniform state update
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
@@ -423,6 +468,7 @@ ICP_DEV int block_median2(SelShared* sh, const KeySrc& keys, int n, int absdev, 
 // return every lane holds the warp total of value number warp_reduce16_owner(lane) in v[0];
 // lanes 2t and 2t+1 hold the same value.  The summation tree is fixed: results do not depend on
 // scheduling.
+// @region warp_reduce16
 ICP_DEV int warp_reduce16_owner(int lane)
 {
     return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);

@@ -58,6 +58,7 @@ struct FusedLayout {
 struct FusedCtl {
     double sums[16];
     double red[kMaxWarps][16];
+    double bcast[8];      // tree mode: inner transform after the update (6), cost (1), decision (1)
     uint64_t hash_part[kMaxWarps];
     uint32_t warp_tot[kMaxWarps];
     uint32_t pair;
@@ -142,6 +143,7 @@ struct FusedParams {
 };
 
 // ---------------------------------------------------------------------------------------------
+// @region build_grid
 template <int THREADS, int DIM>
 ICP_DEV GridGeom cta_build_grid(const double* dst, int m, unsigned char* U, const FusedLayout& L,
                                 FusedCtl* ctl, int cell_budget)
@@ -247,6 +249,7 @@ ICP_DEV GridGeom cta_build_grid(const double* dst, int m, unsigned char* U, cons
 // entries repeat per unrolled point, so that every lane executes the same loads with the same
 // immediates and only the base pointer differs.  Lanes >= 12 mirror lane 0 (same addresses,
 // result discarded).
+// @region chain
 struct ChainPtrs {
     smem_ref x, y, z;   // shared-memory references to double2 arrays
     int iy, iz;         // advance (in double2) per kChainStage points; x always advances
@@ -346,6 +349,7 @@ ICP_DEV ChainPtrs chain_role(int lane, const double2* r2, const double2* c2, con
 // |r - median|, sigma = 1.4826 * MAD (stats.rs:39-47).  est_med / est_sigma carry the previous
 // evaluation's result in and this one's out: they only steer the (exact) selection's bin map.
 // One inlined copy of the selection runs both stages.
+// @region calc_stddevs_driver
 template <int THREADS, int PPT, class KeySrc>
 ICP_DEV int cta_calc_stddevs(SelShared* sel, const KeySrc& ks, int n, double est_med[2], double est_sigma[2],
                              int hist_par, double sigma[2])
@@ -372,6 +376,7 @@ ICP_DEV int cta_calc_stddevs(SelShared* sel, const KeySrc& ks, int n, double est
 }
 
 // ---------------------------------------------------------------------------------------------
+// @region pair_setup
 template <int THREADS, int PPT, int DIM, bool SHARED_TARGET, int MINB, bool ORDERED>
 ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
 {
@@ -398,7 +403,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
     const int tid = (int)threadIdx.x, lane = lane_id(), warp = warp_id();
     unsigned char* slab = p.workspace + (size_t)blockIdx.x * p.ws_stride;
 
-    for (int q = tid; q < 2 * 2 * kSelHistPad; q += THREADS) (&sel->hist[0][0][0])[q] = 0u;
+    for (int q = tid; q < 2 * kSelHistPad; q += THREADS) (&sel->hist[0][0])[q] = 0u;
     int hist_par = 0;
     __syncthreads();
 
@@ -474,6 +479,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                     *reinterpret_cast<uint4*>(U + o) = *reinterpret_cast<const uint4*>(slab + o);
                 __syncthreads();
             }
+// @region search
             // ---- transform (lib.rs:113-116) + correspondence search (lib.rs:118-124)
             double sx[PPT], sy[PPT], dx[PPT], dy[PPT];
             uint64_t hpart = 0;
@@ -554,6 +560,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                 H = H * 0x100000001B3ull + h;
             }
 
+// @region irls_setup
             // ---- estimate_transform (lib.rs:59-84)
             Transform Ti = transform_identity();
             double prev_error = kF64Max;
@@ -565,6 +572,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                     double sigma[2];
                     double jtj[9], jtr[3], error;
                     if (ORDERED) {
+// @region ordered_rows
                         // residuals (lib.rs:230-234)
 #pragma unroll
                         for (int k = 0; k < PPT; ++k) {
@@ -633,6 +641,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                         for (int q = 0; q < 3; ++q) jtr[q] = ctl->sums[9 + q];
                         error = ctl->sums[12];
                     } else {
+// @region tree_residuals
                         // residuals (lib.rs:230-234) stay in registers
                         double2 rr[PPT];
 #pragma unroll
@@ -645,11 +654,12 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                         KeysInRegisters<PPT> ks;
                         ks.v = rr;
                         hist_par = cta_calc_stddevs<THREADS, PPT>(sel, ks, n, est_med, est_sigma, hist_par, sigma);
+// @region tree_accumulate
                         // row weights (lib.rs:245-250), Jacobian (lib.rs:176-184), Huber cost (lib.rs:47-48)
                         // and their sums, reduced as a fixed tree: per-thread partials over the
                         // thread's points (ascending), split butterfly across lanes, warps in order
                         const double g0 = 1. / sigma[0], g1 = 1. / sigma[1];
-                        double acc[16];
+                        double acc[16];   // 0-5 upper triangle of jtj, 6-8 jtr, 9 cost, 10-15 unused (zero)
 #pragma unroll
                         for (int q = 0; q < 16; ++q) acc[q] = 0.;
 #pragma unroll
@@ -659,45 +669,70 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                                 const double a0 = -sy[k], a1 = sx[k];
                                 const double J0[3] = {Ti.r00, Ti.r01, Ti.r00 * a0 + Ti.r01 * a1};
                                 const double J1[3] = {Ti.r10, Ti.r11, Ti.r10 * a0 + Ti.r11 * a1};
+                                // J^T W J is accumulated as its upper triangle (6 sums) and mirrored:
+                                // (c J_a) J_b and (c J_b) J_a differ by one rounding per term, the
+                                // same order as the tree reduction's own reordering
                                 if (sigma[0] != 0.) {
                                     const double c = huber_drho_of_residual(rr[k].x) * g0;
-#pragma unroll
-                                    for (int a = 0; a < 3; ++a) {
-                                        const double pa = c * J0[a];
-#pragma unroll
-                                        for (int b = 0; b < 3; ++b) acc[3 * a + b] = acc[3 * a + b] + pa * J0[b];
-                                        acc[9 + a] = acc[9 + a] + pa * rr[k].x;
-                                    }
+                                    const double p0 = c * J0[0], p1 = c * J0[1], p2 = c * J0[2];
+                                    acc[0] = acc[0] + p0 * J0[0]; acc[1] = acc[1] + p0 * J0[1]; acc[2] = acc[2] + p0 * J0[2];
+                                    acc[3] = acc[3] + p1 * J0[1]; acc[4] = acc[4] + p1 * J0[2]; acc[5] = acc[5] + p2 * J0[2];
+                                    acc[6] = acc[6] + p0 * rr[k].x; acc[7] = acc[7] + p1 * rr[k].x; acc[8] = acc[8] + p2 * rr[k].x;
                                 }
                                 if (sigma[1] != 0.) {
                                     const double c = huber_drho_of_residual(rr[k].y) * g1;
-#pragma unroll
-                                    for (int a = 0; a < 3; ++a) {
-                                        const double pa = c * J1[a];
-#pragma unroll
-                                        for (int b = 0; b < 3; ++b) acc[3 * a + b] = acc[3 * a + b] + pa * J1[b];
-                                        acc[9 + a] = acc[9 + a] + pa * rr[k].y;
-                                    }
+                                    const double p0 = c * J1[0], p1 = c * J1[1], p2 = c * J1[2];
+                                    acc[0] = acc[0] + p0 * J1[0]; acc[1] = acc[1] + p0 * J1[1]; acc[2] = acc[2] + p0 * J1[2];
+                                    acc[3] = acc[3] + p1 * J1[1]; acc[4] = acc[4] + p1 * J1[2]; acc[5] = acc[5] + p2 * J1[2];
+                                    acc[6] = acc[6] + p0 * rr[k].y; acc[7] = acc[7] + p1 * rr[k].y; acc[8] = acc[8] + p2 * rr[k].y;
                                 }
-                                acc[12] = acc[12] + huber_rho(rr[k].x * rr[k].x + rr[k].y * rr[k].y);
+                                acc[9] = acc[9] + huber_rho(rr[k].x * rr[k].x + rr[k].y * rr[k].y);
                             }
                         }
+// @region tree_reduce
                         warp_reduce16(acc);
                         // (the previous evaluation's readers of ctl->red have passed the barriers of
                         // this evaluation's selection before anyone writes here)
                         if ((lane & 1) == 0) ctl->red[warp][warp_reduce16_owner(lane)] = acc[0];
                         __syncthreads();
-                        double tot = 0.;
-                        if (lane < 16) {
-                            tot = ctl->red[0][lane];
-                            for (int w = 1; w < NW; ++w) tot = tot + ctl->red[w][lane];
+                        // warp 0 adds the warps' partials in warp order, solves and takes the break
+                        // decisions (lib.rs:67-81) once; everyone else picks the outcome up
+                        if (warp == 0) {
+                            double tot = 0.;
+                            if (lane < 16) {
+                                tot = ctl->red[0][lane];
+                                for (int w = 1; w < NW; ++w) tot = tot + ctl->red[w][lane];
+                            }
+                            double v[10];
+#pragma unroll
+                            for (int q = 0; q < 10; ++q) v[q] = shfl_f64(tot, q);
+                            const double jtj[9] = {v[0], v[1], v[2], v[1], v[3], v[4], v[2], v[4], v[5]};
+                            const double jtr[3] = {v[6], v[7], v[8]};
+                            const double error = v[9];
+                            double delta[3];
+                            uint32_t decision = kBreakCap;   // kBreakCap here = "update accepted"
+                            Transform Tn = Ti;
+                            if (!solve_normal_equations(jtj, jtr, delta)) decision = kBreakNone;
+                            else if ((delta[0] * delta[0] + delta[1] * delta[1]) + delta[2] * delta[2] < kDeltaNormThreshold) decision = kBreakDelta;
+                            else if (error > prev_error) decision = kBreakError;
+                            else Tn = transform_mul(transform_new(delta[0], delta[1], delta[2]), Ti);
+                            if (lane == 0) {
+                                ctl->bcast[0] = Tn.r00; ctl->bcast[1] = Tn.r01; ctl->bcast[2] = Tn.r10;
+                                ctl->bcast[3] = Tn.r11; ctl->bcast[4] = Tn.tx;  ctl->bcast[5] = Tn.ty;
+                                ctl->bcast[6] = error;
+                                ctl->bcast[7] = (double)decision;
+                            }
                         }
-#pragma unroll
-                        for (int q = 0; q < 9; ++q) jtj[q] = shfl_f64(tot, q);
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) jtr[q] = shfl_f64(tot, 9 + q);
-                        error = shfl_f64(tot, 12);
+                        __syncthreads();
+                        const uint32_t decision = (uint32_t)ctl->bcast[7];
+                        if (decision != kBreakCap) { why = decision; break; }
+                        prev_error = ctl->bcast[6];
+                        Ti.r00 = ctl->bcast[0]; Ti.r01 = ctl->bcast[1]; Ti.r10 = ctl->bcast[2];
+                        Ti.r11 = ctl->bcast[3]; Ti.tx = ctl->bcast[4];  Ti.ty = ctl->bcast[5];
+                        ++accepted;
+                        continue;
                     }
+// @region solve_update
                     // solve + break tests + update: every thread, identically (lib.rs:67-81)
                     double delta[3];
                     if (!solve_normal_equations(jtj, jtr, delta)) { why = kBreakNone; break; }
@@ -711,6 +746,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                     ++accepted;
                 }
             }
+// @region outer_tail
             T = transform_mul(Ti, T);  // lib.rs:127
             if (tid == 0 && p.out_inner) p.out_inner[(size_t)pair * p.max_iter + it] = accepted | (why << 16);
             __syncthreads();  // rows are dead; next iteration restages the target

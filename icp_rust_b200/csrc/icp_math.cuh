@@ -34,6 +34,7 @@ ICP_DEV uint64_t f64_to_bits(double d) { return (uint64_t)__double_as_longlong(d
 // from the published algorithm.  |x| >= 2^20*pi/2 (Payne-Hanek in fdlibm) is folded with an
 // exact fmod by the double nearest 2*pi instead — a diverged solve, documented in DESIGN.md.
 // ---------------------------------------------------------------------------------------------
+// @region sincos
 ICP_DEV double k_sin(double x, double y, int iy)
 {
     const double S1 = bits_to_f64(ICP_HEXD(0xBFC55555u, 0x55555549u));
@@ -182,6 +183,7 @@ ICP_DEV void sincos_libm(double x, double* s, double* c)
 
 // ---------------------------------------------------------------------------------------------
 // src/huber.rs:6-15 / 17-26 (argument e is the SQUARED residual)
+// @region huber
 ICP_DEV double huber_rho(double e)
 {
     const double k2 = kHuberK * kHuberK;
@@ -211,6 +213,7 @@ ICP_DEV double huber_drho_of_residual(double r)
 
 // ---------------------------------------------------------------------------------------------
 // src/transform.rs:22-24: rot * p + t (nalgebra gemv sums columns in ascending order)
+// @region transform_ops
 ICP_DEV void transform_apply(const Transform& T, double x, double y, double* ox, double* oy)
 {
     *ox = (T.r00 * x + T.r01 * y) + T.tx;
@@ -239,6 +242,7 @@ ICP_DEV Transform transform_identity()  // src/transform.rs:34-39
 
 // Transform::new(param) -> se2::calc_rt -> so2::new_rotation2
 // (src/transform.rs:13-16, src/se2.rs:21-41, src/so2.rs:8-17)
+// @region transform_new
 ICP_DEV Transform transform_new(double vx, double vy, double theta)
 {
     double s, c;
@@ -257,6 +261,7 @@ ICP_DEV Transform transform_new(double vx, double vy, double theta)
 
 // src/linalg.rs:3-29 followed by `-jtj_inv * jtr` (src/lib.rs:258).  m is row-major jtj.
 // Returns false for None (det == 0 exactly).
+// @region solve3x3
 ICP_DEV bool solve_normal_equations(const double m[9], const double jtr[3], double delta[3])
 {
     double m00 = m[0], m01 = m[1], m02 = m[2];
@@ -282,6 +287,7 @@ ICP_DEV bool solve_normal_equations(const double m[9], const double jtr[3], doub
 
 // Order-preserving map f64 -> u64 (total order; -0.0 sorts just below +0.0, which cannot change
 // a median VALUE used downstream: see DESIGN.md "median").
+// @region misc_math
 ICP_DEV uint64_t f64_order_key(double v)
 {
     uint64_t b = f64_to_bits(v);
@@ -292,7 +298,7 @@ ICP_DEV double f64_from_order_key(uint64_t k)
     return bits_to_f64((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k);
 }
 
-// correspondence checksum (same definition as the oracle's orc_mix64 / header comment)
+// correspondence checksum: splitmix64 finaliser (definition in DESIGN.md "correspondence checksum")
 ICP_DEV uint64_t mix64(uint64_t x)
 {
     x += 0x9E3779B97F4A7C15ull;

@@ -35,7 +35,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, 1) calc_stddevs_kernel(StatsParams p)
     for (uint32_t b = blockIdx.x; b < p.B; b += gridDim.x) {
         const int n = (int)(p.off[b + 1] - p.off[b]);
         const double* res = p.residuals + (size_t)p.off[b] * 2;
-        for (int q = tid; q < 2 * 2 * kSelHistPad; q += THREADS) (&sel->hist[0][0][0])[q] = 0u;
+        for (int q = tid; q < 2 * kSelHistPad; q += THREADS) (&sel->hist[0][0])[q] = 0u;
         if (n < 1 || n > p.cap) {   // None (stats.rs:15-17) / does not fit
             if (tid < 2) {
                 p.out_sigma[(size_t)b * 2 + tid] = -1.0;

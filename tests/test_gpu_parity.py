@@ -141,7 +141,7 @@ def test_bundled_scans_batch_with_origin_duplicates(ctx, icp, scans2d, ordered):
 
 
 # instance ids: icp_rust_b200/csrc/Makefile (3-7 warp-tree reductions, 11-13 ordered sums)
-INSTANCES = {3: (128, 9, False), 4: (192, 6, False), 5: (256, 5, False), 6: (256, 8, False), 7: (384, 8, False),
+INSTANCES = {3: (384, 3, False), 4: (256, 5, False), 5: (512, 3, False), 6: (256, 8, False), 7: (384, 8, False),
              11: (128, 9, True), 12: (256, 8, True), 13: (384, 8, True)}
 
 
