@@ -78,6 +78,7 @@ struct icp_b200_context {
     std::string last_error;
     int cell_budget = 4096;
     int force_instance = -1;
+    int force_stream = 0;   // ICP_B200_FORCE_STREAM=1: route every warp-tree batch to the streaming kernel (tests)
 };
 
 struct icp_b200_target {
@@ -126,11 +127,18 @@ int pair_status_to_error(int st)
 }
 
 struct LaunchPlan {
-    const Instance* inst = nullptr;
+    const Instance* inst = nullptr;   // fused per-pair kernel ...
     FusedLayout layout{};
     int mcap = 0;
     int grid = 0;
     FusedKernel kernel = nullptr;
+    bool stream = false;              // ... or the streaming kernel for large scans
+    StreamKernel skernel = nullptr;
+    StreamLayout slayout{};
+    uint32_t n_cap = 0, m_cap = 0, c_cap = 0;
+    int threads = 0;
+    uint32_t smem = 0;
+    uint64_t ws_stride = 0;
 };
 
 // Chooses the kernel instance for the largest scan of the batch and sizes its launch.
@@ -143,15 +151,39 @@ int plan_launch(icp_b200_context* ctx, uint32_t dim, bool shared_target, bool or
         inst = kInstances[ctx->force_instance];
     for (int i = 0; !inst && i < kNumInstances; ++i)
         if (fits(kInstances[i])) inst = kInstances[i];
-    if (!inst) return fail(ctx, ICP_B200_ERR_TOO_LARGE, "source scan larger than the largest fused kernel (3072 points)");
-    if (!shared_target && max_m > 65528u)
-        return fail(ctx, ICP_B200_ERR_TOO_LARGE, "per-pair target larger than 65528 points: use icp_b200_target_create");
-    plan->inst = inst;
-    plan->mcap = (int)((max_m + 7u) & ~7u);
-    plan->layout = fused_layout((int)dim, inst->threads * inst->ppt, plan->mcap, ctx->cell_budget, shared_target, ordered);
-    if ((int)plan->layout.total > ctx->max_smem_optin)
-        return fail(ctx, ICP_B200_ERR_TOO_LARGE, "scan pair does not fit the shared memory of one SM: use icp_b200_target_create for large targets");
+    if (inst) {
+        plan->inst = inst;
+        plan->mcap = (int)((max_m + 7u) & ~7u);
+        plan->layout = fused_layout((int)dim, inst->threads * inst->ppt, plan->mcap, ctx->cell_budget, shared_target, ordered);
+        if (!shared_target && max_m > 65528u) inst = nullptr;                   // u16 indices of the shared-memory grid
+        else if ((int)plan->layout.total > ctx->max_smem_optin) inst = nullptr;  // does not fit one SM
+    }
+    if (ctx->force_stream && !ordered) inst = nullptr;
+    if (!inst) {
+        // large scans: streaming kernel, warp-tree sums only
+        if (ordered)
+            return fail(ctx, ICP_B200_ERR_TOO_LARGE,
+                        "scan pair too large for the ordered-sums kernel (3072 source points / shared memory of one SM): clear ICP_B200_FLAG_ORDERED_SUMS");
+        if (max_n > 65535u) return fail(ctx, ICP_B200_ERR_TOO_LARGE, "source scan larger than 65535 points");
+        plan->stream = true;
+        plan->n_cap = std::max<uint32_t>(8u, (max_n + 7u) & ~7u);
+        plan->m_cap = shared_target ? 0u : std::max<uint32_t>(8u, (max_m + 7u) & ~7u);
+        plan->c_cap = shared_target ? 0u : std::max<uint32_t>(64u, 2u * plan->m_cap);
+        plan->slayout = stream_layout((int)dim, plan->n_cap, plan->m_cap, plan->c_cap, shared_target);
+        plan->ws_stride = plan->slayout.total;
+        plan->skernel = kStreamInstance.k[dim - 2][shared_target ? 1 : 0];
+        plan->threads = kStreamInstance.threads;
+        plan->smem = kStreamShared;
+        int occ = 0;
+        ICP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, plan->skernel, plan->threads, plan->smem));
+        if (occ < 1) return fail(ctx, ICP_B200_ERR_CUDA, "streaming kernel cannot be resident (occupancy 0)");
+        plan->grid = (int)std::max<long long>(1, std::min<long long>((long long)occ * ctx->sm_count, pairs));
+        return ICP_B200_OK;
+    }
     plan->kernel = inst->k[dim - 2][shared_target ? 1 : 0];
+    plan->threads = inst->threads;
+    plan->smem = plan->layout.total;
+    plan->ws_stride = ((uint64_t)plan->layout.nn_bytes + 255u) & ~255ull;
     ICP_CUDA(ctx, cudaFuncSetAttribute(plan->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->layout.total));
     int occ = 0;
     ICP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, plan->kernel, inst->threads, plan->layout.total));
@@ -161,7 +193,6 @@ int plan_launch(icp_b200_context* ctx, uint32_t dim, bool shared_target, bool or
     return ICP_B200_OK;
 }
 
-uint64_t ws_stride_of(const FusedLayout& L) { return ((uint64_t)L.nn_bytes + 255u) & ~255ull; }
 
 int validate_batch(icp_b200_context* ctx, const icp_b200_batch* b, bool shared_target)
 {
@@ -187,9 +218,10 @@ int launch_range(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_
     p.out_error = ctx->counters.as<int32_t>() + kMaxChunks;
     p.work_counter = ctx->counters.as<uint32_t>() + chunk_slot;
     p.workspace = ctx->workspace[ws_slot].as<unsigned char>();
-    p.ws_stride = ws_stride_of(plan.layout);
+    p.ws_stride = plan.ws_stride;
     p.pair_begin = begin; p.pair_end = end; p.max_iter = b.max_iter; p.corr_mode = b.corr_mode;
-    p.cell_budget = ctx->cell_budget; p.ncap = plan.inst->threads * plan.inst->ppt; p.mcap = plan.mcap;
+    p.cell_budget = ctx->cell_budget; p.mcap = plan.mcap;
+    p.ncap = plan.stream ? (int)plan.n_cap : plan.inst->threads * plan.inst->ppt;
     p.sm_count = (uint32_t)ctx->sm_count;
     if (tgt) {
         p.target.x = tgt->x.as<double>(); p.target.y = tgt->y.as<double>(); p.target.z = tgt->z.as<double>();
@@ -198,12 +230,18 @@ int launch_range(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_
     }
     const uint32_t pairs = end - begin;
     const int grid = (int)std::min<uint32_t>((uint32_t)plan.grid, pairs);
-    plan.kernel<<<grid, plan.inst->threads, plan.layout.total, stream>>>(p);
+    if (plan.stream) {
+        StreamParams sp{};
+        sp.f = p; sp.n_cap = plan.n_cap; sp.m_cap = plan.m_cap; sp.c_cap = plan.c_cap;
+        plan.skernel<<<grid, plan.threads, plan.smem, stream>>>(sp);
+    } else {
+        plan.kernel<<<grid, plan.threads, plan.smem, stream>>>(p);
+    }
     ICP_CUDA(ctx, cudaGetLastError());
     ctx->info.kernel_launches += 1;
     ctx->info.grid_ctas = (uint32_t)grid;
-    ctx->info.block_threads = (uint32_t)plan.inst->threads;
-    ctx->info.smem_bytes = plan.layout.total;
+    ctx->info.block_threads = (uint32_t)plan.threads;
+    ctx->info.smem_bytes = plan.smem;
     return ICP_B200_OK;
 }
 
@@ -249,7 +287,7 @@ int estimate_device_impl(icp_b200_context* ctx, const icp_b200_target* tgt, cons
     rc = plan_launch(ctx, b->dim, shared, (b->flags & ICP_B200_FLAG_ORDERED_SUMS) != 0, max_n, max_m, b->batch, &plan);
     if (rc != ICP_B200_OK) return rc;
     ICP_CUDA(ctx, ctx->counters.ensure((kMaxChunks + 1) * 4));
-    ICP_CUDA(ctx, ctx->workspace[0].ensure((size_t)plan.grid * ws_stride_of(plan.layout) + 256));
+    ICP_CUDA(ctx, ctx->workspace[0].ensure((size_t)plan.grid * plan.ws_stride + 256));
     ICP_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, (kMaxChunks + 1) * 4, stream));
     ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], stream));
     rc = launch_range(ctx, *b, tgt, plan, 0, b->batch, 0, 0, stream);
@@ -306,8 +344,7 @@ int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b2
     if (hb->out_corr_hash) ICP_CUDA(ctx, ctx->out_hash.ensure((size_t)B * 8));
     if (hb->out_status) ICP_CUDA(ctx, ctx->out_status.ensure((size_t)B * 4));
     ICP_CUDA(ctx, ctx->counters.ensure((kMaxChunks + 1) * 4));
-    const uint64_t wss = ws_stride_of(plan.layout);
-    for (int s = 0; s < 2; ++s) ICP_CUDA(ctx, ctx->workspace[s].ensure((size_t)plan.grid * wss + 256));
+    for (int s = 0; s < 2; ++s) ICP_CUDA(ctx, ctx->workspace[s].ensure((size_t)plan.grid * plan.ws_stride + 256));
 
     icp_b200_batch db = *hb;
     db.src = ctx->src.as<double>(); db.dst = ctx->dst.as<double>();
@@ -450,6 +487,7 @@ int icp_b200_create(int device, icp_b200_context** out)
     }
     ctx->cell_budget = std::max(16, std::min(65000, env_int("ICP_B200_CELL_BUDGET", 4096)));
     ctx->force_instance = env_int("ICP_B200_FORCE_INSTANCE", -1);
+    ctx->force_stream = env_int("ICP_B200_FORCE_STREAM", 0);
     *out = ctx;
     return ICP_B200_OK;
 }
@@ -497,8 +535,13 @@ static int single_pair(icp_b200_context* ctx, uint32_t dim, const double* dst, u
     icp_b200_batch b{};
     b.dim = dim; b.batch = 1; b.max_iter = max_iter; b.corr_mode = ICP_B200_CORR_NONE;
     b.src = src; b.src_off = so; b.dst = dst; b.dst_off = dof; b.init_T = T0; b.out_T = out;
-    b.flags = ICP_B200_FLAG_ORDERED_SUMS;  // one pair: latency is launch-bound anyway, keep the reference's exact sums
-    return estimate_host_impl(ctx, nullptr, &b);
+    b.flags = ICP_B200_FLAG_ORDERED_SUMS;  // one pair: keep the reference's exact sums whenever the scan fits
+    int rc = estimate_host_impl(ctx, nullptr, &b);
+    if (rc == ICP_B200_ERR_TOO_LARGE) {     // large scans (e.g. the bundled 3-D frames): streaming kernel, warp-tree sums
+        b.flags = 0;
+        rc = estimate_host_impl(ctx, nullptr, &b);
+    }
+    return rc;
 }
 
 int icp_b200_icp2d_estimate(icp_b200_context* ctx, const double* dst_xy, uint32_t n_dst, const double* src_xy,

@@ -95,7 +95,8 @@ struct SelBinSpec {
 
 struct SelDecision {   // written by the locating warp, read by every thread
     int action;        // 0 = gather bins [b_lo, b_hi]; 1 = next radix pass; 2 = miss (restart
-                       // in RADIX); 3 = value known (radix prefix exhausted)
+                       // in RADIX); 3 = value known (radix prefix exhausted); 4 = FAST bins
+                       // [b_lo, b_hi] hold the ranks but too many keys: zoom the map into them
     int b_lo, b_hi;
     uint32_t below;    // number of keys in bins < b_lo
     uint32_t count;    // number of keys in bins [b_lo, b_hi]
@@ -214,7 +215,7 @@ ICP_DEV SelDecision sel_locate(const SelScan& sc, int axis, uint32_t k, bool nee
     d.count = warp_sum_u32(part);
     const bool regular = d.b_lo >= 1 && d.b_hi <= kSelBins;
     if (regular && d.count <= (uint32_t)kSelCap) d.action = 0;
-    else if (spec.mode == 0) d.action = 2;
+    else if (spec.mode == 0) d.action = regular ? 4 : 2;
     else if (d.b_lo != d.b_hi) d.action = 2;          // only reachable with need_hi in RADIX: not used
     else if (spec.shift == 0) d.action = 3;           // every surviving key is identical
     else d.action = 1;
@@ -247,8 +248,10 @@ ICP_DEV void sel_finish(const double* list, uint32_t cnt, uint32_t kp, double* v
 struct SelAxisState {
     SelBinSpec spec;
     int phase;       // 0 = searching rank k (+k+1 when FAST), 1 = searching rank k+1 (RADIX), 2 = done
+    int zooms;       // FAST refinements done so far
     double v_lo, v_hi;
 };
+constexpr int kSelMaxZooms = 2;
 
 ICP_DEV void sel_start_radix(SelAxisState& st, int which)
 {
@@ -279,7 +282,8 @@ struct KeysInRegisters {         // the calling thread's own points, held in reg
     ICP_DEV_MEMBER double2 get(int kk, int /*i*/) const { return v[kk]; }
 };
 
-// Medians of the two key columns.  n >= 1, n <= THREADS * PPT.  est_valid[a] enables the FAST map
+// Medians of the two key columns.  n >= 1; n <= THREADS * PPT, or PPT == 0 for any n <= 65535
+// (keys are then visited with a run-time loop and bin numbers are recomputed when gathering).  est_valid[a] enables the FAST map
 // for axis a with value range [est_lo[a], est_lo[a] + kSelBins / est_scale[a]).
 // On return med[a] = median as stats.rs:11-28 defines it ((b + c) / 2 for even n).
 // `hist_parity` names the histogram buffer that is already zeroed on entry; on exit the
@@ -303,6 +307,7 @@ ICP_DEV int block_median2(SelShared* sh, const KeySrc& keys, int n, int absdev, 
     for (int a = 0; a < 2; ++a) {
         st[a].v_lo = 0.;
         st[a].v_hi = 0.;
+        st[a].zooms = 0;
         if (est_valid[a]) {
             st[a].spec.mode = 0;
             st[a].spec.lo = est_lo[a];
@@ -323,31 +328,37 @@ ICP_DEV int block_median2(SelShared* sh, const KeySrc& keys, int n, int absdev, 
         // ---- histogram pass (also clears the other buffer and the list counters)
         for (int q = tid; q < kSelHistPad; q += THREADS) sh->hist[par ^ 1][q] = 0u;
         if (tid < 2) sh->lcnt[tid] = 0u;
-        uint32_t bins[PPT];   // this round's bin of each of the thread's keys: axis 0 | axis 1 << 16
+        // this round's bin of each of the thread's keys (axis 0 | axis 1 << 16), cached for the
+        // gather pass when the per-thread point count is a compile-time constant
+        uint32_t bins[PPT > 0 ? PPT : 1];
         {
             uint32_t under0 = 0, over0 = 0, under1 = 0, over1 = 0;
-#pragma unroll
-            for (int kk = 0; kk < PPT; ++kk) {
-                const int i = tid + kk * THREADS;
-                uint32_t packed = 0xffffffffu;
-                if (i < n) {
-                    const double2 rr = keys.get(kk, i);
-                    int b0 = 0xffff, b1 = 0xffff;
-                    if (st[0].phase != 2) {
-                        b0 = sel_bin(st[0].spec, sel_key(rr.x, absdev, centre[0]));
-                        if (b0 == 0) ++under0;
-                        else if (b0 == kSelBins + 1) ++over0;
-                        else atomicAdd(&h[b0], 1u);
-                    }
-                    if (st[1].phase != 2) {
-                        b1 = sel_bin(st[1].spec, sel_key(rr.y, absdev, centre[1]));
-                        if (b1 == 0) ++under1;
-                        else if (b1 == kSelBins + 1) ++over1;
-                        else atomicAdd(&h[b1], 0x10000u);
-                    }
-                    packed = (uint32_t)b0 | ((uint32_t)b1 << 16);
+            auto bin_point = [&](int kk, int i) -> uint32_t {
+                const double2 rr = keys.get(kk, i);
+                int b0 = 0xffff, b1 = 0xffff;
+                if (st[0].phase != 2) {
+                    b0 = sel_bin(st[0].spec, sel_key(rr.x, absdev, centre[0]));
+                    if (b0 == 0) ++under0;
+                    else if (b0 == kSelBins + 1) ++over0;
+                    else atomicAdd(&h[b0], 1u);
                 }
-                bins[kk] = packed;
+                if (st[1].phase != 2) {
+                    b1 = sel_bin(st[1].spec, sel_key(rr.y, absdev, centre[1]));
+                    if (b1 == 0) ++under1;
+                    else if (b1 == kSelBins + 1) ++over1;
+                    else atomicAdd(&h[b1], 0x10000u);
+                }
+                return (uint32_t)b0 | ((uint32_t)b1 << 16);
+            };
+            if (PPT > 0) {
+#pragma unroll
+                for (int kk = 0; kk < (PPT > 0 ? PPT : 1); ++kk) {
+                    const int i = tid + kk * THREADS;
+                    bins[kk] = (i < n) ? bin_point(kk, i) : 0xffffffffu;
+                }
+            } else {
+                for (int i = tid, kk = 0; i < n; i += THREADS, ++kk) bin_point(kk, i);
+                bins[0] = 0u;
             }
             under0 = warp_sum_u32(under0);
             over0 = warp_sum_u32(over0);
@@ -381,16 +392,32 @@ ICP_DEV int block_median2(SelShared* sh, const KeySrc& keys, int n, int absdev, 
         if (g0 || g1) {
 // @region sel_gather
             // ---- gather the target bins (cached bin numbers; keys are re-read only on a hit)
+            if (PPT > 0) {
 #pragma unroll
-            for (int kk = 0; kk < PPT; ++kk) {
-                const int i = tid + kk * THREADS;
-                const int b0 = (int)(bins[kk] & 0xffffu), b1 = (int)(bins[kk] >> 16);
-                const bool hit0 = g0 && b0 >= d0.b_lo && b0 <= d0.b_hi;   // 0xffff marks "no key"
-                const bool hit1 = g1 && b1 >= d1.b_lo && b1 <= d1.b_hi;
-                if (hit0 || hit1) {
+                for (int kk = 0; kk < (PPT > 0 ? PPT : 1); ++kk) {
+                    const int i = tid + kk * THREADS;
+                    const int b0 = (int)(bins[kk] & 0xffffu), b1 = (int)(bins[kk] >> 16);
+                    const bool hit0 = g0 && b0 >= d0.b_lo && b0 <= d0.b_hi;   // 0xffff marks "no key"
+                    const bool hit1 = g1 && b1 >= d1.b_lo && b1 <= d1.b_hi;
+                    if (hit0 || hit1) {
+                        const double2 rr = keys.get(kk, i);
+                        if (hit0) sh->list[0][atomicAdd(&sh->lcnt[0], 1u)] = sel_key(rr.x, absdev, centre[0]);
+                        if (hit1) sh->list[1][atomicAdd(&sh->lcnt[1], 1u)] = sel_key(rr.y, absdev, centre[1]);
+                    }
+                }
+            } else {
+                for (int i = tid, kk = 0; i < n; i += THREADS, ++kk) {
                     const double2 rr = keys.get(kk, i);
-                    if (hit0) sh->list[0][atomicAdd(&sh->lcnt[0], 1u)] = sel_key(rr.x, absdev, centre[0]);
-                    if (hit1) sh->list[1][atomicAdd(&sh->lcnt[1], 1u)] = sel_key(rr.y, absdev, centre[1]);
+                    if (g0) {
+                        const double v = sel_key(rr.x, absdev, centre[0]);
+                        const int b = sel_bin(st[0].spec, v);
+                        if (b >= d0.b_lo && b <= d0.b_hi) sh->list[0][atomicAdd(&sh->lcnt[0], 1u)] = v;
+                    }
+                    if (g1) {
+                        const double v = sel_key(rr.y, absdev, centre[1]);
+                        const int b = sel_bin(st[1].spec, v);
+                        if (b >= d1.b_lo && b <= d1.b_hi) sh->list[1][atomicAdd(&sh->lcnt[1], 1u)] = v;
+                    }
                 }
             }
             __syncthreads();
@@ -431,7 +458,17 @@ ICP_DEV int block_median2(SelShared* sh, const KeySrc& keys, int n, int absdev, 
                     st[a].v_hi = v0;
                     st[a].phase = 2;
                 }
-            } else if (d.action == 2) {
+            } else if (d.action == 4 && st[a].zooms < kSelMaxZooms) {
+                // FAST found the bins but they are crowded (large n): same map, 256x finer, over
+                // exactly those bins.  Still monotone; keys outside land in UNDER / OVER and keep
+                // the rank bookkeeping right.  If binary32 cannot resolve the range the next
+                // round misses and RADIX takes over.
+                const float width = (float)(d.b_hi - d.b_lo + 1) / st[a].spec.scale;
+                st[a].spec.lo = st[a].spec.lo + (float)(d.b_lo - 1) / st[a].spec.scale;
+                st[a].spec.scale = (float)kSelBins / width;
+                st[a].zooms += 1;
+                if (!(st[a].spec.scale < 1e30f) || !(width > 0.f)) sel_start_radix(st[a], st[a].phase);
+            } else if (d.action == 2 || d.action == 4) {
                 sel_start_radix(st[a], st[a].phase);
             } else {
                 // RADIX: descend into digit (b_lo - 1)

@@ -345,6 +345,79 @@ ICP_DEV ChainPtrs chain_role(int lane, const double2* r2, const double2* c2, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// Warp-tree mode building blocks (shared by the fused and the streaming kernel).
+//
+// One point's contribution to the sums of lib.rs:242-255 and lib.rs:45-50.  acc: 0-5 upper
+// triangle of J^T W J (00 01 02 11 12 22), 6-8 J^T W r, 9 Huber cost, 10-15 unused (zero).
+// J^T W J is accumulated as its upper triangle and mirrored: (c J_a) J_b and (c J_b) J_a differ by
+// one rounding per term, the same order as the tree reduction's own reordering.
+// @region tree_accumulate
+ICP_DEV void tree_accumulate_point(double acc[16], const Transform& Ti, double sx, double sy, double2 rr,
+                                   const double sigma[2], double g0, double g1)
+{
+    const double a0 = -sy, a1 = sx;   // jacobian(), lib.rs:176-184
+    const double J0[3] = {Ti.r00, Ti.r01, Ti.r00 * a0 + Ti.r01 * a1};
+    const double J1[3] = {Ti.r10, Ti.r11, Ti.r10 * a0 + Ti.r11 * a1};
+    if (sigma[0] != 0.) {
+        const double c = huber_drho_of_residual(rr.x) * g0;
+        const double p0 = c * J0[0], p1 = c * J0[1], p2 = c * J0[2];
+        acc[0] = acc[0] + p0 * J0[0]; acc[1] = acc[1] + p0 * J0[1]; acc[2] = acc[2] + p0 * J0[2];
+        acc[3] = acc[3] + p1 * J0[1]; acc[4] = acc[4] + p1 * J0[2]; acc[5] = acc[5] + p2 * J0[2];
+        acc[6] = acc[6] + p0 * rr.x; acc[7] = acc[7] + p1 * rr.x; acc[8] = acc[8] + p2 * rr.x;
+    }
+    if (sigma[1] != 0.) {
+        const double c = huber_drho_of_residual(rr.y) * g1;
+        const double p0 = c * J1[0], p1 = c * J1[1], p2 = c * J1[2];
+        acc[0] = acc[0] + p0 * J1[0]; acc[1] = acc[1] + p0 * J1[1]; acc[2] = acc[2] + p0 * J1[2];
+        acc[3] = acc[3] + p1 * J1[1]; acc[4] = acc[4] + p1 * J1[2]; acc[5] = acc[5] + p2 * J1[2];
+        acc[6] = acc[6] + p0 * rr.y; acc[7] = acc[7] + p1 * rr.y; acc[8] = acc[8] + p2 * rr.y;
+    }
+    acc[9] = acc[9] + huber_rho(rr.x * rr.x + rr.y * rr.y);
+}
+
+// Reduces the threads' partial sums in a fixed tree (split butterfly across lanes, warps in warp
+// order), then warp 0 solves and takes the break decisions of lib.rs:67-81 once and publishes
+// {new inner transform, cost, decision} in ctl->bcast.  Two barriers.  Callers must not write
+// ctl->red / ctl->bcast between two calls without an intervening barrier of their own (the
+// selection of the next evaluation provides several).
+// @region tree_reduce
+template <int NW>
+ICP_DEV void cta_tree_reduce_solve(FusedCtl* ctl, double acc[16], const Transform& Ti, double prev_error)
+{
+    const int lane = lane_id(), warp = warp_id();
+    warp_reduce16(acc);
+    if ((lane & 1) == 0) ctl->red[warp][warp_reduce16_owner(lane)] = acc[0];
+    __syncthreads();
+    if (warp == 0) {
+        double tot = 0.;
+        if (lane < 16) {
+            tot = ctl->red[0][lane];
+            for (int w = 1; w < NW; ++w) tot = tot + ctl->red[w][lane];
+        }
+        double v[10];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) v[q] = shfl_f64(tot, q);
+        const double jtj[9] = {v[0], v[1], v[2], v[1], v[3], v[4], v[2], v[4], v[5]};
+        const double jtr[3] = {v[6], v[7], v[8]};
+        const double error = v[9];
+        double delta[3];
+        uint32_t decision = kBreakCap;   // kBreakCap here = "update accepted"
+        Transform Tn = Ti;
+        if (!solve_normal_equations(jtj, jtr, delta)) decision = kBreakNone;
+        else if ((delta[0] * delta[0] + delta[1] * delta[1]) + delta[2] * delta[2] < kDeltaNormThreshold) decision = kBreakDelta;
+        else if (error > prev_error) decision = kBreakError;
+        else Tn = transform_mul(transform_new(delta[0], delta[1], delta[2]), Ti);
+        if (lane == 0) {
+            ctl->bcast[0] = Tn.r00; ctl->bcast[1] = Tn.r01; ctl->bcast[2] = Tn.r10;
+            ctl->bcast[3] = Tn.r11; ctl->bcast[4] = Tn.tx;  ctl->bcast[5] = Tn.ty;
+            ctl->bcast[6] = error;
+            ctl->bcast[7] = (double)decision;
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
 // calc_stddevs (stats.rs:49-60) over the CTA's residuals: per-axis median, then the median of
 // |r - median|, sigma = 1.4826 * MAD (stats.rs:39-47).  est_med / est_sigma carry the previous
 // evaluation's result in and this one's out: they only steer the (exact) selection's bin map.
@@ -666,64 +739,11 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                         for (int k = 0; k < PPT; ++k) {
                             const int i = tid + k * THREADS;
                             if (i < n) {
-                                const double a0 = -sy[k], a1 = sx[k];
-                                const double J0[3] = {Ti.r00, Ti.r01, Ti.r00 * a0 + Ti.r01 * a1};
-                                const double J1[3] = {Ti.r10, Ti.r11, Ti.r10 * a0 + Ti.r11 * a1};
-                                // J^T W J is accumulated as its upper triangle (6 sums) and mirrored:
-                                // (c J_a) J_b and (c J_b) J_a differ by one rounding per term, the
-                                // same order as the tree reduction's own reordering
-                                if (sigma[0] != 0.) {
-                                    const double c = huber_drho_of_residual(rr[k].x) * g0;
-                                    const double p0 = c * J0[0], p1 = c * J0[1], p2 = c * J0[2];
-                                    acc[0] = acc[0] + p0 * J0[0]; acc[1] = acc[1] + p0 * J0[1]; acc[2] = acc[2] + p0 * J0[2];
-                                    acc[3] = acc[3] + p1 * J0[1]; acc[4] = acc[4] + p1 * J0[2]; acc[5] = acc[5] + p2 * J0[2];
-                                    acc[6] = acc[6] + p0 * rr[k].x; acc[7] = acc[7] + p1 * rr[k].x; acc[8] = acc[8] + p2 * rr[k].x;
-                                }
-                                if (sigma[1] != 0.) {
-                                    const double c = huber_drho_of_residual(rr[k].y) * g1;
-                                    const double p0 = c * J1[0], p1 = c * J1[1], p2 = c * J1[2];
-                                    acc[0] = acc[0] + p0 * J1[0]; acc[1] = acc[1] + p0 * J1[1]; acc[2] = acc[2] + p0 * J1[2];
-                                    acc[3] = acc[3] + p1 * J1[1]; acc[4] = acc[4] + p1 * J1[2]; acc[5] = acc[5] + p2 * J1[2];
-                                    acc[6] = acc[6] + p0 * rr[k].y; acc[7] = acc[7] + p1 * rr[k].y; acc[8] = acc[8] + p2 * rr[k].y;
-                                }
-                                acc[9] = acc[9] + huber_rho(rr[k].x * rr[k].x + rr[k].y * rr[k].y);
+                                tree_accumulate_point(acc, Ti, sx[k], sy[k], rr[k], sigma, g0, g1);
                             }
                         }
 // @region tree_reduce
-                        warp_reduce16(acc);
-                        // (the previous evaluation's readers of ctl->red have passed the barriers of
-                        // this evaluation's selection before anyone writes here)
-                        if ((lane & 1) == 0) ctl->red[warp][warp_reduce16_owner(lane)] = acc[0];
-                        __syncthreads();
-                        // warp 0 adds the warps' partials in warp order, solves and takes the break
-                        // decisions (lib.rs:67-81) once; everyone else picks the outcome up
-                        if (warp == 0) {
-                            double tot = 0.;
-                            if (lane < 16) {
-                                tot = ctl->red[0][lane];
-                                for (int w = 1; w < NW; ++w) tot = tot + ctl->red[w][lane];
-                            }
-                            double v[10];
-#pragma unroll
-                            for (int q = 0; q < 10; ++q) v[q] = shfl_f64(tot, q);
-                            const double jtj[9] = {v[0], v[1], v[2], v[1], v[3], v[4], v[2], v[4], v[5]};
-                            const double jtr[3] = {v[6], v[7], v[8]};
-                            const double error = v[9];
-                            double delta[3];
-                            uint32_t decision = kBreakCap;   // kBreakCap here = "update accepted"
-                            Transform Tn = Ti;
-                            if (!solve_normal_equations(jtj, jtr, delta)) decision = kBreakNone;
-                            else if ((delta[0] * delta[0] + delta[1] * delta[1]) + delta[2] * delta[2] < kDeltaNormThreshold) decision = kBreakDelta;
-                            else if (error > prev_error) decision = kBreakError;
-                            else Tn = transform_mul(transform_new(delta[0], delta[1], delta[2]), Ti);
-                            if (lane == 0) {
-                                ctl->bcast[0] = Tn.r00; ctl->bcast[1] = Tn.r01; ctl->bcast[2] = Tn.r10;
-                                ctl->bcast[3] = Tn.r11; ctl->bcast[4] = Tn.tx;  ctl->bcast[5] = Tn.ty;
-                                ctl->bcast[6] = error;
-                                ctl->bcast[7] = (double)decision;
-                            }
-                        }
-                        __syncthreads();
+                        cta_tree_reduce_solve<NW>(ctl, acc, Ti, prev_error);
                         const uint32_t decision = (uint32_t)ctl->bcast[7];
                         if (decision != kBreakCap) { why = decision; break; }
                         prev_error = ctl->bcast[6];

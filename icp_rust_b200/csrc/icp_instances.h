@@ -1,7 +1,7 @@
 // icp_instances.h — table of the compiled fused-kernel instances (one translation unit each,
 // icp_fused_inst.cu built with -DICP_INST_ID/THREADS/PPT/MINB/ORDERED; list in the Makefile).
 #pragma once
-#include "icp_fused.cuh"
+#include "icp_stream.cuh"
 
 namespace icp {
 
@@ -12,6 +12,14 @@ struct Instance {
     bool ordered;         // reference-order sums (bit-exact) vs warp-tree reductions
     FusedKernel k[2][2];  // [dim-2][shared target]
 };
+
+typedef void (*StreamKernel)(StreamParams);
+constexpr int kStreamThreads = 512;
+struct StreamInstance {
+    int threads;
+    StreamKernel k[2][2];  // [dim-2][shared target]
+};
+extern const StreamInstance kStreamInstance;
 
 #define ICP_DECLARE_INSTANCE(id) extern const Instance kFusedInstance##id;
 ICP_DECLARE_INSTANCE(0) ICP_DECLARE_INSTANCE(1) ICP_DECLARE_INSTANCE(2) ICP_DECLARE_INSTANCE(3)

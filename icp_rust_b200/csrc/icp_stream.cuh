@@ -1,0 +1,303 @@
+// icp_stream.cuh — the ICP loop of one LARGE scan pair in one CTA, state streamed through L2.
+//
+// Same algorithm and helpers as icp_fused.cuh (Icp2d::estimate src/lib.rs:105-130, Icp3d::estimate
+// src/lib.rs:148-173 and everything they call), for scans that do not fit the registers / shared
+// memory of one SM: the bundled 3-D frames hold ~27k points (examples/scan3d.rs:104-131), config 4
+// of BASELINE.json 16k.  Per CTA a workspace slab in global memory (L2-resident: ~2 MB per CTA)
+// holds
+//   - the pair's own sorted cell list (x, y, (z), idx, cstart), built by the CTA itself
+//     (Icp3d::new, lib.rs:139-144) unless a shared device target is used;
+//   - per source point the transformed point and its matched target point (sx, sy | dx, dy).
+// Every Gauss-Newton evaluation streams that state: two exact selections (median, MAD; FAST map
+// with zoom, icp_cta.cuh) and one accumulation pass, reduced as the fixed warp tree of
+// cta_tree_reduce_solve.  Warp-tree sums only (the ordered chain would read 2n rows serially).
+#pragma once
+#include "icp_fused.cuh"
+
+namespace icp {
+
+struct StreamLayout {   // byte offsets inside one CTA's slab
+    uint64_t s0, s1;                       // double2[n_cap] each
+    uint64_t gx, gy, gz, gidx, gslot;      // target copy sorted by cell
+    uint64_t gcnt, gcstart;
+    uint64_t total;
+};
+
+ICP_HD uint64_t align256(uint64_t v) { return (v + 255ull) & ~255ull; }
+
+ICP_HD StreamLayout stream_layout(int dim, uint32_t n_cap, uint32_t m_cap, uint32_t c_cap, bool shared_target)
+{
+    StreamLayout L;
+    uint64_t o = 0;
+    L.s0 = o; o = align256(o + 16ull * n_cap);
+    L.s1 = o; o = align256(o + 16ull * n_cap);
+    if (shared_target) { m_cap = 0; c_cap = 0; }
+    L.gx = o; o = align256(o + 8ull * m_cap);
+    L.gy = o; o = align256(o + 8ull * m_cap);
+    L.gz = o; if (dim == 3) o = align256(o + 8ull * m_cap);
+    L.gidx = o; o = align256(o + 4ull * m_cap);
+    L.gslot = o; o = align256(o + 4ull * m_cap);
+    L.gcnt = o; o = align256(o + 4ull * c_cap);
+    L.gcstart = o; o = align256(o + 4ull * (c_cap + 1ull));
+    L.total = o;
+    return L;
+}
+
+struct StreamParams {
+    FusedParams f;          // same batch description as the fused kernel (workspace/ws_stride = slabs)
+    uint32_t n_cap, m_cap, c_cap;
+};
+
+// residual keys recomputed from the streamed state (lib.rs:34-36)
+struct KeysStreamed {
+    const double2* s0;   // (sx, sy)
+    const double2* s1;   // (dx, dy)
+    Transform Ti;
+    ICP_DEV_MEMBER double2 get(int /*kk*/, int i) const
+    {
+        const double2 s = s0[i], d = s1[i];
+        double tx_, ty_;
+        transform_apply(Ti, s.x, s.y, &tx_, &ty_);
+        double2 r;
+        r.x = tx_ - d.x;
+        r.y = ty_ - d.y;
+        return r;
+    }
+};
+
+constexpr uint32_t kStreamShared = (uint32_t)(((sizeof(SelShared) + 15u) & ~15u) + sizeof(FusedCtl));
+
+// CTA-wide exclusive scan of cnt[0..ncells) into cstart[0..ncells], one contiguous chunk per warp
+template <int THREADS>
+ICP_DEV void cta_scan_cells(const uint32_t* cnt, uint32_t* cstart, uint32_t ncells, uint32_t total, FusedCtl* ctl)
+{
+    constexpr uint32_t NW = THREADS / 32;
+    const int lane = lane_id(), warp = warp_id();
+    const uint32_t chunk = (((ncells + NW - 1) / NW) + 31u) & ~31u;
+    const uint32_t c0 = (uint32_t)warp * chunk;
+    uint32_t s = 0;
+    for (uint32_t c = c0 + lane; c < c0 + chunk; c += 32) s += (c < ncells) ? cnt[c] : 0u;
+    s = warp_sum_u32(s);
+    if (lane == 0) ctl->warp_tot[warp] = s;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < warp; ++w) base += ctl->warp_tot[w];
+    for (uint32_t c = c0 + lane; c < c0 + chunk; c += 32) {
+        const uint32_t v = (c < ncells) ? cnt[c] : 0u;
+        const uint32_t incl = warp_inclusive_scan_u32(v);
+        if (c < ncells) cstart[c] = base + incl - v;
+        base += __shfl_sync(ICP_FULL_MASK, incl, 31);
+    }
+    if (threadIdx.x == 0) cstart[ncells] = total;
+    __syncthreads();
+}
+
+template <int THREADS, int DIM, bool SHARED_TARGET>
+ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, 1) icp_stream_kernel(StreamParams sp)
+{
+    constexpr int NW = THREADS / 32;
+    const FusedParams& p = sp.f;
+    ICP_SHARED_DYN(smem);
+    SelShared* sel = reinterpret_cast<SelShared*>(smem);
+    FusedCtl* ctl = reinterpret_cast<FusedCtl*>(smem + ((sizeof(SelShared) + 15u) & ~15u));
+    const int tid = (int)threadIdx.x, lane = lane_id(), warp = warp_id();
+    const StreamLayout L = stream_layout(DIM, sp.n_cap, sp.m_cap, sp.c_cap, SHARED_TARGET);
+    unsigned char* slab = p.workspace + (size_t)blockIdx.x * p.ws_stride;
+    double2* S0 = reinterpret_cast<double2*>(slab + L.s0);
+    double2* S1 = reinterpret_cast<double2*>(slab + L.s1);
+
+    for (int q = tid; q < 2 * kSelHistPad; q += THREADS) (&sel->hist[0][0])[q] = 0u;
+    int hist_par = 0;
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) ctl->pair = p.pair_begin + atomicAdd(p.work_counter, 1u);
+        __syncthreads();
+        const uint32_t pair = ctl->pair;
+        if (pair >= p.pair_end) break;
+        const int n = (int)(p.src_off[pair + 1] - p.src_off[pair]);
+        const double* src = p.src + (size_t)p.src_off[pair] * DIM;
+        int m;
+        const double* dst = nullptr;
+        if (SHARED_TARGET) {
+            m = (int)p.target.m;
+        } else {
+            m = (int)(p.dst_off[pair + 1] - p.dst_off[pair]);
+            dst = p.dst + (size_t)p.dst_off[pair] * DIM;
+        }
+        Transform T;
+        T.r00 = p.init_T[(size_t)pair * 6 + 0]; T.r01 = p.init_T[(size_t)pair * 6 + 1];
+        T.r10 = p.init_T[(size_t)pair * 6 + 2]; T.r11 = p.init_T[(size_t)pair * 6 + 3];
+        T.tx = p.init_T[(size_t)pair * 6 + 4];  T.ty = p.init_T[(size_t)pair * 6 + 5];
+
+        int status = kPairOk;
+        if (m == 0 && n > 0 && p.max_iter > 0) status = kPairEmptyTarget;
+        if ((uint32_t)n > sp.n_cap || n > 65535 || (!SHARED_TARGET && (uint32_t)m > sp.m_cap)) status = kPairTooLarge;
+        {
+            int bad = 0;
+            for (int q = tid; q < n * DIM; q += THREADS) bad |= !(fabs(src[q]) <= kF64Max);
+            if (!SHARED_TARGET)
+                for (int q = tid; q < m * DIM; q += THREADS) bad |= !(fabs(dst[q]) <= kF64Max);
+            if (tid < 6) bad |= !(fabs(p.init_T[(size_t)pair * 6 + tid]) <= kF64Max);
+            if (__syncthreads_or(bad) && status == kPairOk) status = kPairNonFinite;
+        }
+        if (status != kPairOk) {
+            if (tid == 0) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) p.out_T[(size_t)pair * 6 + q] = p.init_T[(size_t)pair * 6 + q];
+                if (p.out_status) p.out_status[pair] = status;
+                if (p.out_error) atomicMax(p.out_error, status);
+                if (p.out_hash) p.out_hash[pair] = 0ull;
+                if (p.out_inner)
+                    for (uint32_t it = 0; it < p.max_iter; ++it) p.out_inner[(size_t)pair * p.max_iter + it] = 0u;
+            }
+            __syncthreads();
+            continue;
+        }
+
+        // ---- IcpD::new: sorted cell list of this pair's target in the slab
+        GridView<DIM, uint32_t, uint32_t> gv;
+        if (SHARED_TARGET) {
+            gv.x = p.target.x; gv.y = p.target.y; gv.z = p.target.z;
+            gv.idx = p.target.idx; gv.cstart = p.target.cstart; gv.g = p.target.g;
+        } else {
+            double* gx = reinterpret_cast<double*>(slab + L.gx);
+            double* gy = reinterpret_cast<double*>(slab + L.gy);
+            double* gz = reinterpret_cast<double*>(slab + L.gz);
+            uint32_t* gidx = reinterpret_cast<uint32_t*>(slab + L.gidx);
+            uint32_t* gslot = reinterpret_cast<uint32_t*>(slab + L.gslot);
+            uint32_t* gcnt = reinterpret_cast<uint32_t*>(slab + L.gcnt);
+            uint32_t* gcstart = reinterpret_cast<uint32_t*>(slab + L.gcstart);
+            gv.x = gx; gv.y = gy; gv.z = gz; gv.idx = gidx; gv.cstart = gcstart;
+            gv.g = grid_make_geom(0, 0, 0, 0, 0, 0, DIM, 1);
+            if (m > 0) {
+                const double inf = 1.0 / 0.0;
+                double mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};
+                for (int j = tid; j < m; j += THREADS) {
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d) {
+                        const double v = dst[(size_t)j * DIM + d];
+                        mn[d] = fmin(mn[d], v);
+                        mx[d] = fmax(mx[d], v);
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) { mn[d] = warp_min_f64(mn[d]); mx[d] = warp_max_f64(mx[d]); }
+                if (lane == 0) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) { ctl->red[warp][d] = mn[d]; ctl->red[warp][3 + d] = mx[d]; }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int d = 0; d < 3; ++d) { mn[d] = inf; mx[d] = -inf; }
+                for (int w = 0; w < NW; ++w) {
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d) {
+                        mn[d] = fmin(mn[d], ctl->red[w][d]);
+                        mx[d] = fmax(mx[d], ctl->red[w][3 + d]);
+                    }
+                }
+                long long budget = 2ll * m;
+                if (budget < 64) budget = 64;
+                if (budget > (long long)sp.c_cap) budget = (long long)sp.c_cap;
+                const GridGeom g = grid_make_geom(mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], DIM, (int)budget);
+                gv.g = g;
+                const uint32_t ncells = (uint32_t)(g.gx * g.gy * g.gz);
+                for (uint32_t c = (uint32_t)tid; c < ncells; c += THREADS) gcnt[c] = 0u;
+                __syncthreads();
+                auto cell_of = [&](int j) {
+                    const int cx = grid_coord(dst[(size_t)j * DIM + 0], g.ox, g.inv_h, g.gx);
+                    const int cy = grid_coord(dst[(size_t)j * DIM + 1], g.oy, g.inv_h, g.gy);
+                    const int cz = (DIM == 3) ? grid_coord(dst[(size_t)j * DIM + 2], g.oz, g.inv_h, g.gz) : 0;
+                    return (uint32_t)((cz * g.gy + cy) * g.gx + cx);
+                };
+                for (int j = tid; j < m; j += THREADS) gslot[j] = atomicAdd(&gcnt[cell_of(j)], 1u);
+                __syncthreads();
+                cta_scan_cells<THREADS>(gcnt, gcstart, ncells, (uint32_t)m, ctl);
+                for (int j = tid; j < m; j += THREADS) {
+                    const uint32_t pos = gcstart[cell_of(j)] + gslot[j];
+                    gx[pos] = dst[(size_t)j * DIM + 0];
+                    gy[pos] = dst[(size_t)j * DIM + 1];
+                    if (DIM == 3) gz[pos] = dst[(size_t)j * DIM + 2];
+                    gidx[pos] = (uint32_t)j;
+                }
+                __syncthreads();
+            }
+        }
+
+        double est_med[2] = {0., 0.}, est_sigma[2] = {0., 0.};
+        uint64_t H = 0;  // meaningful in thread 0
+        const uint64_t corr_base = (uint64_t)p.src_off[pair] * (p.corr_mode == 2 ? p.max_iter : 1u);
+
+        for (uint32_t it = 0; it < p.max_iter; ++it) {
+            // ---- transform (lib.rs:113-116 / transform_xy lib.rs:52-57) + correspondence search
+            uint64_t hpart = 0;
+            for (int i = tid; i < n; i += THREADS) {
+                double2 s;
+                transform_apply(T, src[(size_t)i * DIM + 0], src[(size_t)i * DIM + 1], &s.x, &s.y);
+                const double pz = (DIM == 3) ? src[(size_t)i * DIM + 2] : 0.0;
+                const NnResult<DIM, uint32_t, uint32_t> r = grid_nn_search(gv, s.x, s.y, pz);
+                double2 d;
+                d.x = gv.x[r.pos]; d.y = gv.y[r.pos];   // get_xy (lib.rs:86-89)
+                S0[i] = s;
+                S1[i] = d;
+                hpart += mix64(((uint64_t)(uint32_t)i << 32) | (uint64_t)(uint32_t)r.idx);
+                if (p.out_corr) {
+                    if (p.corr_mode == 2) p.out_corr[corr_base + (uint64_t)it * (uint64_t)n + (uint64_t)i] = r.idx;
+                    else if (p.corr_mode == 1 && it + 1 == p.max_iter) p.out_corr[corr_base + (uint64_t)i] = r.idx;
+                }
+            }
+            hpart = warp_sum_u64(hpart);
+            if (lane == 0) ctl->hash_part[warp] = hpart;
+            __syncthreads();   // state of every point is visible to the whole CTA
+            if (tid == 0) {
+                uint64_t h = 0;
+                for (int w = 0; w < NW; ++w) h += ctl->hash_part[w];
+                H = H * 0x100000001B3ull + h;
+            }
+
+            // ---- estimate_transform (lib.rs:59-84)
+            Transform Ti = transform_identity();
+            double prev_error = kF64Max;
+            uint32_t accepted = 0, why = kBreakCap;
+            if (n < 2) {
+                why = kBreakNone;
+            } else {
+                for (int inner = 0; inner < kInnerMaxIter; ++inner) {
+                    KeysStreamed ks;
+                    ks.s0 = S0; ks.s1 = S1; ks.Ti = Ti;
+                    double sigma[2];
+                    hist_par = cta_calc_stddevs<THREADS, 0>(sel, ks, n, est_med, est_sigma, hist_par, sigma);
+                    const double g0 = 1. / sigma[0], g1 = 1. / sigma[1];
+                    double acc[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) acc[q] = 0.;
+                    for (int i = tid; i < n; i += THREADS) {
+                        const double2 s = S0[i];
+                        tree_accumulate_point(acc, Ti, s.x, s.y, ks.get(0, i), sigma, g0, g1);
+                    }
+                    cta_tree_reduce_solve<NW>(ctl, acc, Ti, prev_error);
+                    const uint32_t decision = (uint32_t)ctl->bcast[7];
+                    if (decision != kBreakCap) { why = decision; break; }
+                    prev_error = ctl->bcast[6];
+                    Ti.r00 = ctl->bcast[0]; Ti.r01 = ctl->bcast[1]; Ti.r10 = ctl->bcast[2];
+                    Ti.r11 = ctl->bcast[3]; Ti.tx = ctl->bcast[4];  Ti.ty = ctl->bcast[5];
+                    ++accepted;
+                }
+            }
+            T = transform_mul(Ti, T);  // lib.rs:127
+            if (tid == 0 && p.out_inner) p.out_inner[(size_t)pair * p.max_iter + it] = accepted | (why << 16);
+            __syncthreads();
+        }
+        if (tid == 0) {
+            p.out_T[(size_t)pair * 6 + 0] = T.r00; p.out_T[(size_t)pair * 6 + 1] = T.r01;
+            p.out_T[(size_t)pair * 6 + 2] = T.r10; p.out_T[(size_t)pair * 6 + 3] = T.r11;
+            p.out_T[(size_t)pair * 6 + 4] = T.tx;  p.out_T[(size_t)pair * 6 + 5] = T.ty;
+            if (p.out_status) p.out_status[pair] = kPairOk;
+            if (p.out_hash) p.out_hash[pair] = H;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace icp

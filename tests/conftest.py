@@ -19,3 +19,12 @@ def scans2d():
     z = np.load(os.path.join(ROOT, "tests", "golden", "scans2d.npz"))
     pts, off, ids = z["points"], z["offsets"], z["ids"]
     return {int(i): pts[off[k]:off[k + 1]].copy() for k, i in enumerate(ids)}
+
+
+@pytest.fixture(scope="session")
+def scans3d():
+    """First three bundled 3-D frames (tests/golden/scans3d.npz, see make_fixtures.py)."""
+    import numpy as np
+    z = np.load(os.path.join(ROOT, "tests", "golden", "scans3d.npz"))
+    pts, off = z["points"], z["offsets"]
+    return [pts[off[k]:off[k + 1]].copy() for k in range(len(off) - 1)]

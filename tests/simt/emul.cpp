@@ -2,7 +2,7 @@
 // TEST INFRASTRUCTURE: built into tests/simt/_build/libicp_simt.so by tests/simt/Makefile and
 // loaded only by the CPU-only tests.  Never shipped, never a fallback.
 #define ICP_SIMT_EMULATE 1
-#include "icp_fused.cuh"
+#include "icp_stream.cuh"
 #include "icp_stats_kernel.cuh"
 
 #include <vector>
@@ -55,6 +55,50 @@ extern "C" int simt_icp_fused(int dim, int variant, unsigned grid, const double*
         else if (variant == 1) { p.ncap = 1152; run_fused<128, 9, 3>(p, grid, ordered != 0); }
         else if (variant == 2) { p.ncap = 128; run_fused<64, 2, 3>(p, grid, ordered != 0); }
         else { p.ncap = 128; run_fused<32, 4, 3>(p, grid, ordered != 0); }
+    }
+    return err;
+}
+
+// Streaming (large-scan) kernel on the emulator; threads = 32, 64 or 128.
+template <int THREADS, int DIM>
+static void run_stream(StreamParams sp, unsigned grid)
+{
+    simt::launch(grid, THREADS, kStreamShared, [&] { icp_stream_kernel<THREADS, DIM, false>(sp); });
+}
+
+extern "C" int simt_icp_stream(int dim, int threads, unsigned grid, const double* src, const uint32_t* src_off,
+                               const double* dst, const uint32_t* dst_off, const double* init_T, uint32_t B,
+                               uint32_t max_iter, int corr_mode, double* out_T, uint32_t* out_inner, int32_t* out_corr,
+                               uint64_t* out_hash, int32_t* out_status)
+{
+    uint32_t counter = 0;
+    int32_t err = 0;
+    uint32_t ncap = 8, mcap = 8;
+    for (uint32_t b = 0; b < B; ++b) {
+        ncap = std::max(ncap, src_off[b + 1] - src_off[b]);
+        mcap = std::max(mcap, dst_off[b + 1] - dst_off[b]);
+    }
+    ncap = (ncap + 7u) & ~7u;
+    mcap = (mcap + 7u) & ~7u;
+    StreamParams sp{};
+    FusedParams& p = sp.f;
+    p.src = src; p.src_off = src_off; p.dst = dst; p.dst_off = dst_off; p.init_T = init_T;
+    p.out_T = out_T; p.out_inner = out_inner; p.out_corr = out_corr; p.out_hash = out_hash;
+    p.out_status = out_status; p.out_error = &err; p.work_counter = &counter;
+    p.pair_begin = 0; p.pair_end = B; p.max_iter = max_iter; p.corr_mode = corr_mode; p.sm_count = 1;
+    sp.n_cap = ncap; sp.m_cap = mcap; sp.c_cap = std::max(64u, 2u * mcap);
+    const StreamLayout L = stream_layout(dim, sp.n_cap, sp.m_cap, sp.c_cap, false);
+    std::vector<unsigned char> ws((size_t)grid * L.total + 256, 0xCD);
+    p.workspace = ws.data();
+    p.ws_stride = L.total;
+    if (dim == 2) {
+        if (threads == 32) run_stream<32, 2>(sp, grid);
+        else if (threads == 64) run_stream<64, 2>(sp, grid);
+        else run_stream<128, 2>(sp, grid);
+    } else {
+        if (threads == 32) run_stream<32, 3>(sp, grid);
+        else if (threads == 64) run_stream<64, 3>(sp, grid);
+        else run_stream<128, 3>(sp, grid);
     }
     return err;
 }

@@ -65,3 +65,31 @@ def icp_fused(srcs, dsts, init_T, max_iter=20, variant=0, grid=1, corr_mode=2, c
         hashes.ctypes.data_as(C.POINTER(C.c_uint64)), status.ctypes.data_as(C.POINTER(C.c_int32)))
     return {"T": out_T, "inner": inner[:, :max_iter], "corr": corr, "corr_hash": hashes, "status": status,
             "err": err, "src_off": so}
+
+
+def icp_stream(srcs, dsts, init_T, max_iter=20, threads=64, grid=1, corr_mode=2):
+    """The streaming (large-scan) kernel, icp_stream.cuh.  Same result dict as icp_fused."""
+    B = len(srcs)
+    dim = srcs[0].shape[1]
+    so = np.zeros(B + 1, dtype=np.uint32)
+    do = np.zeros(B + 1, dtype=np.uint32)
+    so[1:] = np.cumsum([len(s) for s in srcs])
+    do[1:] = np.cumsum([len(d) for d in dsts])
+    pad = np.zeros((1, dim))
+    src = np.ascontiguousarray(np.concatenate(list(srcs) + [pad]), dtype=np.float64)
+    dst = np.ascontiguousarray(np.concatenate(list(dsts) + [pad]), dtype=np.float64)
+    T0 = np.ascontiguousarray(np.asarray(init_T, dtype=np.float64).reshape(B, 6))
+    out_T = np.zeros((B, 6))
+    inner = np.zeros((B, max(max_iter, 1)), dtype=np.uint32)
+    ncorr = int(so[-1]) * (max_iter if corr_mode == 2 else 1)
+    corr = np.full(max(ncorr, 1), -1, dtype=np.int32)
+    hashes = np.zeros(B, dtype=np.uint64)
+    status = np.zeros(B, dtype=np.int32)
+    err = lib().simt_icp_stream(
+        C.c_int(dim), C.c_int(threads), C.c_uint(grid), src.ctypes.data_as(_dp), so.ctypes.data_as(_u32p),
+        dst.ctypes.data_as(_dp), do.ctypes.data_as(_u32p), T0.ctypes.data_as(_dp), C.c_uint32(B),
+        C.c_uint32(max_iter), C.c_int(corr_mode), out_T.ctypes.data_as(_dp),
+        inner.ctypes.data_as(_u32p), corr.ctypes.data_as(C.POINTER(C.c_int32)),
+        hashes.ctypes.data_as(C.POINTER(C.c_uint64)), status.ctypes.data_as(C.POINTER(C.c_int32)))
+    return {"T": out_T, "inner": inner[:, :max_iter], "corr": corr, "corr_hash": hashes, "status": status,
+            "err": err, "src_off": so}

@@ -209,10 +209,14 @@ def test_status_codes_instead_of_panics(ctx, icp):
         assert np.array_equal(g["T"][b], T0[b], equal_nan=True)
     with pytest.raises(icp.IcpError):
         _run(ctx, icp, srcs, dsts, T0, 2)
+    # above 3072 source points only the streaming kernel (warp-tree sums) holds a scan
     big = rng.normal(0, 100, (3073, 2))
     with pytest.raises(icp.IcpError) as e:
-        _run(ctx, icp, [big], [big], [I6], 1)
+        _run(ctx, icp, [big], [big + 0.25], [I6], 1, ordered=True)
     assert e.value.status == icp.ERR_TOO_LARGE
+    g = _run(ctx, icp, [big], [big + 0.25], [I6], 1)
+    assert ctx.call_info()["block_threads"] == 512
+    _check_vs_oracle(g, [big], [big + 0.25], [I6], 1, ordered=False)
     # max_iter == 0 returns the initial transform (lib.rs:112 runs zero times)
     g = _run(ctx, icp, [a], [a + 1.0], [oracle.transform_new([1., 2., 0.3])], 0)
     assert np.array_equal(g["T"][0], oracle.transform_new([1., 2., 0.3]))
@@ -291,3 +295,65 @@ def test_full_size_config2_properties(ctx, icp, ordered):
     err_t = np.abs(g["T"][:, 4:] - true_T[:, 4:]).max(axis=1)
     err_r = np.abs(g["T"][:, 2] - true_T[:, 2])
     assert np.median(err_t) < 5.0 and np.median(err_r) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# streaming kernel (icp_stream.cuh): scans beyond the fused kernel's capacity
+def test_streaming_kernel_on_config2_pairs(icp):
+    """Same 1080-point pairs, forced through the large-scan kernel: correspondences and iteration
+    counts identical to the oracle, transforms within 1e-9."""
+    os.environ["ICP_B200_FORCE_STREAM"] = "1"
+    try:
+        c = icp.Context(0)
+    finally:
+        os.environ.pop("ICP_B200_FORCE_STREAM")
+    B = 32
+    src, dst, off, _ = icp.synth_scan_pairs(B, beams=1080, first_pair=4242)
+    T0 = np.tile(I6, (B, 1))
+    g = c.estimate_batch(src, off, dst, off, T0, 20, corr_mode=icp.CORR_ALL)
+    assert c.call_info()["block_threads"] == 512
+    g["src_off"] = off
+    _check_vs_oracle(g, [src[off[b]:off[b + 1]] for b in range(B)], [dst[off[b]:off[b + 1]] for b in range(B)],
+                     list(T0), 20, ordered=False)
+    c.close()
+
+
+def test_bundled_3d_frames_chain(ctx, icp, scans3d):
+    """examples/scan3d.rs:104-131: src = frame 0 (27,063 points) fixed, dst = frames 0, 1, 2,
+    warm start, 20 iterations, through the Icp3d facade and through the batch entry.  Frame 0
+    against itself is the degenerate path (all residuals 0 -> sigma 0 -> None every iteration)."""
+    src = scans3d[0]
+    T = I6.copy()
+    for k, dst in enumerate(scans3d):
+        o = oracle.icp_estimate(src, dst, T, 20, nn_mode=oracle.NN_KDTREE, corr_mode=oracle.CORR_LAST)
+        g = ctx.estimate_batch(src, np.array([0, len(src)], np.uint32), dst, np.array([0, len(dst)], np.uint32),
+                               T[None], 20, dim=3, corr_mode=icp.CORR_LAST)
+        assert ctx.call_info()["block_threads"] == 512
+        assert np.array_equal(g["inner"][0], o["inner"])
+        assert int(g["corr_hash"][0]) == int(o["corr_hash"])
+        assert np.array_equal(g["corr"][:len(src)], o["corr"])
+        assert np.abs(g["T"][0] - o["T"]).max() <= TOL
+        est = icp.Icp3d.new(dst, ctx).estimate(src, icp.Transform.from_array(T), 20)
+        assert np.abs(est.to_array() - o["T"]).max() <= TOL
+        if k == 0:
+            assert np.array_equal(g["T"][0], I6) and (g["reason"][0] == icp.BREAK_NONE).all()
+        T = o["T"].copy()
+
+
+def test_config4_shape_batch(ctx, icp, scans3d):
+    """config 4 in small: pairs of 16,384-point 3-D clouds cut from the bundled frames, each pair
+    moved by its own seeded SE(2) transform, seeded initial perturbation."""
+    rng = np.random.default_rng(44)
+    srcs, dsts, T0 = [], [], []
+    for b in range(6):
+        i, j = [(0, 1), (1, 2), (0, 2), (1, 0), (2, 1), (2, 0)][b]
+        W = oracle.transform_new([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-3, 3)])
+        def move(pts):
+            xy = pts[:, :2] @ W[:4].reshape(2, 2).T + W[4:]
+            return np.column_stack([xy, pts[:, 2]])
+        srcs.append(move(scans3d[i][:16384]))
+        dsts.append(move(scans3d[j][:16384]))
+        T0.append(oracle.transform_new([rng.uniform(-0.02, 0.02), rng.uniform(-0.02, 0.02), rng.uniform(-0.01, 0.01)]))
+    g = _run(ctx, icp, srcs, dsts, T0, 20, dim=3)
+    assert ctx.call_info()["block_threads"] == 512
+    _check_vs_oracle(g, srcs, dsts, T0, 20, ordered=False)

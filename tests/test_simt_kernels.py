@@ -134,3 +134,50 @@ def test_fused_status_codes():
     assert g["err"] == 3
     for b in range(3):
         assert np.array_equal(g["T"][b], T0[b], equal_nan=True)
+
+
+# ------------------------------------------------------------------ streaming (large-scan) kernel
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("threads", [32, 128])
+def test_stream_l_shape(dim, threads):  # lib.rs:510-595 through icp_stream.cuh
+    src, dst, init, _ = _l_shape_case(dim)
+    g = E.icp_stream([src], [dst], [init], max_iter=20, threads=threads)
+    _compare(g, _oracle_ref([src], [dst], [init], 20), [src], 20, ordered=False)
+
+
+@pytest.mark.parametrize("schedule", [0, 7])
+def test_stream_real_scans_and_degenerates(scans2d, schedule):
+    E.set_schedule(schedule)
+    try:
+        rng = np.random.default_rng(3)
+        a = rng.normal(0, 100, (40, 2))
+        srcs = [scans2d[1], scans2d[98], a, a[:1], np.zeros((0, 2)), np.zeros((30, 2))]
+        dsts = [scans2d[2], scans2d[99], a.copy(), a, a, np.zeros((30, 2))]
+        T0 = [I6] * len(srcs)
+        g = E.icp_stream(srcs, dsts, T0, max_iter=3, threads=64, grid=2)
+        _compare(g, _oracle_ref(srcs, dsts, T0, 3), srcs, 3, ordered=False)
+        # same bits as the fused kernel's warp-tree mode?  Not required (different summation
+        # tree); but statuses and counts are.
+        assert (g["status"] == 0).all()
+    finally:
+        E.set_schedule(0)
+
+
+def test_stream_crowded_bins_zoom():
+    """3000 residuals with a tiny spread around a large offset: the FAST map's bins are crowded
+    (zoom) or unresolvable in binary32 (RADIX fallback) - the medians must still be exact."""
+    rng = np.random.default_rng(11)
+    n = 3000
+    d = rng.uniform(-1000, 1000, (n, 2))
+    s = d + rng.normal(0, 0.5, (n, 2)) + np.array([0.3, -0.2])
+    g = E.icp_stream([s], [d], [I6], max_iter=2, threads=128)
+    _compare(g, _oracle_ref([s], [d], [I6], 2), [s], 2, ordered=False)
+
+
+def test_stream_status_codes():
+    rng = np.random.default_rng(4)
+    a = rng.normal(0, 100, (20, 2))
+    bad = a.copy()
+    bad[3, 1] = np.nan
+    g = E.icp_stream([a, bad], [np.zeros((0, 2)), a], [I6, I6], max_iter=2, threads=32)
+    assert list(g["status"]) == [1, 3] and g["err"] == 3
