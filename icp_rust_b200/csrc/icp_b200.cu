@@ -78,6 +78,7 @@ struct icp_b200_context {
     std::string last_error;
     int cell_budget = 4096;
     int force_instance = -1;
+    int use_lean = 1;       // ICP_B200_LEAN=0: warp-tree batches on the icp_fused.cuh schedule instead of icp_lean.cuh
     int force_stream = 0;   // ICP_B200_FORCE_STREAM=1: route every warp-tree batch to the streaming kernel (tests)
 };
 
@@ -132,6 +133,7 @@ struct LaunchPlan {
     int mcap = 0;
     int grid = 0;
     FusedKernel kernel = nullptr;
+    bool lean = false;                // icp_lean.cuh schedule of the warp-tree mode
     bool stream = false;              // ... or the streaming kernel for large scans
     StreamKernel skernel = nullptr;
     StreamLayout slayout{};
@@ -155,6 +157,9 @@ int plan_launch(icp_b200_context* ctx, uint32_t dim, bool shared_target, bool or
         plan->inst = inst;
         plan->mcap = (int)((max_m + 7u) & ~7u);
         plan->layout = fused_layout((int)dim, inst->threads * inst->ppt, plan->mcap, ctx->cell_budget, shared_target, ordered);
+        plan->lean = !ordered && ctx->use_lean && inst->lean[dim - 2][shared_target ? 1 : 0] != nullptr;
+        if (plan->lean)
+            plan->layout.total = lean_layout((int)dim, inst->threads * inst->ppt, plan->mcap, ctx->cell_budget, shared_target).total;
         if (!shared_target && max_m > 65528u) inst = nullptr;                   // u16 indices of the shared-memory grid
         else if ((int)plan->layout.total > ctx->max_smem_optin) inst = nullptr;  // does not fit one SM
     }
@@ -180,7 +185,7 @@ int plan_launch(icp_b200_context* ctx, uint32_t dim, bool shared_target, bool or
         plan->grid = (int)std::max<long long>(1, std::min<long long>((long long)occ * ctx->sm_count, pairs));
         return ICP_B200_OK;
     }
-    plan->kernel = inst->k[dim - 2][shared_target ? 1 : 0];
+    plan->kernel = plan->lean ? inst->lean[dim - 2][shared_target ? 1 : 0] : inst->k[dim - 2][shared_target ? 1 : 0];
     plan->threads = inst->threads;
     plan->smem = plan->layout.total;
     plan->ws_stride = ((uint64_t)plan->layout.nn_bytes + 255u) & ~255ull;
@@ -488,6 +493,7 @@ int icp_b200_create(int device, icp_b200_context** out)
     ctx->cell_budget = std::max(16, std::min(65000, env_int("ICP_B200_CELL_BUDGET", 4096)));
     ctx->force_instance = env_int("ICP_B200_FORCE_INSTANCE", -1);
     ctx->force_stream = env_int("ICP_B200_FORCE_STREAM", 0);
+    ctx->use_lean = env_int("ICP_B200_LEAN", 1);
     *out = ctx;
     return ICP_B200_OK;
 }

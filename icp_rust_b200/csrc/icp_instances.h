@@ -1,6 +1,7 @@
 // icp_instances.h — table of the compiled fused-kernel instances (one translation unit each,
 // icp_fused_inst.cu built with -DICP_INST_ID/THREADS/PPT/MINB/ORDERED; list in the Makefile).
 #pragma once
+#include "icp_lean.cuh"
 #include "icp_stream.cuh"
 
 namespace icp {
@@ -11,6 +12,7 @@ struct Instance {
     int threads, ppt, minb;
     bool ordered;         // reference-order sums (bit-exact) vs warp-tree reductions
     FusedKernel k[2][2];  // [dim-2][shared target]
+    FusedKernel lean[2][2];   // icp_lean.cuh schedule of the warp-tree mode (null for ordered instances)
 };
 
 typedef void (*StreamKernel)(StreamParams);

@@ -1,0 +1,550 @@
+// icp_lean.cuh — the whole ICP loop of one scan pair inside one CTA, warp-tree sums, with the
+// robust-scale selection served on a short path.
+//
+// Same algorithm, helpers and results as the warp-tree mode of icp_fused.cuh (Icp2d::estimate
+// src/lib.rs:105-130, Icp3d::estimate src/lib.rs:148-173, estimate_transform lib.rs:59-84,
+// weighted_gauss_newton_update lib.rs:218-261, calc_stddevs stats.rs:49-60); what differs is how a
+// Gauss-Newton evaluation is scheduled on the CTA.  Per evaluation:
+//
+//   all threads   residuals r = Ti*s - d (lib.rs:230-234) -> shared rows; FAST bin of r per axis
+//                 (value-uniform bins around the previous evaluation's median, icp_cta.cuh) ->
+//                 packed two-axis histogram + the point's bin numbers in shared memory
+//   barrier
+//   warp a        axis a: prefix-scan the histogram, find the bin(s) holding the median ranks,
+//                 collect those points' keys by scanning the bin numbers, rank them -> exact median
+//   barrier
+//   all threads   bins of |r - median| -> second histogram
+//   barrier
+//   warp a        same service -> exact MAD; sigma = 1.4826*MAD, 1/sigma and the next
+//                 evaluation's bin maps are published by the service warp
+//   barrier
+//   all threads   Huber weights, Jacobian rows, 10 partial sums; fixed warp tree; warp 0 solves,
+//                 takes the break decisions and publishes the new inner transform (2 barriers)
+//
+// 6 barriers per evaluation and no per-thread selection state.  Whenever the short path cannot
+// serve a selection (no estimate yet, rank outside the binned range, more than 32 keys in the
+// rank's bins) the CTA runs the general selection block_median2 over the shared rows instead, so
+// results never depend on which path ran: both return the exact order statistic.
+#pragma once
+#include "icp_fused.cuh"
+
+namespace icp {
+
+// Short-path histogram: kSelBins regular bins (numbers 1..kSelBins), UNDER = 0, OVER = kSelBins+1;
+// word h[b] packs the count of axis 0 (low half) and axis 1 (high half).  h[1] is 16-byte aligned
+// so that a service lane reads its 8 bins with two 128-bit loads.
+constexpr int kLeanHistWords = 264;          // 3 pad + 258 bins + 3 pad
+constexpr int kLeanHistBase = 3;
+// Buckets: the points of the kLeanWin bins around the bin the previous evaluation's median maps to
+// (number kLeanCentre) are remembered per bin, in arrival order (the slot the histogram atomic
+// returns), so the service warp fetches the median's candidates without looking at other points.
+constexpr int kLeanWin = 64;
+constexpr int kLeanCentre = kSelBins / 2 + 1;
+constexpr int kLeanWinLo = kLeanCentre - kLeanWin / 2;
+constexpr int kLeanCap = 24;
+
+struct LeanSel {
+    SelShared s;                 // histograms + lists of the general selection; list[] also ranks the short path
+    alignas(16) uint32_t lh[2][kLeanHistWords];   // [stage] short-path histogram
+    uint16_t bucket[2][kLeanWin][kLeanCap];    // [axis][bin - kLeanWinLo][slot] -> point index
+    double med[2];               // stage 0 result (median of residuals per axis)
+    double sigma[2];             // stage 1 result (1.4826 * MAD)
+    double g[2];                 // 1 / sigma
+    double est_med[2], est_sigma[2];   // last exact median / sigma (steer the bin maps only)
+    float lo0[2], sc0[2], lo1[2], sc1[2];      // bin maps of the next evaluation, stage 0 / stage 1
+    int valid[2];                // bin maps usable
+    int ok[2];                   // the service warp served its axis in the current stage
+};
+
+struct LeanLayout {
+    FusedLayout f;               // target arrays, build temporaries, residual rows (gn_r)
+    uint32_t bins;               // u32[ncap]: this stage's bin of (axis 0 | axis 1 << 16) per point
+    uint32_t off_sel, off_ctl, total;
+};
+
+ICP_HD LeanLayout lean_layout(int dim, int ncap, int mcap, int cell_budget, bool shared_target)
+{
+    LeanLayout L;
+    L.f = fused_layout(dim, ncap, mcap, cell_budget, shared_target, false);
+    L.bins = align16(L.f.gn_r + 16u * (uint32_t)ncap);
+    uint32_t u = align128(L.bins + 4u * (uint32_t)ncap);
+    if (u < L.f.u_bytes) u = L.f.u_bytes;
+    L.off_sel = u;
+    L.off_ctl = align16(L.off_sel + (uint32_t)sizeof(LeanSel));
+    L.total = align16(L.off_ctl + (uint32_t)sizeof(FusedCtl));
+    return L;
+}
+
+#ifdef ICP_LEAN_STATS
+void lean_stats_record(int stage, int ok, int direct, int b_lo, int b_hi, int count);
+#endif
+// Value-uniform bin in binary32 (icp_cta.cuh sel_bin, mode 0): each step is monotone
+// non-decreasing in v, which is all exactness needs.  0 = UNDER, kSelBins + 1 = OVER.
+// @region lean_bin
+ICP_DEV uint32_t lean_bin(double v, float lo, float scale)
+{
+    float t = (__double2float_rn(v) - lo) * scale;
+    t = fminf(fmaxf(t, -1.0f), (float)kSelBins);
+    return (uint32_t)(__float2int_rd(t) + 1);
+}
+
+// histogram + bucket insertion of one key (all threads)
+ICP_DEV void lean_insert(uint32_t* h, uint16_t (*bucket)[kLeanCap], uint32_t b, uint32_t unit, int sh, int i)
+{
+    const uint32_t slot = (atomicAdd(&h[b], unit) >> sh) & 0xffffu;
+    const uint32_t wb = b - (uint32_t)kLeanWinLo;
+    if (wb < (uint32_t)kLeanWin && slot < (uint32_t)kLeanCap) bucket[wb][slot] = (uint16_t)i;
+}
+
+// Bin holding rank `t` (0-based) among the regular bins whose counts the lanes hold (8 per lane,
+// inclusive prefix `incl`, lane total `tot`): returns bin number, keys below it, its count.
+// All lanes return the same values.  Requires t < total.
+// @region lean_locate
+ICP_DEV void lean_find_rank(const uint32_t c[8], uint32_t incl, uint32_t tot, uint32_t t, uint32_t* bin,
+                            uint32_t* below, uint32_t* count)
+{
+    const int lane = lane_id();
+    const uint32_t vote = __ballot_sync(ICP_FULL_MASK, incl > t);
+    const int owner = __ffs((int)vote) - 1;
+    uint32_t run = incl - tot, bq = 0, bb = 0, bc = 0;
+    bool found = false;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const bool hit = !found && (run + c[q] > t);
+        if (hit) { bq = (uint32_t)q; bb = run; bc = c[q]; found = true; }
+        run += c[q];
+    }
+    *bin = __shfl_sync(ICP_FULL_MASK, (uint32_t)(8 * lane + 1) + bq, owner);
+    *below = __shfl_sync(ICP_FULL_MASK, bb, owner);
+    *count = __shfl_sync(ICP_FULL_MASK, bc, owner);
+}
+
+// One warp serves one axis of one selection stage: returns true and the exact median of the
+// axis' keys (stats.rs:11-28: (b + c) / 2 for even n), or false when the short path cannot
+// decide (caller falls back to block_median2).  Keys: stage 0 r[i].axis, stage 1
+// |r[i].axis - centre|.
+// @region lean_serve
+ICP_DEV bool lean_serve(const uint32_t* h, const uint16_t (*bucket)[kLeanCap], const uint32_t* bins,
+                        const double2* rows, double* list, int n, int axis, int absdev, double centre, double* out)
+{
+    const int lane = lane_id();
+    const int sh = axis * 16;
+    const bool need_hi = (n % 2) == 0;
+    const uint32_t k = need_hi ? (uint32_t)(n / 2 - 1) : (uint32_t)(n / 2);
+    // ---- locate
+    uint32_t c[8];
+    {
+        const uint4 w0 = *reinterpret_cast<const uint4*>(h + 1 + 8 * lane);
+        const uint4 w1 = *reinterpret_cast<const uint4*>(h + 5 + 8 * lane);
+        c[0] = w0.x; c[1] = w0.y; c[2] = w0.z; c[3] = w0.w; c[4] = w1.x; c[5] = w1.y; c[6] = w1.z; c[7] = w1.w;
+    }
+    uint32_t tot = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) tot += c[q];
+    uint32_t incl = warp_inclusive_scan_u32(tot);   // packed halves never carry: <= 65535 keys per axis
+    const uint32_t under = (h[0] >> sh) & 0xffffu;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) c[q] = (c[q] >> sh) & 0xffffu;
+    tot = (tot >> sh) & 0xffffu;
+    incl = ((incl >> sh) & 0xffffu) + under;
+    const uint32_t regular_end = __shfl_sync(ICP_FULL_MASK, incl, 31);   // keys in UNDER + regular bins
+    const uint32_t k_top = need_hi ? k + 1u : k;
+    bool ok = k >= under && k_top < regular_end;
+    uint32_t b_lo = 0, below = 0, c_lo = 0, b_hi = 0, c_hi = 0;
+    if (ok) {
+        lean_find_rank(c, incl, tot, k, &b_lo, &below, &c_lo);
+        b_hi = b_lo;
+        if (need_hi && k + 1u >= below + c_lo) {   // rank k+1 opens the next non-empty bin
+            uint32_t below_hi;
+            lean_find_rank(c, incl, tot, k + 1u, &b_hi, &below_hi, &c_hi);
+        }
+    }
+    const uint32_t count = c_lo + c_hi;
+    ok = ok && count <= (uint32_t)kSelCap;
+    // ---- fetch the candidates: from the buckets, else by scanning the points' bin numbers
+    const uint32_t w_lo = b_lo - (uint32_t)kLeanWinLo, w_hi = b_hi - (uint32_t)kLeanWinLo;
+    const bool direct = w_lo < (uint32_t)kLeanWin && w_hi < (uint32_t)kLeanWin && c_lo <= (uint32_t)kLeanCap &&
+                        c_hi <= (uint32_t)kLeanCap;
+#ifdef ICP_LEAN_STATS
+    if (lane == 0) lean_stats_record(absdev, ok ? 1 : 0, direct ? 1 : 0, (int)b_lo, (int)b_hi, (int)count);
+#endif
+    if (!ok) return false;
+    double mine = 0.;
+    if (direct) {
+        if ((uint32_t)lane < count) {
+            const int i = (uint32_t)lane < c_lo ? (int)bucket[w_lo][lane] : (int)bucket[w_hi][(uint32_t)lane - c_lo];
+            const double2 rr = rows[i];
+            mine = sel_key(axis ? rr.y : rr.x, absdev, centre);
+            list[lane] = mine;
+        }
+        __syncwarp();
+    } else {
+        uint32_t cnt = 0;
+        const uint32_t lt = (1u << lane) - 1u;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const uint32_t w = (i < n) ? bins[i] : 0xffffffffu;
+            const uint32_t b = (w >> sh) & 0xffffu;
+            const bool hit = b == b_lo || b == b_hi;    // 0xffff ("no key") never hits
+            const uint32_t m = __ballot_sync(ICP_FULL_MASK, hit);
+            if (m) {
+                if (hit) {
+                    const double2 rr = rows[i];
+                    list[cnt + (uint32_t)__popc(m & lt)] = sel_key(axis ? rr.y : rr.x, absdev, centre);
+                }
+                cnt += (uint32_t)__popc(m);
+            }
+        }
+        __syncwarp();
+        if ((uint32_t)lane < count) mine = list[lane];
+    }
+    // ---- rank: lt = keys below mine, le = keys not above; the key of rank r satisfies lt <= r < le
+    uint32_t nlt = 0, nle = 0;
+    for (uint32_t m = 0; m < count; ++m) {
+        const double o = list[m];
+        nlt += (o < mine) ? 1u : 0u;
+        nle += (o <= mine) ? 1u : 0u;
+    }
+    const uint32_t kp = k - below;
+    const bool have = (uint32_t)lane < count;
+    const uint32_t vote0 = __ballot_sync(ICP_FULL_MASK, have && nlt <= kp && kp < nle);
+    const uint32_t vote1 = __ballot_sync(ICP_FULL_MASK, have && nlt <= kp + 1u && kp + 1u < nle);
+    const double v0 = shfl_f64(mine, __ffs((int)vote0) - 1);
+    if (need_hi) {
+        const double v1 = shfl_f64(mine, __ffs((int)vote1) - 1);
+        *out = (v0 + v1) / 2.;
+    } else {
+        *out = v0;
+    }
+    return true;
+}
+
+template <int THREADS>
+ICP_DEV void lean_zero_hist(uint32_t* h)
+{
+    for (int q = (int)threadIdx.x; q < kSelHistPad; q += THREADS) h[q] = 0u;
+}
+template <int THREADS>
+ICP_DEV void lean_zero_lh(uint32_t* h)
+{
+    for (int q = (int)threadIdx.x; q < kLeanHistWords; q += THREADS) h[q] = 0u;
+}
+
+// publishes the result of a finished calc_stddevs for axis a: sigma, 1/sigma, and the bin maps
+// the next evaluation will use: kSelBins bins over median +- 2 sigma, then over MAD +- sigma, so
+// that both stages expect their answer in bin kLeanCentre
+// @region lean_publish
+ICP_DEV void lean_publish(LeanSel* sel, int a, double med, double sigma)
+{
+    sel->sigma[a] = sigma;
+    sel->g[a] = 1. / sigma;
+    sel->est_med[a] = med;
+    sel->est_sigma[a] = sigma;
+    float lo0, sc0, lo1, sc1;
+    const bool v0 = sel_fast_params(med - 2.0 * sigma, 4.0 * sigma, &lo0, &sc0);
+    const bool v1 = sel_fast_params(sigma / kPpf34 - sigma, 2.0 * sigma, &lo1, &sc1);
+    sel->lo0[a] = lo0;
+    sel->sc0[a] = sc0;
+    sel->lo1[a] = lo1;
+    sel->sc1[a] = sc1;
+    sel->valid[a] = (v0 && v1) ? 1 : 0;
+}
+
+// General exact selection over the shared rows (any n, any distribution): block_median2 with its
+// FAST / zoom / RADIX maps.  Out of line: it runs once per pair (no estimate yet) and whenever the
+// short path cannot decide, and must not cost the short path registers.
+// @region lean_general_selection
+template <int THREADS, int PPT>
+ICP_DEV_NOINLINE void lean_general_selection(LeanSel* sel, const double2* r2v, int n)
+{
+    const int tid = (int)threadIdx.x;
+    uint32_t* h0 = sel->s.hist[0];
+    uint32_t* h1 = sel->s.hist[1];
+    lean_zero_hist<THREADS>(h0);
+    lean_zero_hist<THREADS>(h1);
+    __syncthreads();
+    double em[2], es[2], sg[2];
+    em[0] = sel->est_med[0]; em[1] = sel->est_med[1];
+    es[0] = sel->est_sigma[0]; es[1] = sel->est_sigma[1];
+    KeysInShared ks;
+    ks.v = r2v;
+    cta_calc_stddevs<THREADS, PPT>(&sel->s, ks, n, em, es, 0, sg);
+    lean_zero_lh<THREADS>(sel->lh[0]);
+    lean_zero_lh<THREADS>(sel->lh[1]);
+    if (tid < 2) lean_publish(sel, tid, tid ? em[1] : em[0], tid ? sg[1] : sg[0]);
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// @region lean_pair_setup
+template <int THREADS, int PPT, int DIM, bool SHARED_TARGET, int MINB>
+ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
+{
+    constexpr int NW = THREADS / 32;
+    constexpr int NCAP = THREADS * PPT;
+    static_assert(THREADS >= 64, "two service warps");
+    ICP_SHARED_DYN(smem);
+    const LeanLayout LL = lean_layout(DIM, NCAP, p.mcap, p.cell_budget, SHARED_TARGET);
+    const FusedLayout& L = LL.f;
+    unsigned char* U = smem;
+    LeanSel* sel = reinterpret_cast<LeanSel*>(smem + LL.off_sel);
+    FusedCtl* ctl = reinterpret_cast<FusedCtl*>(smem + LL.off_ctl);
+    double2* r2v = reinterpret_cast<double2*>(U + L.gn_r);
+    uint32_t* binv = reinterpret_cast<uint32_t*>(U + LL.bins);
+    uint32_t* h0 = sel->lh[0] + kLeanHistBase;
+    uint32_t* h1 = sel->lh[1] + kLeanHistBase;
+
+    const int tid = (int)threadIdx.x, lane = lane_id(), warp = warp_id();
+
+    lean_zero_lh<THREADS>(sel->lh[0]);
+    lean_zero_lh<THREADS>(sel->lh[1]);
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) ctl->pair = p.pair_begin + atomicAdd(p.work_counter, 1u);
+        __syncthreads();
+        const uint32_t pair = ctl->pair;
+        if (pair >= p.pair_end) break;
+        const int n = (int)(p.src_off[pair + 1] - p.src_off[pair]);
+        const double* src = p.src + (size_t)p.src_off[pair] * DIM;
+        int m;
+        const double* dst = nullptr;
+        if (SHARED_TARGET) {
+            m = (int)p.target.m;
+        } else {
+            m = (int)(p.dst_off[pair + 1] - p.dst_off[pair]);
+            dst = p.dst + (size_t)p.dst_off[pair] * DIM;
+        }
+        Transform T;
+        T.r00 = p.init_T[(size_t)pair * 6 + 0]; T.r01 = p.init_T[(size_t)pair * 6 + 1];
+        T.r10 = p.init_T[(size_t)pair * 6 + 2]; T.r11 = p.init_T[(size_t)pair * 6 + 3];
+        T.tx = p.init_T[(size_t)pair * 6 + 4];  T.ty = p.init_T[(size_t)pair * 6 + 5];
+
+        int status = kPairOk;
+        if (m == 0 && n > 0 && p.max_iter > 0) status = kPairEmptyTarget;
+        if (n > NCAP || (!SHARED_TARGET && m > p.mcap)) status = kPairTooLarge;
+        {
+            // the reference panics on NaN residuals (stats.rs:12); reject non-finite input up front
+            int bad = 0;
+            for (int q = tid; q < n * DIM; q += THREADS) bad |= !(fabs(src[q]) <= kF64Max);
+            if (!SHARED_TARGET)
+                for (int q = tid; q < m * DIM; q += THREADS) bad |= !(fabs(dst[q]) <= kF64Max);
+            if (tid < 6) bad |= !(fabs(p.init_T[(size_t)pair * 6 + tid]) <= kF64Max);
+            if (__syncthreads_or(bad) && status == kPairOk) status = kPairNonFinite;
+        }
+        if (status != kPairOk) {
+            if (tid == 0) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) p.out_T[(size_t)pair * 6 + q] = p.init_T[(size_t)pair * 6 + q];
+                if (p.out_status) p.out_status[pair] = status;
+                if (p.out_error) atomicMax(p.out_error, status);
+                if (p.out_hash) p.out_hash[pair] = 0ull;
+                if (p.out_inner)
+                    for (uint32_t it = 0; it < p.max_iter; ++it)
+                        p.out_inner[(size_t)pair * p.max_iter + it] = 0u;
+            }
+            __syncthreads();
+            continue;
+        }
+
+        // ---- Icp2d::new / Icp3d::new (lib.rs:97-102,139-144): sorted cell list of the target
+        GridGeom geom;
+        if (!SHARED_TARGET) {
+            if (m > 0) geom = cta_build_grid<THREADS, DIM>(dst, m, U, L, ctl, p.cell_budget);
+        } else {
+            geom = p.target.g;
+        }
+        if (tid < 2) {   // no estimate of this pair's residual distribution yet
+            sel->valid[tid] = 0;
+            sel->est_med[tid] = 0.;
+            sel->est_sigma[tid] = 0.;
+        }
+
+        uint64_t H = 0;  // meaningful in thread 0
+        const uint64_t corr_base = (uint64_t)p.src_off[pair] * (p.corr_mode == 2 ? p.max_iter : 1u);
+
+        for (uint32_t it = 0; it < p.max_iter; ++it) {
+// @region lean_search
+            // ---- transform (lib.rs:113-116) + correspondence search (lib.rs:118-124): one inlined
+            // copy of the search; queries and matched points go through the thread's own row slots
+            double sx[PPT], sy[PPT], dx[PPT], dy[PPT];
+            uint64_t hpart = 0;
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                const int i = tid + k * THREADS;
+                sx[k] = 0.; sy[k] = 0.; dx[k] = 0.; dy[k] = 0.;
+                if (i < n) {
+                    transform_apply(T, src[(size_t)i * DIM + 0], src[(size_t)i * DIM + 1], &sx[k], &sy[k]);
+                    double2 q;
+                    q.x = sx[k]; q.y = sy[k];
+                    r2v[i] = q;
+                }
+            }
+#pragma unroll 1
+            for (int i = tid; i < n; i += THREADS) {
+                const double2 q = r2v[i];
+                const double pz = (DIM == 3) ? src[(size_t)i * DIM + 2] : 0.0;  // transform_xy keeps z (lib.rs:52-57)
+                double2 d;
+                int idx;
+                if (SHARED_TARGET) {
+                    GridView<DIM, uint32_t, uint32_t> gv;
+                    gv.x = p.target.x; gv.y = p.target.y; gv.z = p.target.z;
+                    gv.idx = p.target.idx; gv.cstart = p.target.cstart; gv.g = geom;
+                    const NnResult<DIM, uint32_t, uint32_t> r = grid_nn_search(gv, q.x, q.y, pz);
+                    d.x = gv.x[r.pos]; d.y = gv.y[r.pos];
+                    idx = r.idx;
+                } else {
+                    GridView<DIM, uint16_t, uint16_t> gv;
+                    gv.x = reinterpret_cast<const double*>(U + L.nn_x);
+                    gv.y = reinterpret_cast<const double*>(U + L.nn_y);
+                    gv.z = reinterpret_cast<const double*>(U + L.nn_z);
+                    gv.idx = reinterpret_cast<const uint16_t*>(U + L.nn_idx);
+                    gv.cstart = reinterpret_cast<const uint16_t*>(U + L.nn_cell);
+                    gv.g = geom;
+                    const NnResult<DIM, uint16_t, uint16_t> r = grid_nn_search(gv, q.x, q.y, pz);
+                    d.x = gv.x[r.pos]; d.y = gv.y[r.pos];
+                    idx = r.idx;
+                }
+                r2v[i] = d;
+                hpart += mix64(((uint64_t)(uint32_t)i << 32) | (uint64_t)(uint32_t)idx);
+                if (p.out_corr) {
+                    if (p.corr_mode == 2) p.out_corr[corr_base + (uint64_t)it * (uint64_t)n + (uint64_t)i] = idx;
+                    else if (p.corr_mode == 1 && it + 1 == p.max_iter) p.out_corr[corr_base + (uint64_t)i] = idx;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                const int i = tid + k * THREADS;
+                if (i < n) {
+                    const double2 d = r2v[i];
+                    dx[k] = d.x; dy[k] = d.y;
+                }
+            }
+            hpart = warp_sum_u64(hpart);
+            if (lane == 0) ctl->hash_part[warp] = hpart;
+            __syncthreads();
+            if (tid == 0) {
+                uint64_t h = 0;
+                for (int w = 0; w < NW; ++w) h += ctl->hash_part[w];
+                H = H * 0x100000001B3ull + h;
+            }
+
+// @region lean_irls
+            // ---- estimate_transform (lib.rs:59-84)
+            Transform Ti = transform_identity();
+            double prev_error = kF64Max;
+            uint32_t accepted = 0, why = kBreakCap;
+            if (n < 2) {
+                why = kBreakNone;  // check_input_size (lib.rs:186-189,225-228)
+            } else {
+                for (int inner = 0; inner < kInnerMaxIter; ++inner) {
+// @region lean_stage0
+                    // residuals (lib.rs:230-234): registers + shared rows (read by the service warps)
+                    double2 rr[PPT];
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k) {
+                        const int i = tid + k * THREADS;
+                        double tx_, ty_;
+                        transform_apply(Ti, sx[k], sy[k], &tx_, &ty_);
+                        rr[k].x = tx_ - dx[k];
+                        rr[k].y = ty_ - dy[k];
+                        if (i < n) r2v[i] = rr[k];
+                    }
+                    bool served = false;
+                    if (sel->valid[0] & sel->valid[1]) {
+                        {
+                            const float lo0 = sel->lo0[0], lo1 = sel->lo0[1], s0 = sel->sc0[0], s1 = sel->sc0[1];
+#pragma unroll
+                            for (int k = 0; k < PPT; ++k) {
+                                const int i = tid + k * THREADS;
+                                if (i < n) {
+                                    const uint32_t b0 = lean_bin(rr[k].x, lo0, s0);
+                                    const uint32_t b1 = lean_bin(rr[k].y, lo1, s1);
+                                    lean_insert(h0, sel->bucket[0], b0, 1u, 0, i);
+                                    lean_insert(h0, sel->bucket[1], b1, 0x10000u, 16, i);
+                                    binv[i] = b0 | (b1 << 16);
+                                }
+                            }
+                        }
+                        __syncthreads();
+                        if (warp < 2) {
+                            double v = 0.;
+                            const bool ok = lean_serve(h0, sel->bucket[warp], binv, r2v, sel->s.list[warp], n, warp, 0, 0., &v);
+                            if (lane == 0) { sel->med[warp] = v; sel->ok[warp] = ok ? 1 : 0; }
+                        }
+                        __syncthreads();
+                        if (sel->ok[0] & sel->ok[1]) {
+// @region lean_stage1
+                            const double m0 = sel->med[0], m1 = sel->med[1];
+                            const float l0 = sel->lo1[0], l1 = sel->lo1[1], s0 = sel->sc1[0], s1 = sel->sc1[1];
+                            lean_zero_lh<THREADS>(sel->lh[0]);
+#pragma unroll
+                            for (int k = 0; k < PPT; ++k) {
+                                const int i = tid + k * THREADS;
+                                if (i < n) {
+                                    const uint32_t b0 = lean_bin(fabs(rr[k].x - m0), l0, s0);
+                                    const uint32_t b1 = lean_bin(fabs(rr[k].y - m1), l1, s1);
+                                    lean_insert(h1, sel->bucket[0], b0, 1u, 0, i);
+                                    lean_insert(h1, sel->bucket[1], b1, 0x10000u, 16, i);
+                                    binv[i] = b0 | (b1 << 16);
+                                }
+                            }
+                            __syncthreads();
+                            if (warp < 2) {
+                                double v = 0.;
+                                const bool ok = lean_serve(h1, sel->bucket[warp], binv, r2v, sel->s.list[warp], n, warp, 1, warp ? m1 : m0, &v);
+                                if (lane == 0) {
+                                    sel->ok[warp] = ok ? 1 : 0;
+                                    if (ok) lean_publish(sel, warp, warp ? m1 : m0, kPpf34 * v);   // stats.rs:39-47
+                                }
+                            }
+                            __syncthreads();
+                            served = (sel->ok[0] & sel->ok[1]) != 0;
+                        }
+                    }
+                    if (!served) {
+// @region lean_general_selection
+                        lean_general_selection<THREADS, PPT>(sel, r2v, n);
+                    } else {
+                        lean_zero_lh<THREADS>(sel->lh[1]);
+                    }
+// @region lean_accumulate
+                    // row weights (lib.rs:245-250), Jacobian (lib.rs:176-184), Huber cost (lib.rs:47-48)
+                    double sigma[2];
+                    sigma[0] = sel->sigma[0]; sigma[1] = sel->sigma[1];
+                    const double g0 = sel->g[0], g1 = sel->g[1];
+                    double acc[16];   // 0-5 upper triangle of jtj, 6-8 jtr, 9 cost, 10-15 unused (zero)
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) acc[q] = 0.;
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k) {
+                        const int i = tid + k * THREADS;
+                        if (i < n) tree_accumulate_point(acc, Ti, sx[k], sy[k], rr[k], sigma, g0, g1);
+                    }
+// @region lean_reduce
+                    cta_tree_reduce_solve<NW>(ctl, acc, Ti, prev_error);
+                    const uint32_t decision = (uint32_t)ctl->bcast[7];
+                    if (decision != kBreakCap) { why = decision; break; }
+                    prev_error = ctl->bcast[6];
+                    Ti.r00 = ctl->bcast[0]; Ti.r01 = ctl->bcast[1]; Ti.r10 = ctl->bcast[2];
+                    Ti.r11 = ctl->bcast[3]; Ti.tx = ctl->bcast[4];  Ti.ty = ctl->bcast[5];
+                    ++accepted;
+                }
+            }
+// @region lean_outer_tail
+            T = transform_mul(Ti, T);  // lib.rs:127
+            if (tid == 0 && p.out_inner) p.out_inner[(size_t)pair * p.max_iter + it] = accepted | (why << 16);
+            __syncthreads();  // rows are rewritten by the next search; ctl->bcast by the next solve
+        }
+        if (tid == 0) {
+            p.out_T[(size_t)pair * 6 + 0] = T.r00; p.out_T[(size_t)pair * 6 + 1] = T.r01;
+            p.out_T[(size_t)pair * 6 + 2] = T.r10; p.out_T[(size_t)pair * 6 + 3] = T.r11;
+            p.out_T[(size_t)pair * 6 + 4] = T.tx;  p.out_T[(size_t)pair * 6 + 5] = T.ty;
+            if (p.out_status) p.out_status[pair] = kPairOk;
+            if (p.out_hash) p.out_hash[pair] = H;
+        }
+        __syncthreads();  // ctl->pair is rewritten at the top of the loop
+    }
+}
+
+}  // namespace icp

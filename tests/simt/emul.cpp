@@ -2,6 +2,7 @@
 // TEST INFRASTRUCTURE: built into tests/simt/_build/libicp_simt.so by tests/simt/Makefile and
 // loaded only by the CPU-only tests.  Never shipped, never a fallback.
 #define ICP_SIMT_EMULATE 1
+#include "icp_lean.cuh"
 #include "icp_stream.cuh"
 #include "icp_stats_kernel.cuh"
 
@@ -9,9 +10,17 @@
 
 using namespace icp;
 
+// ordered: 0 warp-tree (icp_fused.cuh), 1 ordered sums, 2 warp-tree on the icp_lean.cuh schedule
 template <int THREADS, int PPT, int DIM>
-static void run_fused(FusedParams p, unsigned grid, bool ordered)
+static void run_fused(FusedParams p, unsigned grid, int ordered)
 {
+    if (ordered == 2) {
+        if constexpr (THREADS >= 64) {
+            const LeanLayout LL = lean_layout(DIM, THREADS * PPT, p.mcap, p.cell_budget, false);
+            simt::launch(grid, THREADS, LL.total, [&] { icp_lean_kernel<THREADS, PPT, DIM, false, 1>(p); });
+        }
+        return;
+    }
     const FusedLayout L = fused_layout(DIM, THREADS * PPT, p.mcap, p.cell_budget, false, ordered);
     if (ordered) simt::launch(grid, THREADS, L.total, [&] { icp_fused_kernel<THREADS, PPT, DIM, false, 1, true>(p); });
     else simt::launch(grid, THREADS, L.total, [&] { icp_fused_kernel<THREADS, PPT, DIM, false, 1, false>(p); });
@@ -46,15 +55,15 @@ extern "C" int simt_icp_fused(int dim, int variant, unsigned grid, const double*
     p.workspace = ws.data();
     p.ws_stride = L.nn_bytes + 64 - ((L.nn_bytes + 64) % 16);
     if (dim == 2) {
-        if (variant == 0) { p.ncap = 384; run_fused<128, 3, 2>(p, grid, ordered != 0); }
-        else if (variant == 1) { p.ncap = 1152; run_fused<128, 9, 2>(p, grid, ordered != 0); }
-        else if (variant == 2) { p.ncap = 128; run_fused<64, 2, 2>(p, grid, ordered != 0); }
-        else { p.ncap = 128; run_fused<32, 4, 2>(p, grid, ordered != 0); }
+        if (variant == 0) { p.ncap = 384; run_fused<128, 3, 2>(p, grid, ordered); }
+        else if (variant == 1) { p.ncap = 1152; run_fused<128, 9, 2>(p, grid, ordered); }
+        else if (variant == 2) { p.ncap = 128; run_fused<64, 2, 2>(p, grid, ordered); }
+        else { p.ncap = 128; run_fused<32, 4, 2>(p, grid, ordered); }
     } else {
-        if (variant == 0) { p.ncap = 384; run_fused<128, 3, 3>(p, grid, ordered != 0); }
-        else if (variant == 1) { p.ncap = 1152; run_fused<128, 9, 3>(p, grid, ordered != 0); }
-        else if (variant == 2) { p.ncap = 128; run_fused<64, 2, 3>(p, grid, ordered != 0); }
-        else { p.ncap = 128; run_fused<32, 4, 3>(p, grid, ordered != 0); }
+        if (variant == 0) { p.ncap = 384; run_fused<128, 3, 3>(p, grid, ordered); }
+        else if (variant == 1) { p.ncap = 1152; run_fused<128, 9, 3>(p, grid, ordered); }
+        else if (variant == 2) { p.ncap = 128; run_fused<64, 2, 3>(p, grid, ordered); }
+        else { p.ncap = 128; run_fused<32, 4, 3>(p, grid, ordered); }
     }
     return err;
 }

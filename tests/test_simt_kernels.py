@@ -28,7 +28,7 @@ def _compare(g, refs, srcs, max_iter, ordered=True):
         gc = g["corr"][int(so[b]) * max_iter:int(so[b]) * max_iter + n * max_iter].reshape(max_iter, n)
         assert np.array_equal(gc, o["corr"]), f"pair {b}: correspondences differ"
         assert np.array_equal(g["inner"][b], o["inner"]), f"pair {b}: inner iteration counts differ"
-        if ordered:
+        if ordered is True:
             assert np.array_equal(g["T"][b], o["T"]), f"pair {b}: transform differs"
         else:
             assert np.abs(g["T"][b] - o["T"]).max() <= 1e-9, f"pair {b}: transform differs by more than 1e-9"
@@ -79,10 +79,12 @@ def _l_shape_case(dim):
     return src, dst, init, true_T
 
 
-@pytest.mark.parametrize("ordered", [True, False])
+@pytest.mark.parametrize("ordered", [True, False, "lean"])
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("variant", [2, 3])
 def test_fused_l_shape(dim, variant, ordered):  # lib.rs:510-595
+    if ordered == "lean" and variant == 3:
+        pytest.skip("icp_lean.cuh needs two service warps")
     src, dst, init, true_T = _l_shape_case(dim)
     g = E.icp_fused([src], [dst], [init], max_iter=20, variant=variant, ordered=ordered)
     _compare(g, _oracle_ref([src], [dst], [init], 20), [src], 20, ordered)
@@ -91,7 +93,7 @@ def test_fused_l_shape(dim, variant, ordered):  # lib.rs:510-595
         assert np.linalg.norm(got - q[:2]) < 1e-3
 
 
-@pytest.mark.parametrize("ordered", [True, False])
+@pytest.mark.parametrize("ordered", [True, False, "lean"])
 @pytest.mark.parametrize("schedule", [0, 1, 7])
 def test_fused_real_scans(scans2d, schedule, ordered):
     E.set_schedule(schedule)
@@ -101,7 +103,8 @@ def test_fused_real_scans(scans2d, schedule, ordered):
         T0 = [I6, I6]
         g = E.icp_fused(srcs, dsts, T0, max_iter=3, variant=1, grid=2, ordered=ordered)
         _compare(g, _oracle_ref(srcs, dsts, T0, 3), srcs, 3, ordered)
-        if not ordered:   # tree reductions are schedule-independent: same bits under every interleaving
+        if ordered is not True:   # tree reductions are schedule-independent: same bits under every interleaving,
+            # and the same bits on either schedule of the warp-tree mode (icp_fused.cuh / icp_lean.cuh)
             ref = E.icp_fused(srcs, dsts, T0, max_iter=3, variant=1, grid=1, ordered=False)
             assert np.array_equal(ref["T"], g["T"])
     finally:
@@ -114,7 +117,7 @@ def test_fused_degenerate_pairs():
     srcs = [a, a[:1], np.zeros((0, 2)), a, np.zeros((30, 2))]
     dsts = [a.copy(), a, a, a[:1], np.zeros((30, 2))]  # identical clouds: sigma == 0 -> None
     T0 = [I6] * 5
-    for ordered in (True, False):
+    for ordered in (True, False, "lean"):
         g = E.icp_fused(srcs, dsts, T0, max_iter=4, variant=2, grid=1, ordered=ordered)
         _compare(g, _oracle_ref(srcs, dsts, T0, 4), srcs, 4, ordered)
         assert np.array_equal(g["T"][0], I6)
@@ -129,11 +132,30 @@ def test_fused_status_codes():
     srcs = [a, bad, a]
     dsts = [np.zeros((0, 2)), a, a]
     T0 = [I6, I6, np.array([1., 0., 0., 1., np.inf, 0.])]
-    g = E.icp_fused(srcs, dsts, T0, max_iter=2, variant=2)
-    assert list(g["status"]) == [1, 3, 3]
-    assert g["err"] == 3
-    for b in range(3):
-        assert np.array_equal(g["T"][b], T0[b], equal_nan=True)
+    for ordered in (True, "lean"):
+        g = E.icp_fused(srcs, dsts, T0, max_iter=2, variant=2, ordered=ordered)
+        assert list(g["status"]) == [1, 3, 3]
+        assert g["err"] == 3
+        for b in range(3):
+            assert np.array_equal(g["T"][b], T0[b], equal_nan=True)
+
+
+def test_lean_crowded_and_odd_sizes():
+    """icp_lean.cuh: the short selection path must hand over to the general selection whenever it
+    cannot decide (crowded bins, heavy duplicates, tiny spreads around a large offset) and the
+    result must not depend on which path ran.  Odd and even n (stats.rs:23-27)."""
+    rng = np.random.default_rng(12)
+    srcs, dsts = [], []
+    for n, spread in ((1101, 0.5), (1100, 1e-7), (333, 30.0), (64, 3.0)):
+        d = rng.uniform(-1000, 1000, (n, 2))
+        s = d + rng.normal(0, spread, (n, 2)) + np.array([0.3, -0.2])
+        s[: n // 3] = d[: n // 3] + np.array([0.25, 0.25])   # one third share the same residual
+        srcs.append(s); dsts.append(d)
+    T0 = [I6] * len(srcs)
+    g = E.icp_fused(srcs, dsts, T0, max_iter=3, variant=1, grid=2, ordered="lean")
+    _compare(g, _oracle_ref(srcs, dsts, T0, 3), srcs, 3, ordered=False)
+    ref = E.icp_fused(srcs, dsts, T0, max_iter=3, variant=1, grid=1, ordered=False)
+    assert np.array_equal(ref["T"], g["T"]) and np.array_equal(ref["inner"], g["inner"])
 
 
 # ------------------------------------------------------------------ streaming (large-scan) kernel
