@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(_HERE, "lib")
+LIB_DIR = os.environ.get("ICP_B200_LIB_DIR") or os.path.join(_HERE, "lib")   # override: debug builds (tools/)
 CUDA_SO = os.path.join(LIB_DIR, "libicp_b200.so")
 SYNTH_SO = os.path.join(LIB_DIR, "libicp_synth.so")
 

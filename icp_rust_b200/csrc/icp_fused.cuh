@@ -352,27 +352,71 @@ ICP_DEV ChainPtrs chain_role(int lane, const double2* r2, const double2* c2, con
 // J^T W J is accumulated as its upper triangle and mirrored: (c J_a) J_b and (c J_b) J_a differ by
 // one rounding per term, the same order as the tree reduction's own reordering.
 // @region tree_accumulate
+// `valid` false (a thread's slot beyond the scan's last point; its coordinates are zeros, its
+// residual is finite): every term is formed and enters as c = 0, i.e. as +-0, which leaves the
+// sums unchanged.  No branch on it, so the PPT points of a thread form one basic block and their
+// quotients and square roots overlap.
 ICP_DEV void tree_accumulate_point(double acc[16], const Transform& Ti, double sx, double sy, double2 rr,
-                                   const double sigma[2], double g0, double g1)
+                                   const double sigma[2], double g0, double g1, bool valid = true)
 {
     const double a0 = -sy, a1 = sx;   // jacobian(), lib.rs:176-184
     const double J0[3] = {Ti.r00, Ti.r01, Ti.r00 * a0 + Ti.r01 * a1};
     const double J1[3] = {Ti.r10, Ti.r11, Ti.r10 * a0 + Ti.r11 * a1};
     if (sigma[0] != 0.) {
-        const double c = huber_drho_of_residual(rr.x) * g0;
+        const double cw = huber_drho_of_residual(rr.x) * g0;
+        const double c = valid ? cw : 0.;
         const double p0 = c * J0[0], p1 = c * J0[1], p2 = c * J0[2];
         acc[0] = acc[0] + p0 * J0[0]; acc[1] = acc[1] + p0 * J0[1]; acc[2] = acc[2] + p0 * J0[2];
         acc[3] = acc[3] + p1 * J0[1]; acc[4] = acc[4] + p1 * J0[2]; acc[5] = acc[5] + p2 * J0[2];
         acc[6] = acc[6] + p0 * rr.x; acc[7] = acc[7] + p1 * rr.x; acc[8] = acc[8] + p2 * rr.x;
     }
     if (sigma[1] != 0.) {
-        const double c = huber_drho_of_residual(rr.y) * g1;
+        const double cw = huber_drho_of_residual(rr.y) * g1;
+        const double c = valid ? cw : 0.;
         const double p0 = c * J1[0], p1 = c * J1[1], p2 = c * J1[2];
         acc[0] = acc[0] + p0 * J1[0]; acc[1] = acc[1] + p0 * J1[1]; acc[2] = acc[2] + p0 * J1[2];
         acc[3] = acc[3] + p1 * J1[1]; acc[4] = acc[4] + p1 * J1[2]; acc[5] = acc[5] + p2 * J1[2];
         acc[6] = acc[6] + p0 * rr.y; acc[7] = acc[7] + p1 * rr.y; acc[8] = acc[8] + p2 * rr.y;
     }
-    acc[9] = acc[9] + huber_rho(rr.x * rr.x + rr.y * rr.y);
+    const double rho = huber_rho(rr.x * rr.x + rr.y * rr.y);
+    acc[9] = acc[9] + (valid ? rho : 0.);
+}
+
+// @region solve3x3
+// The same solve by one full warp whose lanes hold identical arguments: all lanes form the nine
+// cofactor numerators, lane q < 9 forms the one quotient i_q = numerator_q / det and the warp
+// exchanges them — one division on the critical path instead of nine.  Same operations on the
+// same operands as solve_normal_equations, hence the same bits.
+ICP_DEV bool solve_normal_equations_warp(const double m[9], const double jtr[3], double delta[3])
+{
+    const double m00 = m[0], m01 = m[1], m02 = m[2];
+    const double m10 = m[3], m11 = m[4], m12 = m[5];
+    const double m20 = m[6], m21 = m[7], m22 = m[8];
+    const double n00 = m22 * m11 - m21 * m12;
+    const double c01 = m22 * m01 - m21 * m02;
+    const double n02 = m12 * m01 - m11 * m02;
+    const double det = m00 * n00 - m10 * c01 + m20 * n02;
+    if (det == 0.) return false;
+    const double n01 = -c01;
+    const double n10 = -(m22 * m10 - m20 * m12);
+    const double n11 = m22 * m00 - m20 * m02;
+    const double n12 = -(m12 * m00 - m10 * m02);
+    const double n20 = m21 * m10 - m20 * m11;
+    const double n21 = -(m21 * m00 - m20 * m01);
+    const double n22 = m11 * m00 - m10 * m01;
+    const int lane = lane_id();
+    double num = n00;
+    num = lane == 1 ? n01 : num; num = lane == 2 ? n02 : num;
+    num = lane == 3 ? n10 : num; num = lane == 4 ? n11 : num; num = lane == 5 ? n12 : num;
+    num = lane == 6 ? n20 : num; num = lane == 7 ? n21 : num; num = lane == 8 ? n22 : num;
+    const double iq = num / det;
+    const double i00 = shfl_f64(iq, 0), i01 = shfl_f64(iq, 1), i02 = shfl_f64(iq, 2);
+    const double i10 = shfl_f64(iq, 3), i11 = shfl_f64(iq, 4), i12 = shfl_f64(iq, 5);
+    const double i20 = shfl_f64(iq, 6), i21 = shfl_f64(iq, 7), i22 = shfl_f64(iq, 8);
+    delta[0] = ((-i00) * jtr[0] + (-i01) * jtr[1]) + (-i02) * jtr[2];
+    delta[1] = ((-i10) * jtr[0] + (-i11) * jtr[1]) + (-i12) * jtr[2];
+    delta[2] = ((-i20) * jtr[0] + (-i21) * jtr[1]) + (-i22) * jtr[2];
+    return true;
 }
 
 // Reduces the threads' partial sums in a fixed tree (split butterfly across lanes, warps in warp
@@ -403,7 +447,7 @@ ICP_DEV void cta_tree_reduce_solve(FusedCtl* ctl, double acc[16], const Transfor
         double delta[3];
         uint32_t decision = kBreakCap;   // kBreakCap here = "update accepted"
         Transform Tn = Ti;
-        if (!solve_normal_equations(jtj, jtr, delta)) decision = kBreakNone;
+        if (!solve_normal_equations_warp(jtj, jtr, delta)) decision = kBreakNone;
         else if ((delta[0] * delta[0] + delta[1] * delta[1]) + delta[2] * delta[2] < kDeltaNormThreshold) decision = kBreakDelta;
         else if (error > prev_error) decision = kBreakError;
         else Tn = transform_mul(transform_new(delta[0], delta[1], delta[2]), Ti);

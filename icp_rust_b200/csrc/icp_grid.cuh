@@ -155,10 +155,13 @@ ICP_DEV NnResult<DIM, IdxT, CellT> grid_nn_search(const GridView<DIM, IdxT, Cell
     best.idx = 0x7fffffff;
     best.pos = -1;
     const double inf = 1.0 / 0.0;
-    for (int rho = 0;; ++rho) {
+    // 2-D: the first step scans the whole 3x3 block (rings 0 and 1 together).  The lanes of a warp
+    // almost never all stop after ring 0, so its separate bound test and row bookkeeping only
+    // cost; the set of visited cells before each bound test is still a full block [x0,x1]x[y0,y1].
+    for (int rho = (DIM == 2) ? 1 : 0;; ++rho) {
         const int x0 = cx - rho, x1 = cx + rho, y0 = cy - rho, y1 = cy + rho;
         if (DIM == 2) {
-            grid_scan_ring_slab(gv, 0, x0, x1, y0, y1, false, qx, qy, qz, best);
+            grid_scan_ring_slab(gv, 0, x0, x1, y0, y1, rho == 1, qx, qy, qz, best);
         } else {
             const int z0 = cz - rho, z1 = cz + rho;
             const int za = z0 < 0 ? 0 : z0, zb = z1 > g.gz - 1 ? g.gz - 1 : z1;

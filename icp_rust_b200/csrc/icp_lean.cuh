@@ -26,6 +26,9 @@
 // rank's bins) the CTA runs the general selection block_median2 over the shared rows instead, so
 // results never depend on which path ran: both return the exact order statistic.
 #pragma once
+#ifdef ICP_LEAN_TIMING
+#include <cstdio>
+#endif
 #include "icp_fused.cuh"
 
 namespace icp {
@@ -236,18 +239,20 @@ ICP_DEV void lean_zero_lh(uint32_t* h)
 // @region lean_publish
 ICP_DEV void lean_publish(LeanSel* sel, int a, double med, double sigma)
 {
+    const double g = 1. / sigma;
     sel->sigma[a] = sigma;
-    sel->g[a] = 1. / sigma;
+    sel->g[a] = g;
     sel->est_med[a] = med;
     sel->est_sigma[a] = sigma;
-    float lo0, sc0, lo1, sc1;
-    const bool v0 = sel_fast_params(med - 2.0 * sigma, 4.0 * sigma, &lo0, &sc0);
-    const bool v1 = sel_fast_params(sigma / kPpf34 - sigma, 2.0 * sigma, &lo1, &sc1);
-    sel->lo0[a] = lo0;
-    sel->sc0[a] = sc0;
-    sel->lo1[a] = lo1;
-    sel->sc1[a] = sc1;
-    sel->valid[a] = (v0 && v1) ? 1 : 0;
+    // bins/width from the quotient already formed (the maps only steer the selection; any
+    // monotone map gives the same exact order statistic): kSelBins/(4 sigma), kSelBins/(2 sigma)
+    const double lo0 = med - 2.0 * sigma, sc0 = (0.25 * (double)kSelBins) * g;
+    const double lo1 = sigma * (1.0 / kPpf34) - sigma, sc1 = (0.5 * (double)kSelBins) * g;
+    sel->lo0[a] = __double2float_rn(lo0);
+    sel->sc0[a] = __double2float_rn(sc0);
+    sel->lo1[a] = __double2float_rn(lo1);
+    sel->sc1[a] = __double2float_rn(sc1);
+    sel->valid[a] = (sigma > 0.0 && sc0 < 1e30 && sc1 > 1e-30 && fabs(lo0) < 1e30 && fabs(lo1) < 1e30) ? 1 : 0;
 }
 
 // General exact selection over the shared rows (any n, any distribution): block_median2 with its
@@ -275,6 +280,18 @@ ICP_DEV_NOINLINE void lean_general_selection(LeanSel* sel, const double2* r2v, i
     __syncthreads();
 }
 
+// Phase timing of CTA 0 (debug builds only, -DICP_LEAN_TIMING): thread 0 accumulates clock64()
+// differences between the barriers of an evaluation and prints the per-pair averages.
+#ifdef ICP_LEAN_TIMING
+#define ICP_LT_DECL long long lt_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long lt_t = 0, lt_n = 0, lt_e = 0;
+#define ICP_LT_START lt_t = clock64();
+#define ICP_LT_MARK(q) { const long long lt_now = clock64(); lt_acc[q] += lt_now - lt_t; lt_t = lt_now; }
+#else
+#define ICP_LT_DECL
+#define ICP_LT_START
+#define ICP_LT_MARK(q)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // @region lean_pair_setup
 template <int THREADS, int PPT, int DIM, bool SHARED_TARGET, int MINB>
@@ -299,8 +316,10 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
     lean_zero_lh<THREADS>(sel->lh[0]);
     lean_zero_lh<THREADS>(sel->lh[1]);
     __syncthreads();
+    ICP_LT_DECL
 
     for (;;) {
+        ICP_LT_START
         if (tid == 0) ctl->pair = p.pair_begin + atomicAdd(p.work_counter, 1u);
         __syncthreads();
         const uint32_t pair = ctl->pair;
@@ -363,6 +382,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
         uint64_t H = 0;  // meaningful in thread 0
         const uint64_t corr_base = (uint64_t)p.src_off[pair] * (p.corr_mode == 2 ? p.max_iter : 1u);
 
+        ICP_LT_MARK(0)
         for (uint32_t it = 0; it < p.max_iter; ++it) {
 // @region lean_search
             // ---- transform (lib.rs:113-116) + correspondence search (lib.rs:118-124): one inlined
@@ -428,6 +448,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                 for (int w = 0; w < NW; ++w) h += ctl->hash_part[w];
                 H = H * 0x100000001B3ull + h;
             }
+            ICP_LT_MARK(1)
 
 // @region lean_irls
             // ---- estimate_transform (lib.rs:59-84)
@@ -467,12 +488,14 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                             }
                         }
                         __syncthreads();
+                        ICP_LT_MARK(2)
                         if (warp < 2) {
                             double v = 0.;
                             const bool ok = lean_serve(h0, sel->bucket[warp], binv, r2v, sel->s.list[warp], n, warp, 0, 0., &v);
                             if (lane == 0) { sel->med[warp] = v; sel->ok[warp] = ok ? 1 : 0; }
                         }
                         __syncthreads();
+                        ICP_LT_MARK(3)
                         if (sel->ok[0] & sel->ok[1]) {
 // @region lean_stage1
                             const double m0 = sel->med[0], m1 = sel->med[1];
@@ -490,6 +513,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                                 }
                             }
                             __syncthreads();
+                            ICP_LT_MARK(4)
                             if (warp < 2) {
                                 double v = 0.;
                                 const bool ok = lean_serve(h1, sel->bucket[warp], binv, r2v, sel->s.list[warp], n, warp, 1, warp ? m1 : m0, &v);
@@ -499,6 +523,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                                 }
                             }
                             __syncthreads();
+                            ICP_LT_MARK(5)
                             served = (sel->ok[0] & sel->ok[1]) != 0;
                         }
                     }
@@ -519,10 +544,15 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
 #pragma unroll
                     for (int k = 0; k < PPT; ++k) {
                         const int i = tid + k * THREADS;
-                        if (i < n) tree_accumulate_point(acc, Ti, sx[k], sy[k], rr[k], sigma, g0, g1);
+                        tree_accumulate_point(acc, Ti, sx[k], sy[k], rr[k], sigma, g0, g1, i < n);
                     }
 // @region lean_reduce
+                    ICP_LT_MARK(6)
+#ifdef ICP_LEAN_TIMING
+                    ++lt_e;
+#endif
                     cta_tree_reduce_solve<NW>(ctl, acc, Ti, prev_error);
+                    ICP_LT_MARK(7)
                     const uint32_t decision = (uint32_t)ctl->bcast[7];
                     if (decision != kBreakCap) { why = decision; break; }
                     prev_error = ctl->bcast[6];
@@ -544,7 +574,17 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
             if (p.out_hash) p.out_hash[pair] = H;
         }
         __syncthreads();  // ctl->pair is rewritten at the top of the loop
+        ICP_LT_MARK(8)
+#ifdef ICP_LEAN_TIMING
+        ++lt_n;
+#endif
     }
+#ifdef ICP_LEAN_TIMING
+    if (blockIdx.x == 0 && tid == 0 && lt_n > 0)
+        printf("lean timing CTA0: pairs %lld evals %lld | cycles/pair: setup+build %lld search %lld tail %lld | cycles/eval: stage0 %lld serve0 %lld stage1 %lld serve1 %lld accumulate %lld reduce+solve %lld\n",
+               lt_n, lt_e, lt_acc[0] / lt_n, lt_acc[1] / lt_n, lt_acc[8] / lt_n, lt_acc[2] / lt_e, lt_acc[3] / lt_e,
+               lt_acc[4] / lt_e, lt_acc[5] / lt_e, lt_acc[6] / lt_e, lt_acc[7] / lt_e);
+#endif
 }
 
 }  // namespace icp

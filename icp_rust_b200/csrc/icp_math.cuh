@@ -184,11 +184,13 @@ ICP_DEV void sincos_libm(double x, double* s, double* c)
 // ---------------------------------------------------------------------------------------------
 // src/huber.rs:6-15 / 17-26 (argument e is the SQUARED residual)
 // @region huber
+// Branch-free on purpose: lanes of a warp rarely agree on the branch, and without it the square
+// roots / quotients of a thread's points are independent instructions the scheduler interleaves.
 ICP_DEV double huber_rho(double e)
 {
     const double k2 = kHuberK * kHuberK;
-    if (e <= k2) return e;
-    return 2. * kHuberK * sqrt(e) - k2;
+    const double far = 2. * kHuberK * sqrt(e) - k2;
+    return (e <= k2) ? e : far;
 }
 ICP_DEV double huber_drho(double e)
 {
@@ -206,9 +208,9 @@ ICP_DEV double huber_drho_of_residual(double r)
 {
     const double k2 = kHuberK * kHuberK;
     const double e = r * r;
-    if (e <= k2) return 1.;
-    if (e > kF64Max) return kHuberK / sqrt(e);
-    return kHuberK / fabs(r);
+    const double den = (e > kF64Max) ? e : fabs(r);   // e == +inf there and sqrt(+inf) == +inf
+    const double q = kHuberK / den;                   // r == 0: k / 0 = +inf, not selected
+    return (e <= k2) ? 1. : q;
 }
 
 // ---------------------------------------------------------------------------------------------
