@@ -88,6 +88,8 @@ struct icp_b200_target {
     uint32_t m = 0;
     GridGeom g{};
     DevBuf pts, x, y, z, idx, cstart, cnt, slot, keys;
+    DevBuf pf, seed;          // 2-D fast search (icp_target_nn.cuh); seed_ptr null when it is off
+    const uint32_t* seed_ptr = nullptr;
     DevBuf queries, out_idx;
 };
 
@@ -232,6 +234,7 @@ int launch_range(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_
         p.target.x = tgt->x.as<double>(); p.target.y = tgt->y.as<double>(); p.target.z = tgt->z.as<double>();
         p.target.idx = tgt->idx.as<uint32_t>(); p.target.cstart = tgt->cstart.as<uint32_t>();
         p.target.g = tgt->g; p.target.m = tgt->m;
+        p.target.seed = tgt->seed_ptr; p.target.pf = tgt->seed_ptr ? tgt->pf.as<float2>() : nullptr;
     }
     const uint32_t pairs = end - begin;
     const int grid = (int)std::min<uint32_t>((uint32_t)plan.grid, pairs);
@@ -609,8 +612,11 @@ int icp_b200_target_create(icp_b200_context* ctx, uint32_t dim, const double* ds
         unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
         double d; std::memcpy(&d, &b, 8); return d;
     };
-    // cell budget: about two cells per point, bounded (cell table stays L2-resident)
-    long long budget = std::max<long long>(64, std::min<long long>((long long)m * env_int("ICP_B200_TARGET_CELLS_PER_POINT", 2), 1ll << 24));
+    // cell budget per point, bounded (cell tables stay L2-resident).  2-D targets search a seeded disc
+    // (icp_target_nn.cuh): empty cells cost nothing there, so the cells are small; the ring search of
+    // 3-D targets pays for every empty cell it crosses.
+    const int cells_per_point = env_int("ICP_B200_TARGET_CELLS_PER_POINT", dim == 2 ? 32 : 2);
+    long long budget = std::max<long long>(64, std::min<long long>((long long)m * cells_per_point, 1ll << 24));
     t->g = grid_make_geom(unkey(keys[0]), unkey(keys[1]), unkey(keys[2]), unkey(keys[3]), unkey(keys[4]), unkey(keys[5]), (int)dim, (int)budget);
     const uint32_t ncells = (uint32_t)(t->g.gx * t->g.gy * t->g.gz);
     ICP_T(t->cnt.ensure((size_t)ncells * 4));
@@ -618,12 +624,41 @@ int icp_b200_target_create(icp_b200_context* ctx, uint32_t dim, const double* ds
     ICP_T(cudaMemsetAsync(t->cnt.p, 0, (size_t)ncells * 4, st));
     tb.g = t->g; tb.cnt = t->cnt.as<uint32_t>(); tb.slot = t->slot.as<uint32_t>(); tb.cstart = t->cstart.as<uint32_t>();
     tb.x = t->x.as<double>(); tb.y = t->y.as<double>(); tb.z = t->z.as<double>(); tb.idx = t->idx.as<uint32_t>();
+    // binary32 filter + seeds: 2-D, and a geometry whose squares stay inside binary32's range
+    const bool fast2d = dim == 2 && env_int("ICP_B200_TARGET_FAST", 1) != 0 && t->g.h >= 1e-10 &&
+                        t->g.h * (double)std::max(t->g.gx, t->g.gy) <= 1e15;
+    if (fast2d) {
+        ICP_T(t->pf.ensure((size_t)m * 8));
+        ICP_T(t->seed.ensure((size_t)ncells * 4));
+        tb.pf = t->pf.as<float2>();
+    }
     if (dim == 2) target_count_kernel<2><<<blocks, 256, 0, st>>>(tb); else target_count_kernel<3><<<blocks, 256, 0, st>>>(tb);
-    target_scan_kernel<<<1, 1024, 0, st>>>(tb, ncells);
+    target_scan_kernel<<<1, 1024, 128, st>>>(tb, ncells);
     if (dim == 2) target_scatter_kernel<2><<<blocks, 256, 0, st>>>(tb); else target_scatter_kernel<3><<<blocks, 256, 0, st>>>(tb);
     ICP_T(cudaGetLastError());
-    ICP_T(cudaStreamSynchronize(st));
     ctx->info.kernel_launches = 4;
+    if (fast2d) {
+        // jump flooding: steps 2^k >= half the grid ... 1, then 1 once more; cnt[] is free after the scan
+        const int cblocks = (int)std::min<uint32_t>((ncells + 255) / 256, (uint32_t)ctx->sm_count * 16);
+        uint32_t* bufs[2] = {t->seed.as<uint32_t>(), t->cnt.as<uint32_t>()};
+        int cur = 0;
+        target_seed_init_kernel<<<cblocks, 256, 0, st>>>(tb.cstart, ncells, bufs[cur]);
+        int step = 1;
+        while (step * 2 < std::max(t->g.gx, t->g.gy)) step *= 2;
+        std::vector<int> steps;
+        for (; step >= 1; step /= 2) steps.push_back(step);
+        steps.push_back(1);
+        ctx->info.kernel_launches += 1 + (uint32_t)steps.size();
+        for (int sp : steps) {
+            target_seed_pass_kernel<<<cblocks, 256, 0, st>>>(t->g, tb.x, tb.y, bufs[cur], bufs[cur ^ 1], sp);
+            cur ^= 1;
+        }
+        if (cur != 0)
+            ICP_T(cudaMemcpyAsync(bufs[0], bufs[1], (size_t)ncells * 4, cudaMemcpyDeviceToDevice, st));
+        ICP_T(cudaGetLastError());
+        t->seed_ptr = t->seed.as<uint32_t>();
+    }
+    ICP_T(cudaStreamSynchronize(st));
 #undef ICP_T
     *out = t;
     return ICP_B200_OK;
@@ -633,7 +668,7 @@ void icp_b200_target_destroy(icp_b200_target* t)
 {
     if (!t) return;
     if (t->ctx) cudaSetDevice(t->ctx->device);
-    DevBuf* bufs[] = {&t->pts, &t->x, &t->y, &t->z, &t->idx, &t->cstart, &t->cnt, &t->slot, &t->keys, &t->queries, &t->out_idx};
+    DevBuf* bufs[] = {&t->pts, &t->x, &t->y, &t->z, &t->idx, &t->cstart, &t->cnt, &t->slot, &t->keys, &t->queries, &t->out_idx, &t->pf, &t->seed};
     for (DevBuf* b : bufs) b->release();
     delete t;
 }
@@ -667,6 +702,7 @@ int icp_b200_target_search_device(icp_b200_target* t, const double* queries, uin
     TargetView tv{};
     tv.x = t->x.as<double>(); tv.y = t->y.as<double>(); tv.z = t->z.as<double>();
     tv.idx = t->idx.as<uint32_t>(); tv.cstart = t->cstart.as<uint32_t>(); tv.g = t->g; tv.m = t->m;
+    tv.seed = t->seed_ptr; tv.pf = t->seed_ptr ? t->pf.as<float2>() : nullptr;
     const int threads = 256;
     const long long want = (long long)((nq + threads - 1) / threads);
     const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)ctx->sm_count * 8));

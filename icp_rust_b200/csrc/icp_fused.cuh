@@ -31,7 +31,7 @@
 //             {sorted target, cell table} during search and as {r, c, b, rho} row arrays during
 //             IRLS (the target is re-staged from an L2-resident per-CTA slab each outer iteration).
 #pragma once
-#include "icp_grid.cuh"
+#include "icp_target_nn.cuh"
 
 namespace icp {
 
@@ -66,17 +66,6 @@ struct FusedCtl {
 
 ICP_HD uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
 ICP_HD uint32_t align128(uint32_t v) { return (v + 127u) & ~127u; }
-
-// Shared target (Icp2d::new analogue kept on the device, reused by many estimates)
-struct TargetView {
-    const double* x;
-    const double* y;
-    const double* z;
-    const uint32_t* idx;
-    const uint32_t* cstart;
-    GridGeom g;
-    uint32_t m;
-};
 
 ICP_HD FusedLayout fused_layout(int dim, int ncap, int mcap, int cell_budget, bool shared_target, bool ordered)
 {
@@ -604,11 +593,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                 const double pz = (DIM == 3) ? src[(size_t)i * DIM + 2] : 0.0;  // transform_xy keeps z (lib.rs:52-57)
                 int idx;
                 if (SHARED_TARGET) {
-                    GridView<DIM, uint32_t, uint32_t> gv;
-                    gv.x = p.target.x; gv.y = p.target.y; gv.z = p.target.z;
-                    gv.idx = p.target.idx; gv.cstart = p.target.cstart; gv.g = geom;
-                    NnResult<DIM, uint32_t, uint32_t> r = grid_nn_search(gv, qx, qy, pz);
-                    *ox = gv.x[r.pos]; *oy = gv.y[r.pos];
+                    const NnResult<DIM, uint32_t, uint32_t> r = target_nn_search<DIM>(p.target, qx, qy, pz);
+                    *ox = p.target.x[r.pos]; *oy = p.target.y[r.pos];
                     idx = r.idx;
                 } else {
                     GridView<DIM, uint16_t, uint16_t> gv;

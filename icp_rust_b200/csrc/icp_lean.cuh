@@ -407,11 +407,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                 double2 d;
                 int idx;
                 if (SHARED_TARGET) {
-                    GridView<DIM, uint32_t, uint32_t> gv;
-                    gv.x = p.target.x; gv.y = p.target.y; gv.z = p.target.z;
-                    gv.idx = p.target.idx; gv.cstart = p.target.cstart; gv.g = geom;
-                    const NnResult<DIM, uint32_t, uint32_t> r = grid_nn_search(gv, q.x, q.y, pz);
-                    d.x = gv.x[r.pos]; d.y = gv.y[r.pos];
+                    const NnResult<DIM, uint32_t, uint32_t> r = target_nn_search<DIM>(p.target, q.x, q.y, pz);
+                    d.x = p.target.x[r.pos]; d.y = p.target.y[r.pos];
                     idx = r.idx;
                 } else {
                     GridView<DIM, uint16_t, uint16_t> gv;

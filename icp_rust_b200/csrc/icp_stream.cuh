@@ -236,7 +236,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, 1) icp_stream_kernel(StreamParams sp)
                 double2 s;
                 transform_apply(T, src[(size_t)i * DIM + 0], src[(size_t)i * DIM + 1], &s.x, &s.y);
                 const double pz = (DIM == 3) ? src[(size_t)i * DIM + 2] : 0.0;
-                const NnResult<DIM, uint32_t, uint32_t> r = grid_nn_search(gv, s.x, s.y, pz);
+                const NnResult<DIM, uint32_t, uint32_t> r =
+                    SHARED_TARGET ? target_nn_search<DIM>(p.target, s.x, s.y, pz) : grid_nn_search(gv, s.x, s.y, pz);
                 double2 d;
                 d.x = gv.x[r.pos]; d.y = gv.y[r.pos];   // get_xy (lib.rs:86-89)
                 S0[i] = s;

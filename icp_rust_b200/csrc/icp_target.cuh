@@ -6,6 +6,9 @@
 //   x[m], y[m], (z[m])   f64   coordinates, bit-identical copies of the caller's points
 //   idx[m]               u32   original index of the point at each sorted position
 //   cstart[ncells + 1]   u32   first sorted position of every cell
+//   2-D only (icp_target_nn.cuh):
+//   pf[m]                f32x2 the point relative to the centre of its 32x32-cell block
+//   seed[ncells]         u32   sorted position of a point near each cell (jump flooding)
 // Algorithmic traffic of one search call: 8*DIM*Q (queries) + 4*Q (indices) + the structure
 // read once = 20 B/query in 2-D, 28 B/query in 3-D for Q >> m.
 #pragma once
@@ -23,6 +26,7 @@ struct TargetBuild {
     double* x; double* y; double* z;
     uint32_t* idx;
     unsigned long long* bbox_keys;  // [6] min xyz, max xyz as order-preserving keys
+    float2* pf;            // null: no binary32 copies (3-D, degenerate geometry)
 };
 
 template <int DIM>
@@ -69,10 +73,11 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, 1) target_count_kernel(TargetBuild b)
         b.slot[j] = atomicAdd(&b.cnt[target_cell_of<DIM>(b, j)], 1u);
 }
 
-// single CTA: exclusive scan of cnt[ncells] into cstart[ncells+1]
+// single CTA (128 B of dynamic shared memory): exclusive scan of cnt[ncells] into cstart[ncells+1]
 ICP_GLOBAL void ICP_LAUNCH_BOUNDS(1024, 1) target_scan_kernel(TargetBuild b, uint32_t ncells)
 {
-    __shared__ uint32_t warp_tot[32];
+    ICP_SHARED_DYN(scan_smem);   // 32 x u32
+    uint32_t* warp_tot = reinterpret_cast<uint32_t*>(scan_smem);
     const int lane = lane_id(), warp = warp_id();
     const uint32_t nw = blockDim.x / 32;
     const uint32_t chunk = (((ncells + nw - 1) / nw) + 31u) & ~31u;
@@ -102,6 +107,48 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, 1) target_scatter_kernel(TargetBuild b)
         b.y[pos] = b.pts[(size_t)j * DIM + 1];
         if (DIM == 3) b.z[pos] = b.pts[(size_t)j * DIM + 2];
         b.idx[pos] = j;
+        if (DIM == 2 && b.pf) {
+            const GridGeom& g = b.g;
+            const double px = b.pts[(size_t)j * 2 + 0], py = b.pts[(size_t)j * 2 + 1];
+            const int cx = grid_coord(px, g.ox, g.inv_h, g.gx);
+            const int cy = grid_coord(py, g.oy, g.inv_h, g.gy);
+            float2 v;
+            v.x = (float)(px - nn_block_origin(g.ox, g.h, cx >> kNnBlockShift));
+            v.y = (float)(py - nn_block_origin(g.oy, g.h, cy >> kNnBlockShift));
+            b.pf[pos] = v;
+        }
+    }
+}
+
+// Seeds by jump flooding (2-D).  seed_init: a cell's own first point, or none.  seed_pass(step):
+// every cell keeps the closest (to its centre, binary32 is plenty) of its own seed and the seeds of
+// the 8 cells `step` away.  Ping-pong buffers keep the outcome independent of the schedule.  Seeds
+// only bound the search disc (icp_target_nn.cuh): their quality affects speed, never results.
+ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, 1) target_seed_init_kernel(const uint32_t* cstart, uint32_t ncells, uint32_t* seed)
+{
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += gridDim.x * blockDim.x)
+        seed[c] = (cstart[c + 1] > cstart[c]) ? cstart[c] : kNnNoSeed;
+}
+
+ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, 1) target_seed_pass_kernel(GridGeom g, const double* x, const double* y,
+                                                                   const uint32_t* in, uint32_t* out, int step)
+{
+    const uint32_t ncells = (uint32_t)(g.gx * g.gy);
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += gridDim.x * blockDim.x) {
+        const int cy = (int)(c / (uint32_t)g.gx), cx = (int)(c - (uint32_t)cy * (uint32_t)g.gx);
+        const double mx = g.ox + ((double)cx + 0.5) * g.h, my = g.oy + ((double)cy + 0.5) * g.h;
+        uint32_t best = kNnNoSeed;
+        float bd = 3.0e38f;
+        for (int k = 0; k < 9; ++k) {   // k == 4 is the cell itself
+            const int nx = cx + (k % 3 - 1) * step, ny = cy + (k / 3 - 1) * step;
+            if (nx < 0 || ny < 0 || nx >= g.gx || ny >= g.gy) continue;
+            const uint32_t s = in[(uint32_t)ny * (uint32_t)g.gx + (uint32_t)nx];
+            if (s == kNnNoSeed) continue;
+            const float ex = (float)(x[s] - mx), ey = (float)(y[s] - my);
+            const float d = ex * ex + ey * ey;
+            if (d < bd || (d == bd && s < best)) { bd = d; best = s; }
+        }
+        out[c] = best;
     }
 }
 
@@ -111,8 +158,6 @@ template <int DIM>
 ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, 2) nn_search_kernel(TargetView tv, const double* queries,
                                                           unsigned long long nq, int32_t* out_idx)
 {
-    GridView<DIM, uint32_t, uint32_t> gv;
-    gv.x = tv.x; gv.y = tv.y; gv.z = tv.z; gv.idx = tv.idx; gv.cstart = tv.cstart; gv.g = tv.g;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
         double qx, qy, qz = 0.0;
@@ -122,7 +167,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, 2) nn_search_kernel(TargetView tv, const 
         } else {
             qx = queries[q * 3 + 0]; qy = queries[q * 3 + 1]; qz = queries[q * 3 + 2];
         }
-        NnResult<DIM, uint32_t, uint32_t> r = grid_nn_search(gv, qx, qy, qz);
+        const NnResult<DIM, uint32_t, uint32_t> r = target_nn_search<DIM>(tv, qx, qy, qz);
         out_idx[q] = r.idx;
     }
 }

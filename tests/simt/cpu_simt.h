@@ -19,6 +19,7 @@
 #include <vector>
 
 struct double2 { double x, y; };
+struct float2 { float x, y; };
 struct uint4 { uint32_t x, y, z, w; };
 struct dim3_ { unsigned x = 1, y = 1, z = 1; };
 

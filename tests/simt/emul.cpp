@@ -5,6 +5,7 @@
 #include "icp_lean.cuh"
 #include "icp_stream.cuh"
 #include "icp_stats_kernel.cuh"
+#include "icp_target.cuh"
 
 #include <vector>
 
@@ -125,6 +126,66 @@ extern "C" int simt_calc_stddevs(const double* residuals, const uint32_t* off, u
     else if (threads == 256) simt::launch(grid, 256, stats_smem_bytes(cap), [&] { calc_stddevs_kernel<256, 8>(p); });
     else simt::launch(grid, 128, stats_smem_bytes(cap), [&] { calc_stddevs_kernel<128, kStatsPpt>(p); });
     return 0;
+}
+
+// Shared-target structure (icp_target.cuh) built and searched on the emulator: the same kernels the
+// library launches in icp_b200_target_create / icp_b200_target_search.  fast != 0 selects the seeded
+// binary32-filtered search of icp_target_nn.cuh (2-D), else the ring search.
+extern "C" int simt_target_search(int dim, const double* pts, uint32_t m, long long budget, int fast,
+                                  const double* queries, uint64_t nq, int32_t* out_idx)
+{
+    if (m == 0 || (dim != 2 && dim != 3)) return -1;
+    double mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+    for (int d = 0; d < dim; ++d) {
+        mn[d] = mx[d] = pts[d];
+        for (uint32_t j = 1; j < m; ++j) {
+            mn[d] = std::min(mn[d], pts[(size_t)j * dim + d]);
+            mx[d] = std::max(mx[d], pts[(size_t)j * dim + d]);
+        }
+    }
+    const GridGeom g = grid_make_geom(mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], dim, (int)budget);
+    const uint32_t ncells = (uint32_t)(g.gx * g.gy * g.gz);
+    std::vector<uint32_t> cnt(ncells, 0u), slot(m), cstart(ncells + 1), idx(m), seed(ncells), seed2(ncells);
+    std::vector<double> x(m), y(m), z(m);
+    std::vector<float2> pf(m);
+    TargetBuild tb{};
+    tb.pts = pts; tb.m = m; tb.g = g; tb.cnt = cnt.data(); tb.slot = slot.data(); tb.cstart = cstart.data();
+    tb.x = x.data(); tb.y = y.data(); tb.z = z.data(); tb.idx = idx.data();
+    const bool fast2d = fast && dim == 2;
+    tb.pf = fast2d ? pf.data() : nullptr;
+    if (dim == 2) simt::launch(3, 256, 0, [&] { target_count_kernel<2>(tb); });
+    else simt::launch(3, 256, 0, [&] { target_count_kernel<3>(tb); });
+    simt::launch(1, 1024, 128, [&] { target_scan_kernel(tb, ncells); });
+    if (dim == 2) simt::launch(3, 256, 0, [&] { target_scatter_kernel<2>(tb); });
+    else simt::launch(3, 256, 0, [&] { target_scatter_kernel<3>(tb); });
+    TargetView tv{};
+    tv.x = x.data(); tv.y = y.data(); tv.z = z.data(); tv.idx = idx.data(); tv.cstart = cstart.data();
+    tv.g = g; tv.m = m;
+    if (fast2d) {
+        uint32_t* bufs[2] = {seed.data(), seed2.data()};
+        int cur = 0;
+        simt::launch(4, 256, 0, [&] { target_seed_init_kernel(cstart.data(), ncells, bufs[0]); });
+        int step = 1;
+        while (step * 2 < std::max(g.gx, g.gy)) step *= 2;
+        std::vector<int> steps;
+        for (; step >= 1; step /= 2) steps.push_back(step);
+        steps.push_back(1);
+        for (int sp : steps) {
+            simt::launch(4, 256, 0, [&] { target_seed_pass_kernel(g, x.data(), y.data(), bufs[cur], bufs[cur ^ 1], sp); });
+            cur ^= 1;
+        }
+        tv.seed = bufs[cur]; tv.pf = pf.data();
+    }
+    if (dim == 2) simt::launch(2, 256, 0, [&] { nn_search_kernel<2>(tv, queries, nq, out_idx); });
+    else simt::launch(2, 256, 0, [&] { nn_search_kernel<3>(tv, queries, nq, out_idx); });
+    return 0;
+}
+
+extern "C" void simt_nn_counters(unsigned long long* out6, int reset)
+{
+    NnCounters& c = nn_counters();
+    out6[0] = c.q; out6[1] = c.rows; out6[2] = c.spans; out6[3] = c.cand; out6[4] = c.pass2; out6[5] = c.exact; out6[6] = c.pre;
+    if (reset) c = NnCounters{};
 }
 
 extern "C" unsigned long long simt_yield_count() { return simt::st().yields; }

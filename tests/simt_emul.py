@@ -93,3 +93,22 @@ def icp_stream(srcs, dsts, init_T, max_iter=20, threads=64, grid=1, corr_mode=2)
         hashes.ctypes.data_as(C.POINTER(C.c_uint64)), status.ctypes.data_as(C.POINTER(C.c_int32)))
     return {"T": out_T, "inner": inner[:, :max_iter], "corr": corr, "corr_hash": hashes, "status": status,
             "err": err, "src_off": so}
+
+
+def target_search(dst, queries, budget, fast=True):
+    """icp_target.cuh build kernels + nn_search_kernel on the emulator -> original indices (int32)."""
+    d = np.ascontiguousarray(dst, dtype=np.float64)
+    q = np.ascontiguousarray(queries, dtype=np.float64)
+    out = np.full(q.shape[0], -1, dtype=np.int32)
+    rc = lib().simt_target_search(C.c_int(d.shape[1]), d.ctypes.data_as(_dp), C.c_uint32(d.shape[0]),
+                                  C.c_longlong(int(budget)), C.c_int(1 if fast else 0), q.ctypes.data_as(_dp),
+                                  C.c_uint64(q.shape[0]), out.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == 0
+    return out
+
+
+def nn_counters(reset=True):
+    """Work counters of the fast shared-target search since the last reset (emulator only)."""
+    out = (C.c_ulonglong * 8)()
+    lib().simt_nn_counters(out, C.c_int(1 if reset else 0))
+    return dict(zip(("queries", "rows", "spans", "candidates", "pass2_queries", "exact_evals", "prescan"), [int(v) for v in out]))

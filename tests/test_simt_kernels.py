@@ -203,3 +203,51 @@ def test_stream_status_codes():
     bad[3, 1] = np.nan
     g = E.icp_stream([a, bad], [np.zeros((0, 2)), a], [I6, I6], max_iter=2, threads=32)
     assert list(g["status"]) == [1, 3] and g["err"] == 3
+
+
+# ------------------------------------------------------------------------------------------------
+# Shared-target search (icp_target.cuh + icp_target_nn.cuh): KdTree::search, lib.rs:121,164
+def _map_queries(seed, count=6, beams=360):
+    import icp_rust_b200 as icp
+    scans, off, T0 = icp.synth_map_scans(count, beams=beams, seed=seed, nthreads=1)
+    out = []
+    for b in range(count):
+        s = scans[off[b]:off[b + 1]]
+        R2 = T0[b, :4].reshape(2, 2)
+        out.append(s @ R2.T + T0[b, 4:6])
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("cells_per_point", [2, 32, 200])
+def test_target_search_fast_path_is_exact(cells_per_point):
+    """Seeded, binary32-filtered disc search == brute force on a map sampled densely along walls:
+    near-ties (neighbours on a wall), exact duplicates, queries on target points, far outside."""
+    import icp_rust_b200 as icp
+    m = icp.synth_map(6000, seed=7)
+    m[700:720] = m[100]              # duplicates: lowest index must win
+    m[3000] = m[2999]
+    rng = np.random.default_rng(5)
+    q = np.concatenate([_map_queries(7), m[95:105], m[2995:3005], m[::97] + 1e-9,
+                        rng.uniform(-5e3, 45e3, (300, 2)), rng.uniform(-1e7, 1e7, (16, 2)),
+                        np.zeros((1, 2)), [[1e300, -1e300], [5e-324, 0.0]]])
+    exp = oracle.nn_search(m, q, oracle.NN_BRUTE)
+    got = E.target_search(m, q, budget=len(m) * cells_per_point, fast=True)
+    assert np.array_equal(got, exp)
+    assert np.array_equal(E.target_search(m, q[:400], budget=len(m) * 2, fast=False), exp[:400])
+
+
+def test_target_search_fast_path_odd_geometries():
+    rng = np.random.default_rng(9)
+    line = np.stack([np.linspace(-1.0, 1.0, 500), np.full(500, 3.25)], axis=1)       # flat in y
+    lattice = np.stack(np.meshgrid(np.arange(40.), np.arange(40.)), -1).reshape(-1, 2)  # ties everywhere
+    tiny = rng.normal(0, 1e-7, (300, 2)) + 1e3                                        # far from the origin
+    one = np.array([[2.0, -1.0]])
+    for d in (line, lattice, tiny, one):
+        span = np.ptp(d, axis=0).max() + 1.0
+        q = np.concatenate([d[:: max(1, len(d) // 50)], d.mean(0) + rng.normal(0, span, (200, 2)),
+                            d.mean(0) + rng.normal(0, span * 1e-3, (100, 2))])
+        if d is lattice:
+            q = np.concatenate([q, lattice[:200] + 0.5, lattice[:100] + [0.5, 0.0]])   # 4-way and 2-way ties
+        exp = oracle.nn_search(d, q, oracle.NN_BRUTE)
+        for cpp in (4, 64):
+            assert np.array_equal(E.target_search(d, q, budget=max(64, len(d) * cpp), fast=True), exp)
