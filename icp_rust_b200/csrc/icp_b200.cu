@@ -625,7 +625,7 @@ int icp_b200_target_create(icp_b200_context* ctx, uint32_t dim, const double* ds
     tb.g = t->g; tb.cnt = t->cnt.as<uint32_t>(); tb.slot = t->slot.as<uint32_t>(); tb.cstart = t->cstart.as<uint32_t>();
     tb.x = t->x.as<double>(); tb.y = t->y.as<double>(); tb.z = t->z.as<double>(); tb.idx = t->idx.as<uint32_t>();
     // binary32 filter + seeds: 2-D, and a geometry whose squares stay inside binary32's range
-    const bool fast2d = dim == 2 && env_int("ICP_B200_TARGET_FAST", 1) != 0 && t->g.h >= 1e-10 &&
+    const bool fast2d = dim == 2 && env_int("ICP_B200_TARGET_FAST", 1) != 0 && m < kNnMaxPoints && t->g.h >= 1e-10 &&
                         t->g.h * (double)std::max(t->g.gx, t->g.gy) <= 1e15;
     if (fast2d) {
         ICP_T(t->pf.ensure((size_t)m * 8));

@@ -7,7 +7,7 @@
 //   idx[m]               u32   original index of the point at each sorted position
 //   cstart[ncells + 1]   u32   first sorted position of every cell
 //   2-D only (icp_target_nn.cuh):
-//   pf[m]                f32x2 the point relative to the centre of its 32x32-cell block
+//   pf[m]                f32x2 the point in cell units relative to the centre of its 32x32-cell block
 //   seed[ncells]         u32   sorted position of a point near each cell (jump flooding)
 // Algorithmic traffic of one search call: 8*DIM*Q (queries) + 4*Q (indices) + the structure
 // read once = 20 B/query in 2-D, 28 B/query in 3-D for Q >> m.
@@ -113,8 +113,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, 1) target_scatter_kernel(TargetBuild b)
             const int cx = grid_coord(px, g.ox, g.inv_h, g.gx);
             const int cy = grid_coord(py, g.oy, g.inv_h, g.gy);
             float2 v;
-            v.x = (float)(px - nn_block_origin(g.ox, g.h, cx >> kNnBlockShift));
-            v.y = (float)(py - nn_block_origin(g.oy, g.h, cy >> kNnBlockShift));
+            v.x = (float)(nn_cell_coord(px, g.ox, g.inv_h) - nn_block_centre(cx));
+            v.y = (float)(nn_cell_coord(py, g.oy, g.inv_h) - nn_block_centre(cy));
             b.pf[pos] = v;
         }
     }

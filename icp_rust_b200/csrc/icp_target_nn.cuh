@@ -7,8 +7,9 @@
 // 2-D targets carry, besides the sorted cell list of icp_grid.cuh,
 //   seed[c]  u32     sorted position of a target point near cell c (jump flooding at build time);
 //                    ANY point is a valid seed — its exact d2 bounds the search disc, nothing more
-//   pf[p]    float2  binary32 copy of point p relative to the centre of its 32x32-cell block, so
-//                    that a binary32 distance to a query carries an error of ~2^-22 (U + 40h)
+//   pf[p]    float2  binary32 copy of point p in CELL UNITS relative to the centre of its 32x32-cell
+//                    block: (T(p.x) - centre, T(p.y) - centre) with T(v) = (v - o) * inv_h, the very
+//                    expression grid_coord floors.  |.| <= 17, so one rounding is <= 2^-24 * 17 cells
 // and the search runs
 //   1. U2 = exact d2 of the seed: every point the disc test skips has computed d2 > U2;
 //   2. one row of cells at a time, the cells the disc of radius sqrt(U2) reaches (a contiguous span
@@ -19,6 +20,11 @@
 // Every skip is justified by a bound that holds for the computed binary64 d2 (comments "bound:"),
 // so the result is bit-identical to scanning all target points.  Geometry, seeds and the filter
 // change speed only.  3-D targets and degenerate geometries use the ring search of icp_grid.cuh.
+//
+// One thread per query, in nn_search_kernel and in the fused kernels alike.  A warp-collective form
+// that pooled the candidates of 32 queries in shared memory (chunks of 8, folded into their owners'
+// slots with shared-memory atomics) ran the candidate loop at 30 of 32 lanes but lost more in list
+// upkeep than it won: 4.7 against 5.5 G queries/s on B200 (profiles/r01_nn_sweep.md); removed.
 #pragma once
 #include "icp_grid.cuh"
 
@@ -41,11 +47,14 @@ constexpr int kNnBlockShift = 5;                    // 32x32-cell blocks share o
 constexpr int kNnBlockCells = 1 << kNnBlockShift;
 constexpr uint32_t kNnNoSeed = 0xffffffffu;
 
-// Origin of block b along one axis.  Build and search evaluate this same expression.
-ICP_HD double nn_block_origin(double o, double h, int b)
+// Centre of the block that holds cell c, in cell units.  Build and search evaluate this same expression.
+ICP_HD double nn_block_centre(int c)
 {
-    return o + (double)(b * kNnBlockCells + kNnBlockCells / 2) * h;
+    return (double)(((c >> kNnBlockShift) << kNnBlockShift) + kNnBlockCells / 2);
 }
+
+// T(v): the cell coordinate grid_coord floors (before its clamp).  Monotone non-decreasing in v.
+ICP_HD double nn_cell_coord(double v, double o, double inv_h) { return (v - o) * inv_h; }
 
 ICP_DEV float nn_fma(float a, float b, float c)
 {
@@ -54,6 +63,17 @@ ICP_DEV float nn_fma(float a, float b, float c)
 #else
     return __fmaf_rn(a, b, c);
 #endif
+}
+
+// floor to int, clamped to [0, hi]; |v| <= ~1e9 is guaranteed by the caller (NnQuery::slow otherwise)
+ICP_DEV int nn_floor_clamp(float v, int hi)
+{
+#ifdef ICP_SIMT_EMULATE
+    const int c = (int)std::floor(v);
+#else
+    const int c = __float2int_rd(v);
+#endif
+    return c < 0 ? 0 : (c > hi ? hi : c);
 }
 
 #ifdef ICP_SIMT_EMULATE
@@ -66,115 +86,158 @@ inline NnCounters& nn_counters() { static NnCounters c{}; return c; }
 #endif
 
 struct NnFilterState {
-    float m1, m2;   // smallest and second smallest binary32 d2 seen
+    float m1, m2;   // smallest and second smallest binary32 d2 seen (cell units squared)
     int pos;        // sorted position of the smallest
 };
 
-// Exact 1-NN on a 2-D shared target with seeds.  Requires tv.m > 0, tv.seed, tv.pf.
-ICP_DEV NnResult<2, uint32_t, uint32_t> target_nn_search2(const TargetView& tv, double qx, double qy)
+// Per-query constants of the disc walk.  All binary32 quantities are in cell units.
+//
+// bound (cells): a point p of column c has T(p.x) in [c, c+1) up to the clamp at the grid's edge
+// (where no points lie beyond), T is the monotone map above, and T(v) = (v - o)/h (1 + e), |e| <
+// 2^-51.  So for a column c > x: (p.x - q.x)/h >= c - T(q.x) - 2^-50 gx, and likewise on the other
+// side and for rows.  txf/tyf are T(q) rounded to binary32; `sx`/`sy` = 1.5 * 2^-22 (|t| + 1) cover that
+// rounding, the rounding of every binary32 difference formed with them, and the 2^-50 terms.
+struct NnQuery {
+    double tx, ty;     // T(q.x), T(q.y)
+    float txf, tyf, sx, sy;
+    float Uc2;         // >= U2 (1 + 1e-6) / h^2
+    float a;           // error bound of one binary32 coordinate difference
+    int ya, yb;        // rows the disc reaches
+    uint32_t seed;
+    double U2;         // exact d2 of the seed
+    bool slow;         // outside the filter's range: ring search instead
+};
+
+ICP_DEV NnQuery nn_query_setup(const TargetView& tv, double qx, double qy)
 {
     const GridGeom& g = tv.g;
+    NnQuery Q;
+    Q.tx = nn_cell_coord(qx, g.ox, g.inv_h);
+    Q.ty = nn_cell_coord(qy, g.oy, g.inv_h);
+    Q.txf = (float)Q.tx; Q.tyf = (float)Q.ty;
+    Q.slow = false;
+    Q.ya = 1; Q.yb = 0; Q.Uc2 = 0.0f; Q.a = 0.0f; Q.sx = 0.0f; Q.sy = 0.0f; Q.U2 = 0.0;
     const int cx = grid_coord(qx, g.ox, g.inv_h, g.gx);
     const int cy = grid_coord(qy, g.oy, g.inv_h, g.gy);
-    NnResult<2, uint32_t, uint32_t> best;
-    const uint32_t s = tv.seed[cy * g.gx + cx];
-    if (s >= tv.m) {   // no seed (cannot happen after a complete flood): ring search
-        GridView<2, uint32_t, uint32_t> gv;
-        gv.x = tv.x; gv.y = tv.y; gv.z = tv.z; gv.idx = tv.idx; gv.cstart = tv.cstart; gv.g = g;
-        return grid_nn_search(gv, qx, qy, 0.0);
-    }
-    {
-        const double dx = qx - tv.x[s], dy = qy - tv.y[s];
-        best.d2 = dx * dx + dy * dy;
-        best.pos = (int)s;
-    }
-    const double U2 = best.d2;
-    // binary32 upper bounds of U2 and sqrt(U2) (each factor 1.000001 covers one rounding of 2^-24)
-    // (+1e-30: keeps the bounds valid where binary32 would go subnormal)
-    const float U2f = (float)U2 * 1.000001f + 1e-30f;
-    const float Uf = sqrtf(U2f) * 1.000001f;
-    const float hf = (float)g.h;
-    if (!(U2f <= 1e30f) || !(U2 >= 0.0)) {   // overflow of the filter's range / NaN: ring search
-        GridView<2, uint32_t, uint32_t> gv;
-        gv.x = tv.x; gv.y = tv.y; gv.z = tv.z; gv.idx = tv.idx; gv.cstart = tv.cstart; gv.g = g;
-        return grid_nn_search(gv, qx, qy, 0.0);
-    }
-    // absolute slack that keeps q -+ radius on the safe side of its own rounding
-    const double eps_abs = (fabs(qx) + fabs(qy)) * 1e-15;
-    const double Ud = (double)Uf + eps_abs;
-    // bound (rows): a point in a row above cell(fl(qy + Ud)) has p.y > fl(qy + Ud) because grid_coord
-    // is monotone, so |q.y - p.y| > sqrt(U2)(1 + 5e-7) and its computed d2 exceeds U2.  Same below.
-    const int ya = grid_coord(qy - Ud, g.oy, g.inv_h, g.gy);
-    const int yb = grid_coord(qy + Ud, g.oy, g.inv_h, g.gy);
-    // error bound of one binary32 coordinate difference: the stored point (|.| <= 17h) and the query
-    // offset (|.| <= U + 18h) are rounded to 24 bits, and so is their difference (|.| <= U + 35h)
-    const float a = (Uf + 40.0f * hf) * 2.4e-7f;   // 2^-22
-    ICP_NN_COUNT(q, 1);
-    NnFilterState f;
-    f.m1 = 3.0e38f; f.m2 = 3.0e38f; f.pos = (int)s;
+    Q.seed = tv.seed[cy * g.gx + cx];
+    if (Q.seed >= tv.m || !(fabsf(Q.txf) + fabsf(Q.tyf) <= 1e9f)) { Q.slow = true; return Q; }
+    const double dx = qx - tv.x[Q.seed], dy = qy - tv.y[Q.seed];
+    Q.U2 = dx * dx + dy * dy;
+    // binary32 upper bound of U2 / h^2: four roundings of 2^-24 against the factor 1.000001, and
+    // 1e-30 where binary32 would go subnormal
+    const float ihf = (float)g.inv_h;
+    Q.Uc2 = ((float)Q.U2 * ihf) * ihf * 1.000001f + 1e-30f;
+    if (!(Q.Uc2 <= 1e12f) || !(Q.U2 >= 0.0)) { Q.slow = true; return Q; }
+    const float Uc = sqrtf(Q.Uc2) * 1.000001f;
+    Q.sx = (fabsf(Q.txf) + 1.0f) * 3.6e-7f;   // 1.5 * 2^-22
+    Q.sy = (fabsf(Q.tyf) + 1.0f) * 3.6e-7f;
+    // bound (rows): a point in a row above yb has (p.y - q.y)/h > Uc, hence |q.y - p.y| >
+    // sqrt(U2)(1 + 4e-7) and its computed d2 exceeds U2.  Same below ya.
+    Q.ya = nn_floor_clamp(Q.tyf - Uc - Q.sy, g.gy - 1);
+    Q.yb = nn_floor_clamp(Q.tyf + Uc + Q.sy, g.gy - 1);
+    // the stored point (|.| <= 17), the query's block offset (|.| <= Uc + 18) and their difference
+    // (|.| <= Uc + 35) are each rounded to 24 bits
+    Q.a = (Uc + 40.0f) * 2.4e-7f;
+    return Q;
+}
 
-    // Walks the cells the disc reaches; `visit(p, d32)` sees every candidate's binary32 d2.
-    auto walk = [&](auto&& visit) {
-        for (int yy = ya; yy <= yb; ++yy) {
-            // bound (columns): points of row yy have |q.y - p.y| >= yd (cell boundary up to `margin`,
-            // icp_grid.cuh); outside [q.x - wd, q.x + wd] their computed d2 is
-            // >= (wd^2 + yd^2)(1 - 2^-50) >= U2 (1 + 8e-7) > U2.  Monotone grid_coord again turns the
-            // interval into a span of cells.
-            double yd = 0.0;
-            if (yy > cy) yd = (g.oy + (double)yy * g.h) - qy - g.margin;
-            else if (yy < cy) yd = qy - (g.oy + (double)(yy + 1) * g.h) - g.margin;
-            const float ydf = (float)fmax(yd, 0.0) * 0.999999f;
-            const float w2 = U2f - ydf * ydf;
-            if (w2 < 0.0f) continue;
-            ICP_NN_COUNT(rows, 1);
-            const double wd = (double)(sqrtf(w2) * 1.000001f) + eps_abs;
-            const int xa = grid_coord(qx - wd, g.ox, g.inv_h, g.gx);
-            const int xb = grid_coord(qx + wd, g.ox, g.inv_h, g.gx);
-            const float qry = (float)(qy - nn_block_origin(g.oy, g.h, yy >> kNnBlockShift));
-            const int row = yy * g.gx;
-            for (int xs = xa; xs <= xb;) {
-                const int xe_blk = xs | (kNnBlockCells - 1);
-                const int xe = xe_blk < xb ? xe_blk : xb;
-                const int p0 = (int)tv.cstart[row + xs];
-                const int p1 = (int)tv.cstart[row + xe + 1];
-                ICP_NN_COUNT(spans, 1);
-                ICP_NN_COUNT(cand, p1 - p0);
-                if (p1 > p0) {
-                    const float qrx = (float)(qx - nn_block_origin(g.ox, g.h, xs >> kNnBlockShift));
-                    for (int p = p0; p < p1; ++p) {
-                        const float2 v = tv.pf[p];
-                        const float ex = qrx - v.x, ey = qry - v.y;
-                        visit(p, nn_fma(ex, ex, ey * ey));
-                    }
-                }
-                xs = xe + 1;
+// Columns of row yy the disc reaches: false when none.
+// bound (columns): points of row yy have |q.y - p.y|/h >= ydc; outside [T(q.x) - wc, T(q.x) + wc]
+// their computed d2 is >= h^2 (wc^2 + ydc^2)(1 - 2^-49) >= U2 (1 + 5e-7) > U2.
+ICP_DEV bool nn_row_span(const NnQuery& Q, int yy, int gx, int* xa, int* xb)
+{
+    const float yf = (float)yy;
+    const float ydc = fmaxf(fmaxf(yf - Q.tyf, Q.tyf - (yf + 1.0f)) - Q.sy, 0.0f) * 0.999999f;
+    const float w2 = Q.Uc2 - ydc * ydc;
+    if (w2 < 0.0f) return false;
+    const float wc = sqrtf(w2) * 1.000001f + Q.sx;
+    *xa = nn_floor_clamp(Q.txf - wc, gx - 1);
+    *xb = nn_floor_clamp(Q.txf + wc, gx - 1);
+    return true;
+}
+
+// query offsets from the centre of the block holding column / row c, rounded once to binary32
+ICP_DEV float nn_block_offset(double t, int c) { return (float)(t - nn_block_centre(c)); }
+
+// bound (filter): sqrt(d32) is within 1.5a + 2^-22 sqrt(d32) of the true distance D/h.  The winner w
+// of the exact ranking has D(w) <= D(p)(1 + 2^-50) for every p, in particular for the binary32
+// minimum, hence sqrt(d32(w)) <= sqrt(m1)(1 + 2^-20) + 4a.  Candidates above the band cannot win.
+ICP_DEV float nn_filter_band(float m1, float a)
+{
+    const float t = sqrtf(m1) * 1.000004f + 5.0f * a;
+    return t * t * 1.000001f + 1e-30f;
+}
+
+ICP_DEV NnResult<2, uint32_t, uint32_t> nn_ring_search(const TargetView& tv, double qx, double qy)
+{
+    GridView<2, uint32_t, uint32_t> gv;
+    gv.x = tv.x; gv.y = tv.y; gv.z = tv.z; gv.idx = tv.idx; gv.cstart = tv.cstart; gv.g = tv.g;
+    return grid_nn_search(gv, qx, qy, 0.0);
+}
+
+ICP_DEV NnResult<2, uint32_t, uint32_t> nn_result_at(const TargetView& tv, double qx, double qy, int p)
+{
+    NnResult<2, uint32_t, uint32_t> r;
+    const double dx = qx - tv.x[p], dy = qy - tv.y[p];
+    r.d2 = dx * dx + dy * dy;
+    r.pos = p;
+    r.idx = (int)tv.idx[p];
+    return r;
+}
+
+// Walks the cells the disc reaches; `visit(p, d32)` sees every candidate's binary32 d2.
+// Shape of the loop: each trip first advances to the query's next NON-EMPTY span (cells of one row
+// inside one 32-cell block), then runs the candidates of that span.  The lanes of a warp meet their
+// occupied rows at different row numbers; advancing first lets them run their k-th candidate loops
+// together instead of one lane at a time.
+template <typename Visit>
+ICP_DEV void nn_walk(const TargetView& tv, const NnQuery& Q, Visit&& visit)
+{
+    const int gx = tv.g.gx;
+    int yy = Q.ya, xs = 1, xb = 0, row = 0;
+    float qry = 0.0f;
+    bool have_row = false;
+    for (;;) {
+        int p0 = 0, p1 = 0;
+        float qrx = 0.0f;
+        while (p1 == p0 && (have_row || yy <= Q.yb)) {
+            if (!have_row) {
+                int xa;
+                if (!nn_row_span(Q, yy, gx, &xa, &xb)) { ++yy; continue; }
+                ICP_NN_COUNT(rows, 1);
+                row = yy * gx;
+                if (tv.cstart[row + xa] == tv.cstart[row + xb + 1]) { ++yy; continue; }   // nothing in the whole span
+                qry = nn_block_offset(Q.ty, yy);
+                xs = xa;
+                have_row = true;
             }
+            const int xe_blk = xs | (kNnBlockCells - 1);
+            const int xe = xe_blk < xb ? xe_blk : xb;
+            p0 = (int)tv.cstart[row + xs];
+            p1 = (int)tv.cstart[row + xe + 1];
+            qrx = nn_block_offset(Q.tx, xs);
+            ICP_NN_COUNT(spans, 1);
+            xs = xe + 1;
+            if (xs > xb) { have_row = false; ++yy; }
         }
-    };
-
-    walk([&](int p, float d32) {
-        f.m2 = fminf(f.m2, fmaxf(d32, f.m1));
-        f.pos = (d32 < f.m1) ? p : f.pos;
-        f.m1 = fminf(f.m1, d32);
-    });
-
-    // bound (filter): sqrt(d32) is within 1.5a + 2^-22 sqrt(d32) of the true distance D.  The winner w
-    // of the exact ranking has D(w) <= D(p)(1 + 2^-50) for every p, in particular for the binary32
-    // minimum, hence sqrt(d32(w)) <= sqrt(m1)(1 + 2^-20) + 4a.  Candidates above `thr` cannot win.
-    const float t = sqrtf(f.m1) * 1.000004f + 5.0f * a;
-    const float thr = t * t * 1.000001f + 1e-30f;
-    if (f.m2 > thr && f.m1 < 3.0e38f) {
-        // a single candidate inside the band, and the exact winner is inside the band: it is the winner
-        const int p = f.pos;
-        const double dx = qx - tv.x[p], dy = qy - tv.y[p];
-        best.d2 = dx * dx + dy * dy;
-        best.pos = p;
-        best.idx = (int)tv.idx[p];
-        return best;
+        if (p1 == p0) break;
+        ICP_NN_COUNT(cand, p1 - p0);
+        for (int p = p0; p < p1; ++p) {
+            const float2 v = tv.pf[p];
+            const float ex = qrx - v.x, ey = qry - v.y;
+            visit(p, nn_fma(ex, ex, ey * ey));
+        }
     }
-    best.idx = (int)tv.idx[s];
+}
+
+// Exact ranking of the candidates inside the band (ties, near-ties, duplicates).
+ICP_DEV NnResult<2, uint32_t, uint32_t> nn_exact_pass(const TargetView& tv, const NnQuery& Q, double qx, double qy,
+                                                      float thr)
+{
+    NnResult<2, uint32_t, uint32_t> best;
+    best.d2 = Q.U2; best.pos = (int)Q.seed; best.idx = (int)tv.idx[Q.seed];
     ICP_NN_COUNT(pass2, 1);
-    walk([&](int p, float d32) {
+    nn_walk(tv, Q, [&](int p, float d32) {
         if (d32 <= thr) {
             ICP_NN_COUNT(exact, 1);
             const double dx = qx - tv.x[p], dy = qy - tv.y[p];
@@ -187,6 +250,27 @@ ICP_DEV NnResult<2, uint32_t, uint32_t> target_nn_search2(const TargetView& tv, 
     });
     return best;
 }
+
+// Exact 1-NN on a 2-D shared target with seeds.  Requires tv.m > 0, tv.seed, tv.pf.
+ICP_DEV NnResult<2, uint32_t, uint32_t> target_nn_search2(const TargetView& tv, double qx, double qy)
+{
+    const NnQuery Q = nn_query_setup(tv, qx, qy);
+    if (Q.slow) return nn_ring_search(tv, qx, qy);
+    ICP_NN_COUNT(q, 1);
+    NnFilterState f;
+    f.m1 = 3.0e38f; f.m2 = 3.0e38f; f.pos = (int)Q.seed;
+    nn_walk(tv, Q, [&](int p, float d32) {
+        f.m2 = fminf(f.m2, fmaxf(d32, f.m1));
+        f.pos = (d32 < f.m1) ? p : f.pos;
+        f.m1 = fminf(f.m1, d32);
+    });
+    const float thr = nn_filter_band(f.m1, Q.a);
+    // a single candidate inside the band, and the exact winner is inside the band: it is the winner
+    if (f.m2 > thr && f.m1 < 3.0e38f) return nn_result_at(tv, qx, qy, f.pos);
+    return nn_exact_pass(tv, Q, qx, qy, thr);
+}
+
+constexpr uint32_t kNnMaxPoints = 1u << 31;   // positions and original indices travel as int
 
 template <int DIM>
 ICP_DEV NnResult<DIM, uint32_t, uint32_t> target_nn_search(const TargetView& tv, double qx, double qy, double qz)

@@ -21,6 +21,8 @@
 struct double2 { double x, y; };
 struct float2 { float x, y; };
 struct uint4 { uint32_t x, y, z, w; };
+static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 struct dim3_ { unsigned x = 1, y = 1, z = 1; };
 
 namespace simt {
@@ -214,9 +216,17 @@ static inline uint32_t __reduce_add_sync(unsigned, uint32_t v)
     for (int i = 0; i < 32; ++i) r += s[i];
     return r;
 }
+static inline uint32_t __reduce_max_sync(unsigned, uint32_t v)
+{
+    const uint32_t* s = simt::warp_exchange(v);
+    uint32_t r = 0;
+    for (int i = 0; i < 32; ++i) r = s[i] > r ? s[i] : r;
+    return r;
+}
 // NOTE: partial warps (block size not a multiple of 32) are not supported by the collectives.
 
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+static inline uint32_t atomicMin(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
 static inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) { auto o = *p; if (v < o) *p = v; return o; }
 static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { auto o = *p; if (v > o) *p = v; return o; }
