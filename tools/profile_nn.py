@@ -17,8 +17,9 @@ def main():
     scans, off, T0 = icp.synth_map_scans(nscan, beams=1080, seed=7)
     sd = torch.from_numpy(scans).to(dev).reshape(nscan, 1080, 2)
     Td = torch.from_numpy(T0).to(dev)
-    R = Td[:, :4].reshape(nscan, 2, 2)
-    q_scan = (torch.einsum("bij,bnj->bni", R, sd) + Td[:, None, 4:6]).reshape(-1, 2).contiguous()
+    sx_, sy_ = sd[..., 0], sd[..., 1]
+    q_scan = torch.stack([Td[:, None, 0] * sx_ + Td[:, None, 1] * sy_ + Td[:, None, 4],
+                          Td[:, None, 2] * sx_ + Td[:, None, 3] * sy_ + Td[:, None, 5]], dim=-1).reshape(-1, 2).contiguous()
     nq = q_scan.shape[0]
     g = torch.Generator(device=dev)
     g.manual_seed(1234)
