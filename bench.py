@@ -66,14 +66,19 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def profiled_traffic(kernel):
-    """dram bytes per launch from the committed ncu --set full capture (profiles/traffic.json)."""
+def profiled_traffic(kernel, units=None):
+    """dram bytes per launch from the committed ncu --set full capture (profiles/traffic.json),
+    scaled to `units` (pairs / queries per launch) when the capture was of a different size."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         with open(p) as f:
             ent = json.load(f).get(kernel)
         if ent:
-            return ent.get("dram_bytes_per_launch")
+            b = ent.get("dram_bytes_per_launch")
+            cap = ent.get("pairs") or ent.get("queries")
+            if b is not None and units and cap and cap != units:
+                return int(round(b * units / cap))
+            return b
     return None
 
 
@@ -347,8 +352,10 @@ def run_gpu(args, rank, local_rank, world):
                     "d2h_bytes_per_step": int(hinfo["d2h_bytes"]), "ms_per_step": e2e_s / K * 1e3,
                     "bit_identical_to_device_path": same},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": f"icp_fused_kernel<{info['block_threads']} threads>", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic("icp_fused_kernel"),
+            "roofline": {"kernel": ("icp_fused_kernel" if args.ordered else "icp_lean_kernel") + f"<{info['block_threads']} threads>",
+                         "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None if args.ordered else profiled_traffic("icp_lean_kernel", B),
                          "peak_source": peak_src, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": BYTES_PER_PAIR * B,
                          "note": "latency/FP64-chain bound by design (34.7 KB per pair, ~190 Gauss-Newton evaluations per pair); see DESIGN.md"},
             "reduction_mode": "ordered sums (bit-exact transforms)" if args.ordered else "warp-tree reductions (default)",
@@ -414,7 +421,7 @@ def bench_nn_search(icp, ctx, torch, dev, stream, map_points=100_000, nscan=1553
             "queries": nq, "map_points": map_points, "ms_per_launch": ms, "parity_sample_ok": ok and okj,
             "jittered_map_points": {"value": nq / (ms_j * 1e-3), "unit": "queries/s", "ms_per_launch": ms_j},
             "roofline": {"kernel": "nn_search_kernel<2>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": profiled_traffic("nn_search_kernel"), "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": profiled_traffic("nn_search_kernel", nq), "peak_source": peak_src,
                          "l2": "268 MB of queries per launch (larger than L2)",
                          "note": "issue-bound: ~60 candidate distances per query in binary32, 2.4 of 4 issue slots, 13 of 32 lanes "
                                  "active (profiles/r01_ncu_full_summary.md); the 20 B/query stream is 2 % of HBM bandwidth"}}
