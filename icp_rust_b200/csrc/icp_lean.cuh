@@ -62,6 +62,7 @@ struct LeanSel {
 struct LeanLayout {
     FusedLayout f;               // target arrays, build temporaries, residual rows (gn_r)
     uint32_t bins;               // u32[ncap]: this stage's bin of (axis 0 | axis 1 << 16) per point
+    uint32_t pos;                // u32[ncap]: sorted position of the point's match in the previous outer iteration
     uint32_t off_sel, off_ctl, total;
 };
 
@@ -70,7 +71,8 @@ ICP_HD LeanLayout lean_layout(int dim, int ncap, int mcap, int cell_budget, bool
     LeanLayout L;
     L.f = fused_layout(dim, ncap, mcap, cell_budget, shared_target, false);
     L.bins = align16(L.f.gn_r + 16u * (uint32_t)ncap);
-    uint32_t u = align128(L.bins + 4u * (uint32_t)ncap);
+    L.pos = align16(L.bins + 4u * (uint32_t)ncap);
+    uint32_t u = align128(L.pos + 4u * (uint32_t)ncap);
     if (u < L.f.u_bytes) u = L.f.u_bytes;
     L.off_sel = u;
     L.off_ctl = align16(L.off_sel + (uint32_t)sizeof(LeanSel));
@@ -308,6 +310,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
     FusedCtl* ctl = reinterpret_cast<FusedCtl*>(smem + LL.off_ctl);
     double2* r2v = reinterpret_cast<double2*>(U + L.gn_r);
     uint32_t* binv = reinterpret_cast<uint32_t*>(U + LL.bins);
+    uint32_t* prev_pos = reinterpret_cast<uint32_t*>(U + LL.pos);
     uint32_t* h0 = sel->lh[0] + kLeanHistBase;
     uint32_t* h1 = sel->lh[1] + kLeanHistBase;
 
@@ -406,10 +409,26 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                 const double pz = (DIM == 3) ? src[(size_t)i * DIM + 2] : 0.0;  // transform_xy keeps z (lib.rs:52-57)
                 double2 d;
                 int idx;
+                // from the second outer iteration on the previous match seeds the search (2-D)
+                const int seed = (DIM == 2 && it > 0) ? (int)prev_pos[i] : -1;
                 if (SHARED_TARGET) {
-                    const NnResult<DIM, uint32_t, uint32_t> r = target_nn_search<DIM>(p.target, q.x, q.y, pz);
+                    const NnResult<DIM, uint32_t, uint32_t> r = target_nn_search<DIM>(p.target, q.x, q.y, pz, seed);
                     d.x = p.target.x[r.pos]; d.y = p.target.y[r.pos];
                     idx = r.idx;
+                    if (DIM == 2) prev_pos[i] = (uint32_t)r.pos;
+                } else if (DIM == 2) {
+                    GridView<2, uint16_t, uint16_t> gv;
+                    gv.x = reinterpret_cast<const double*>(U + L.nn_x);
+                    gv.y = reinterpret_cast<const double*>(U + L.nn_y);
+                    gv.z = nullptr;
+                    gv.idx = reinterpret_cast<const uint16_t*>(U + L.nn_idx);
+                    gv.cstart = reinterpret_cast<const uint16_t*>(U + L.nn_cell);
+                    gv.g = geom;
+                    const NnResult<2, uint16_t, uint16_t> r =
+                        seed >= 0 ? grid_nn_search_seeded(gv, q.x, q.y, seed) : grid_nn_search(gv, q.x, q.y, 0.0);
+                    d.x = gv.x[r.pos]; d.y = gv.y[r.pos];
+                    idx = r.idx;
+                    prev_pos[i] = (uint32_t)r.pos;
                 } else {
                     GridView<DIM, uint16_t, uint16_t> gv;
                     gv.x = reinterpret_cast<const double*>(U + L.nn_x);

@@ -108,7 +108,9 @@ struct NnQuery {
     bool slow;         // outside the filter's range: ring search instead
 };
 
-ICP_DEV NnQuery nn_query_setup(const TargetView& tv, double qx, double qy)
+// seed_pos < 0: the seed of the query's cell; else any sorted position (e.g. the match the same
+// source point had in the previous outer iteration — usually the tighter disc)
+ICP_DEV NnQuery nn_query_setup(const TargetView& tv, double qx, double qy, int seed_pos = -1)
 {
     const GridGeom& g = tv.g;
     NnQuery Q;
@@ -117,9 +119,13 @@ ICP_DEV NnQuery nn_query_setup(const TargetView& tv, double qx, double qy)
     Q.txf = (float)Q.tx; Q.tyf = (float)Q.ty;
     Q.slow = false;
     Q.ya = 1; Q.yb = 0; Q.Uc2 = 0.0f; Q.a = 0.0f; Q.sx = 0.0f; Q.sy = 0.0f; Q.U2 = 0.0;
-    const int cx = grid_coord(qx, g.ox, g.inv_h, g.gx);
-    const int cy = grid_coord(qy, g.oy, g.inv_h, g.gy);
-    Q.seed = tv.seed[cy * g.gx + cx];
+    if (seed_pos >= 0) {
+        Q.seed = (uint32_t)seed_pos;
+    } else {
+        const int cx = grid_coord(qx, g.ox, g.inv_h, g.gx);
+        const int cy = grid_coord(qy, g.oy, g.inv_h, g.gy);
+        Q.seed = tv.seed[cy * g.gx + cx];
+    }
     if (Q.seed >= tv.m || !(fabsf(Q.txf) + fabsf(Q.tyf) <= 1e9f)) { Q.slow = true; return Q; }
     const double dx = qx - tv.x[Q.seed], dy = qy - tv.y[Q.seed];
     Q.U2 = dx * dx + dy * dy;
@@ -252,9 +258,9 @@ ICP_DEV NnResult<2, uint32_t, uint32_t> nn_exact_pass(const TargetView& tv, cons
 }
 
 // Exact 1-NN on a 2-D shared target with seeds.  Requires tv.m > 0, tv.seed, tv.pf.
-ICP_DEV NnResult<2, uint32_t, uint32_t> target_nn_search2(const TargetView& tv, double qx, double qy)
+ICP_DEV NnResult<2, uint32_t, uint32_t> target_nn_search2(const TargetView& tv, double qx, double qy, int seed_pos = -1)
 {
-    const NnQuery Q = nn_query_setup(tv, qx, qy);
+    const NnQuery Q = nn_query_setup(tv, qx, qy, seed_pos);
     if (Q.slow) return nn_ring_search(tv, qx, qy);
     ICP_NN_COUNT(q, 1);
     NnFilterState f;
@@ -272,11 +278,50 @@ ICP_DEV NnResult<2, uint32_t, uint32_t> target_nn_search2(const TargetView& tv, 
 
 constexpr uint32_t kNnMaxPoints = 1u << 31;   // positions and original indices travel as int
 
+// ---------------------------------------------------------------------------------------------
+// Per-pair grids (shared memory / L2 slab, icp_fused.cuh, icp_lean.cuh): the same disc walk seeded
+// with the match the source point had in the previous outer iteration.  ICP moves the scan by less
+// and less, so that match is usually still the nearest point or next to it, and the disc covers one
+// or two cells where the ring search always opens 3x3.  No binary32 copies here: the few candidates
+// are ranked directly on their exact binary64 d2 (lowest original index on ties).  2-D only.
+template <typename IdxT, typename CellT>
+ICP_DEV NnResult<2, IdxT, CellT> grid_nn_search_seeded(const GridView<2, IdxT, CellT>& gv, double qx, double qy, int seed_pos)
+{
+    const GridGeom& g = gv.g;
+    NnResult<2, IdxT, CellT> best;
+    {
+        const double dx = qx - gv.x[seed_pos], dy = qy - gv.y[seed_pos];
+        best.d2 = dx * dx + dy * dy;
+        best.pos = seed_pos;
+        best.idx = (int)gv.idx[seed_pos];
+    }
+    NnQuery Q;
+    Q.tx = nn_cell_coord(qx, g.ox, g.inv_h);
+    Q.ty = nn_cell_coord(qy, g.oy, g.inv_h);
+    Q.txf = (float)Q.tx; Q.tyf = (float)Q.ty;
+    const float ihf = (float)g.inv_h;
+    Q.Uc2 = ((float)best.d2 * ihf) * ihf * 1.000001f + 1e-30f;      // as in nn_query_setup
+    if (!(fabsf(Q.txf) + fabsf(Q.tyf) <= 1e9f) || !(Q.Uc2 <= 1e12f) || !(best.d2 >= 0.0))
+        return grid_nn_search(gv, qx, qy, 0.0);
+    const float Uc = sqrtf(Q.Uc2) * 1.000001f;
+    Q.sx = (fabsf(Q.txf) + 1.0f) * 3.6e-7f;
+    Q.sy = (fabsf(Q.tyf) + 1.0f) * 3.6e-7f;
+    const int ya = nn_floor_clamp(Q.tyf - Uc - Q.sy, g.gy - 1);     // bound (rows)
+    const int yb = nn_floor_clamp(Q.tyf + Uc + Q.sy, g.gy - 1);
+    for (int yy = ya; yy <= yb; ++yy) {
+        int xa, xb;
+        if (!nn_row_span(Q, yy, g.gx, &xa, &xb)) continue;          // bound (columns)
+        grid_scan_cells(gv, yy * g.gx, xa, xb, qx, qy, 0.0, best);
+    }
+    return best;
+}
+
 template <int DIM>
-ICP_DEV NnResult<DIM, uint32_t, uint32_t> target_nn_search(const TargetView& tv, double qx, double qy, double qz)
+ICP_DEV NnResult<DIM, uint32_t, uint32_t> target_nn_search(const TargetView& tv, double qx, double qy, double qz,
+                                                          int seed_pos = -1)
 {
     if constexpr (DIM == 2) {
-        if (tv.pf != nullptr) return target_nn_search2(tv, qx, qy);
+        if (tv.pf != nullptr) return target_nn_search2(tv, qx, qy, seed_pos);
     }
     GridView<DIM, uint32_t, uint32_t> gv;
     gv.x = tv.x; gv.y = tv.y; gv.z = tv.z; gv.idx = tv.idx; gv.cstart = tv.cstart; gv.g = tv.g;
