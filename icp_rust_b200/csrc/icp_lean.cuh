@@ -409,24 +409,11 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                 const double pz = (DIM == 3) ? src[(size_t)i * DIM + 2] : 0.0;  // transform_xy keeps z (lib.rs:52-57)
                 double2 d;
                 int idx;
-                // from the second outer iteration on the previous match seeds the search (2-D)
-                const int seed = (DIM == 2 && it > 0) ? (int)prev_pos[i] : -1;
+                // from the second outer iteration on the previous match seeds the search
+                const int seed = (it > 0) ? (int)prev_pos[i] : -1;
                 if (SHARED_TARGET) {
                     const NnResult<DIM, uint32_t, uint32_t> r = target_nn_search<DIM>(p.target, q.x, q.y, pz, seed);
                     d.x = p.target.x[r.pos]; d.y = p.target.y[r.pos];
-                    idx = r.idx;
-                    if (DIM == 2) prev_pos[i] = (uint32_t)r.pos;
-                } else if (DIM == 2) {
-                    GridView<2, uint16_t, uint16_t> gv;
-                    gv.x = reinterpret_cast<const double*>(U + L.nn_x);
-                    gv.y = reinterpret_cast<const double*>(U + L.nn_y);
-                    gv.z = nullptr;
-                    gv.idx = reinterpret_cast<const uint16_t*>(U + L.nn_idx);
-                    gv.cstart = reinterpret_cast<const uint16_t*>(U + L.nn_cell);
-                    gv.g = geom;
-                    const NnResult<2, uint16_t, uint16_t> r =
-                        seed >= 0 ? grid_nn_search_seeded(gv, q.x, q.y, seed) : grid_nn_search(gv, q.x, q.y, 0.0);
-                    d.x = gv.x[r.pos]; d.y = gv.y[r.pos];
                     idx = r.idx;
                     prev_pos[i] = (uint32_t)r.pos;
                 } else {
@@ -437,9 +424,11 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                     gv.idx = reinterpret_cast<const uint16_t*>(U + L.nn_idx);
                     gv.cstart = reinterpret_cast<const uint16_t*>(U + L.nn_cell);
                     gv.g = geom;
-                    const NnResult<DIM, uint16_t, uint16_t> r = grid_nn_search(gv, q.x, q.y, pz);
+                    const NnResult<DIM, uint16_t, uint16_t> r =
+                        seed >= 0 ? grid_nn_search_seeded(gv, q.x, q.y, pz, seed) : grid_nn_search(gv, q.x, q.y, pz);
                     d.x = gv.x[r.pos]; d.y = gv.y[r.pos];
                     idx = r.idx;
+                    prev_pos[i] = (uint32_t)r.pos;
                 }
                 r2v[i] = d;
                 hpart += mix64(((uint64_t)(uint32_t)i << 32) | (uint64_t)(uint32_t)idx);

@@ -18,6 +18,7 @@ namespace icp {
 
 struct StreamLayout {   // byte offsets inside one CTA's slab
     uint64_t s0, s1;                       // double2[n_cap] each
+    uint64_t spos;                         // u32[n_cap]: sorted position of each point's previous match
     uint64_t gx, gy, gz, gidx, gslot;      // target copy sorted by cell
     uint64_t gcnt, gcstart;
     uint64_t total;
@@ -31,6 +32,7 @@ ICP_HD StreamLayout stream_layout(int dim, uint32_t n_cap, uint32_t m_cap, uint3
     uint64_t o = 0;
     L.s0 = o; o = align256(o + 16ull * n_cap);
     L.s1 = o; o = align256(o + 16ull * n_cap);
+    L.spos = o; o = align256(o + 4ull * n_cap);
     if (shared_target) { m_cap = 0; c_cap = 0; }
     L.gx = o; o = align256(o + 8ull * m_cap);
     L.gy = o; o = align256(o + 8ull * m_cap);
@@ -105,6 +107,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, 1) icp_stream_kernel(StreamParams sp)
     unsigned char* slab = p.workspace + (size_t)blockIdx.x * p.ws_stride;
     double2* S0 = reinterpret_cast<double2*>(slab + L.s0);
     double2* S1 = reinterpret_cast<double2*>(slab + L.s1);
+    uint32_t* spos = reinterpret_cast<uint32_t*>(slab + L.spos);
 
     for (int q = tid; q < 2 * kSelHistPad; q += THREADS) (&sel->hist[0][0])[q] = 0u;
     int hist_par = 0;
@@ -236,8 +239,12 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, 1) icp_stream_kernel(StreamParams sp)
                 double2 s;
                 transform_apply(T, src[(size_t)i * DIM + 0], src[(size_t)i * DIM + 1], &s.x, &s.y);
                 const double pz = (DIM == 3) ? src[(size_t)i * DIM + 2] : 0.0;
+                // from the second outer iteration on the previous match seeds the search (icp_target_nn.cuh)
+                const int seed = (it > 0) ? (int)spos[i] : -1;
                 const NnResult<DIM, uint32_t, uint32_t> r =
-                    SHARED_TARGET ? target_nn_search<DIM>(p.target, s.x, s.y, pz) : grid_nn_search(gv, s.x, s.y, pz);
+                    SHARED_TARGET ? target_nn_search<DIM>(p.target, s.x, s.y, pz, seed)
+                                  : (seed >= 0 ? grid_nn_search_seeded(gv, s.x, s.y, pz, seed) : grid_nn_search(gv, s.x, s.y, pz));
+                spos[i] = (uint32_t)r.pos;
                 double2 d;
                 d.x = gv.x[r.pos]; d.y = gv.y[r.pos];   // get_xy (lib.rs:86-89)
                 S0[i] = s;

@@ -279,19 +279,29 @@ ICP_DEV NnResult<2, uint32_t, uint32_t> target_nn_search2(const TargetView& tv, 
 constexpr uint32_t kNnMaxPoints = 1u << 31;   // positions and original indices travel as int
 
 // ---------------------------------------------------------------------------------------------
-// Per-pair grids (shared memory / L2 slab, icp_fused.cuh, icp_lean.cuh): the same disc walk seeded
-// with the match the source point had in the previous outer iteration.  ICP moves the scan by less
-// and less, so that match is usually still the nearest point or next to it, and the disc covers one
-// or two cells where the ring search always opens 3x3.  No binary32 copies here: the few candidates
-// are ranked directly on their exact binary64 d2 (lowest original index on ties).  2-D only.
-template <typename IdxT, typename CellT>
-ICP_DEV NnResult<2, IdxT, CellT> grid_nn_search_seeded(const GridView<2, IdxT, CellT>& gv, double qx, double qy, int seed_pos)
+// Per-pair grids (shared memory / L2 slab: icp_lean.cuh, icp_stream.cuh) and 3-D shared targets:
+// the same disc (ball) walk seeded with the match the source point had in the previous outer
+// iteration.  ICP moves the scan by less and less, so that match is usually still the nearest point
+// or next to it, and the disc covers one or two cells where the ring search always opens 3x3(x3).
+// No binary32 copies here: the few candidates are ranked directly on their exact binary64 d2 (lowest
+// original index on ties).
+//
+// bound (3-D): a skipped point lies in a slab outside [za, zb] (|dz|/h > Uc), or in a row of slab zz
+// outside [ya, yb] (dy^2 + dz^2 > h^2 (ry^2 + zdc^2) >= h^2 Uc2), or in a column outside [xa, xb]
+// (dx^2 + dy^2 + dz^2 > h^2 (wc^2 + ydc^2 + zdc^2) >= h^2 Uc2): its computed d2 exceeds the seed's.
+template <int DIM, typename IdxT, typename CellT>
+ICP_DEV NnResult<DIM, IdxT, CellT> grid_nn_search_seeded(const GridView<DIM, IdxT, CellT>& gv, double qx, double qy,
+                                                         double qz, int seed_pos)
 {
     const GridGeom& g = gv.g;
-    NnResult<2, IdxT, CellT> best;
+    NnResult<DIM, IdxT, CellT> best;
     {
         const double dx = qx - gv.x[seed_pos], dy = qy - gv.y[seed_pos];
         best.d2 = dx * dx + dy * dy;
+        if (DIM == 3) {
+            const double dz = qz - gv.z[seed_pos];
+            best.d2 = best.d2 + dz * dz;
+        }
         best.pos = seed_pos;
         best.idx = (int)gv.idx[seed_pos];
     }
@@ -299,23 +309,47 @@ ICP_DEV NnResult<2, IdxT, CellT> grid_nn_search_seeded(const GridView<2, IdxT, C
     Q.tx = nn_cell_coord(qx, g.ox, g.inv_h);
     Q.ty = nn_cell_coord(qy, g.oy, g.inv_h);
     Q.txf = (float)Q.tx; Q.tyf = (float)Q.ty;
+    const float tzf = (DIM == 3) ? (float)nn_cell_coord(qz, g.oz, g.inv_h) : 0.0f;
     const float ihf = (float)g.inv_h;
     Q.Uc2 = ((float)best.d2 * ihf) * ihf * 1.000001f + 1e-30f;      // as in nn_query_setup
-    if (!(fabsf(Q.txf) + fabsf(Q.tyf) <= 1e9f) || !(Q.Uc2 <= 1e12f) || !(best.d2 >= 0.0))
-        return grid_nn_search(gv, qx, qy, 0.0);
+    if (!(fabsf(Q.txf) + fabsf(Q.tyf) + fabsf(tzf) <= 1e9f) || !(Q.Uc2 <= 1e12f) || !(best.d2 >= 0.0))
+        return grid_nn_search(gv, qx, qy, qz);
     const float Uc = sqrtf(Q.Uc2) * 1.000001f;
     Q.sx = (fabsf(Q.txf) + 1.0f) * 3.6e-7f;
     Q.sy = (fabsf(Q.tyf) + 1.0f) * 3.6e-7f;
-    const int ya = nn_floor_clamp(Q.tyf - Uc - Q.sy, g.gy - 1);     // bound (rows)
-    const int yb = nn_floor_clamp(Q.tyf + Uc + Q.sy, g.gy - 1);
-    for (int yy = ya; yy <= yb; ++yy) {
-        int xa, xb;
-        if (!nn_row_span(Q, yy, g.gx, &xa, &xb)) continue;          // bound (columns)
-        grid_scan_cells(gv, yy * g.gx, xa, xb, qx, qy, 0.0, best);
+    if (DIM == 2) {
+        const int ya = nn_floor_clamp(Q.tyf - Uc - Q.sy, g.gy - 1);     // bound (rows)
+        const int yb = nn_floor_clamp(Q.tyf + Uc + Q.sy, g.gy - 1);
+        for (int yy = ya; yy <= yb; ++yy) {
+            int xa, xb;
+            if (!nn_row_span(Q, yy, g.gx, &xa, &xb)) continue;          // bound (columns)
+            grid_scan_cells(gv, yy * g.gx, xa, xb, qx, qy, qz, best);
+        }
+    } else {
+        const float sz = (fabsf(tzf) + 1.0f) * 3.6e-7f;
+        const int za = nn_floor_clamp(tzf - Uc - sz, g.gz - 1);
+        const int zb = nn_floor_clamp(tzf + Uc + sz, g.gz - 1);
+        const float Uc2 = Q.Uc2;
+        for (int zz = za; zz <= zb; ++zz) {
+            const float zf = (float)zz;
+            const float zdc = fmaxf(fmaxf(zf - tzf, tzf - (zf + 1.0f)) - sz, 0.0f) * 0.999999f;
+            const float rem2 = Uc2 - zdc * zdc;
+            if (rem2 < 0.0f) continue;
+            const float ry = sqrtf(rem2) * 1.000001f + Q.sy;
+            const int ya = nn_floor_clamp(Q.tyf - ry, g.gy - 1);
+            const int yb = nn_floor_clamp(Q.tyf + ry, g.gy - 1);
+            Q.Uc2 = rem2;   // nn_row_span then tests wc^2 + ydc^2 against Uc2 - zdc^2
+            for (int yy = ya; yy <= yb; ++yy) {
+                int xa, xb;
+                if (!nn_row_span(Q, yy, g.gx, &xa, &xb)) continue;
+                grid_scan_cells(gv, (zz * g.gy + yy) * g.gx, xa, xb, qx, qy, qz, best);
+            }
+        }
     }
     return best;
 }
 
+// seed_pos >= 0: a sorted position of the target (the previous outer iteration's match); -1: none
 template <int DIM>
 ICP_DEV NnResult<DIM, uint32_t, uint32_t> target_nn_search(const TargetView& tv, double qx, double qy, double qz,
                                                           int seed_pos = -1)
@@ -325,6 +359,7 @@ ICP_DEV NnResult<DIM, uint32_t, uint32_t> target_nn_search(const TargetView& tv,
     }
     GridView<DIM, uint32_t, uint32_t> gv;
     gv.x = tv.x; gv.y = tv.y; gv.z = tv.z; gv.idx = tv.idx; gv.cstart = tv.cstart; gv.g = tv.g;
+    if (seed_pos >= 0 && (uint32_t)seed_pos < tv.m) return grid_nn_search_seeded(gv, qx, qy, qz, seed_pos);
     return grid_nn_search(gv, qx, qy, qz);
 }
 
