@@ -357,3 +357,47 @@ def test_config4_shape_batch(ctx, icp, scans3d):
     g = _run(ctx, icp, srcs, dsts, T0, 20, dim=3)
     assert ctx.call_info()["block_threads"] == 512
     _check_vs_oracle(g, srcs, dsts, T0, 20, ordered=False)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_scan_chain_driver_matches_oracle_chain(ctx, icp, scans2d):
+    """examples/scan2d.rs:62-105 through icp_rust_b200.scans.scan_chain: transforms bit-identical to
+    the oracle's warm-started chain, path = translation of the inverse (transform.rs:26-32)."""
+    from icp_rust_b200 import scans as S
+    seq = [scans2d[k] for k in range(1, 8)]
+    transforms, path = S.scan_chain(seq, 20, ctx)
+    T = I6.copy()
+    for k, est in enumerate(transforms):
+        T = oracle.icp_estimate(seq[0], seq[k + 1], T, 20)["T"]
+        assert np.array_equal(est.to_array(), T)
+        assert np.allclose(path[k], oracle.transform_inverse(T)[4:], rtol=0, atol=1e-9)
+
+
+def test_scan_chain_driver_3d(ctx, icp, scans3d):
+    """examples/scan3d.rs:104-148 on the bundled frames (27k points: streaming kernel)."""
+    from icp_rust_b200 import scans as S
+    frames = [scans3d[0][:6000], scans3d[0][:6000], scans3d[1][:6000]]
+    transforms, path = S.scan_chain(frames, 5, ctx)
+    T = I6.copy()
+    for k, est in enumerate(transforms):
+        T = oracle.icp_estimate(frames[0], frames[k + 1], T, 5, nn_mode=oracle.NN_KDTREE)["T"]
+        assert np.abs(est.to_array() - T).max() <= 1e-9
+    assert path.shape == (2, 2)
+
+
+def test_multi_hypothesis_front_end(ctx, icp, scans2d):
+    """many initial transforms for one pair in one batch, scored with lib.rs:45-50."""
+    from icp_rust_b200 import scans as S
+    src, dst = scans2d[10], scans2d[12]
+    inits = [I6, oracle.transform_new([30., -20., 0.02]), oracle.transform_new([-60., 45., -0.05]),
+             oracle.transform_new([400., 400., 0.6])]
+    r = S.estimate_best_of(src, dst, inits, 20, ctx)
+    costs = []
+    for h, T0 in enumerate(inits):
+        o = oracle.icp_estimate(src, dst, T0, 20, nn_mode=oracle.NN_KDTREE)
+        assert np.abs(r["T"][h] - o["T"]).max() <= 1e-9
+        moved = np.array([oracle.transform_apply(o["T"], p) for p in src])
+        m = dst[oracle.nn_search(dst, moved, oracle.NN_BRUTE)]
+        costs.append(oracle.huber_error(o["T"], src, m))
+    assert np.allclose(r["cost"], costs, rtol=1e-6)
+    assert r["best"] == int(np.argmin(costs))

@@ -1,7 +1,10 @@
 """Per-source-line totals of an `ncu -i rep --page source --csv --print-source cuda,sass` dump:
 share of warp instructions, average active lanes per instruction, share of stall samples.
-usage: ncu_srclines.py <dump.csv> [kernel ordinal, default 0] [top N, default 40]"""
+usage: ncu_srclines.py <dump.csv> [kernel ordinal, default 0] [top N, default 40] [csrc dir: also per-region totals]
+A source line belongs to the last `// @region <name>` marker above it in its file."""
 import csv
+import os
+import re
 import sys
 from collections import defaultdict
 
@@ -43,6 +46,26 @@ def main():
     print(f"warp instructions {tot}, thread instructions {sum(v[1] for v in agg.values())}, samples {tots}")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
         print(f"{k[0]:20s}{k[1]:4d} inst {100 * v[0] / tot:5.1f}%  lanes {v[1] / v[0]:5.1f}  samples {100 * v[2] / tots:5.1f}%  {src[k].strip()[:88]}")
+    if len(sys.argv) > 4:
+        csrc = sys.argv[4]
+        reg = defaultdict(lambda: [0, 0, 0])
+        rmap = {}
+        for fn in os.listdir(csrc):
+            if fn.endswith((".cuh", ".cu", ".h")):
+                cur, m = fn, {}
+                for ln, text in enumerate(open(os.path.join(csrc, fn), errors="replace"), 1):
+                    g = re.search(r"//\s*@region\s+(\S+)", text)
+                    if g:
+                        cur = g.group(1)
+                    m[ln] = cur
+                rmap[fn] = m
+        for (fn, ln), v in agg.items():
+            r = rmap.get(fn, {}).get(ln, fn)
+            for q in range(3):
+                reg[r][q] += v[q]
+        print("\nper region:")
+        for r, v in sorted(reg.items(), key=lambda kv: -kv[1][0]):
+            print(f"{r:28s} inst {100 * v[0] / tot:5.1f}%  lanes {v[1] / max(v[0], 1):5.1f}  samples {100 * v[2] / tots:5.1f}%")
 
 
 if __name__ == "__main__":
