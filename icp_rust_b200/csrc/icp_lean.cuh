@@ -12,16 +12,17 @@
 //   barrier
 //   warp a        axis a: prefix-scan the histogram, find the bin(s) holding the median ranks,
 //                 collect those points' keys by scanning the bin numbers, rank them -> exact median
+//                 ... and, from the SAME histogram, the exact MAD: |r - median| <= t is the window
+//                 [median - t, median + t] of r, so the rank's candidates sit in the two bins the
+//                 window's ends reach (lean_serve_mad; verified before it is trusted); sigma =
+//                 1.4826*MAD, 1/sigma and the next evaluation's bin maps are published by the warp
 //   barrier
-//   all threads   bins of |r - median| -> second histogram
-//   barrier
-//   warp a        same service -> exact MAD; sigma = 1.4826*MAD, 1/sigma and the next
-//                 evaluation's bin maps are published by the service warp
-//   barrier
+//   (only when lean_serve_mad declines: all threads bin |r - median| into a second histogram,
+//    barrier, warp a serves it as in stage 0, barrier)
 //   all threads   Huber weights, Jacobian rows, 10 partial sums; fixed warp tree; warp 0 solves,
 //                 takes the break decisions and publishes the new inner transform (2 barriers)
 //
-// 6 barriers per evaluation and no per-thread selection state.  Whenever the short path cannot
+// 4 barriers per evaluation (6 on the second-histogram path) and no per-thread selection state.  Whenever the short path cannot
 // serve a selection (no estimate yet, rank outside the binned range, more than 32 keys in the
 // rank's bins) the CTA runs the general selection block_median2 over the shared rows instead, so
 // results never depend on which path ran: both return the exact order statistic.
@@ -41,7 +42,7 @@ constexpr int kLeanHistBase = 3;
 // Buckets: the points of the kLeanWin bins around the bin the previous evaluation's median maps to
 // (number kLeanCentre) are remembered per bin, in arrival order (the slot the histogram atomic
 // returns), so the service warp fetches the median's candidates without looking at other points.
-constexpr int kLeanWin = 64;
+constexpr int kLeanWin = 128;   // covers median +- 1 sigma: the MAD's bins (+-0.67 sigma) fall inside
 constexpr int kLeanCentre = kSelBins / 2 + 1;
 constexpr int kLeanWinLo = kLeanCentre - kLeanWin / 2;
 constexpr int kLeanCap = 24;
@@ -57,6 +58,7 @@ struct LeanSel {
     float lo0[2], sc0[2], lo1[2], sc1[2];      // bin maps of the next evaluation, stage 0 / stage 1
     int valid[2];                // bin maps usable
     int ok[2];                   // the service warp served its axis in the current stage
+    int ok1[2];                  // ... and also found the MAD from the stage-0 histogram
 };
 
 struct LeanLayout {
@@ -130,7 +132,8 @@ ICP_DEV void lean_find_rank(const uint32_t c[8], uint32_t incl, uint32_t tot, ui
 // |r[i].axis - centre|.
 // @region lean_serve
 ICP_DEV bool lean_serve(const uint32_t* h, const uint16_t (*bucket)[kLeanCap], const uint32_t* bins,
-                        const double2* rows, double* list, int n, int axis, int absdev, double centre, double* out)
+                        const double2* rows, double* list, int n, int axis, int absdev, double centre, double* out,
+                        uint32_t* pfx = nullptr)
 {
     const int lane = lane_id();
     const int sh = axis * 16;
@@ -152,6 +155,15 @@ ICP_DEV bool lean_serve(const uint32_t* h, const uint16_t (*bucket)[kLeanCap], c
     for (int q = 0; q < 8; ++q) c[q] = (c[q] >> sh) & 0xffffu;
     tot = (tot >> sh) & 0xffffu;
     incl = ((incl >> sh) & 0xffffu) + under;
+    if (pfx) {   // inclusive prefix of the bins for lean_serve_mad: pfx[b] = keys in bins 0..b
+        uint32_t run = incl - tot;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            run += c[q];
+            pfx[8 * lane + 1 + q] = run;
+        }
+        if (lane == 0) pfx[0] = under;
+    }
     const uint32_t regular_end = __shfl_sync(ICP_FULL_MASK, incl, 31);   // keys in UNDER + regular bins
     const uint32_t k_top = need_hi ? k + 1u : k;
     bool ok = k >= under && k_top < regular_end;
@@ -221,6 +233,103 @@ ICP_DEV bool lean_serve(const uint32_t* h, const uint16_t (*bucket)[kLeanCap], c
     } else {
         *out = v0;
     }
+    return true;
+}
+
+// MAD of one axis from the STAGE-0 histogram (bins of r under the map (lo, scale)), by the warp
+// that has just found the exact median `med`: the k-th smallest |r - med| is the smallest t whose
+// window [med - t, med + t] holds k + 1 points.  Bins are uniform in value, so as t grows the
+// window's ends cross bin edges alternately; state s = 0, 1, 2, ... names the pair of bins (bl, bh)
+// the ends lie in.  For the first state whose bins [bl, bh] hold more than the wanted rank(s), the
+// points strictly between bl and bh are closer than the answer, the points outside farther, and the
+// points of bl and bh are ranked exactly.  The state arithmetic is only a guess: the result is
+// returned only if binning the window's ends for the ranked answer reproduces (bl, bh) with slack
+// on the safe side — that check alone carries the proof:
+//   bound: bin() is monotone.  bin(r) > bl = bin(med - v0 + eps) gives r > med - v0 + eps, i.e.
+//   computed |r - med| < v0 (eps = 1e-15 (|med| + t) exceeds every rounding involved); bin(r) < bl =
+//   bin(med - v1 - eps) gives r < med - v1 - eps, i.e. computed |r - med| > v1; same on the right.
+// Otherwise (ends near a bin edge, crowded or far bins) false: the caller bins |r - med| itself.
+// `pfx`: the inclusive bin prefix lean_serve left for this axis (260 words owned by this warp).
+// @region lean_serve_mad
+ICP_DEV bool lean_serve_mad(const uint16_t (*bucket)[kLeanCap], const double2* rows, double* list,
+                            const uint32_t* pfx, int n, int axis, double med, float lo, float scale, double* out)
+{
+    const int lane = lane_id();
+    const bool need_hi = (n % 2) == 0;
+    const uint32_t k = need_hi ? (uint32_t)(n / 2 - 1) : (uint32_t)(n / 2);
+    const uint32_t k_top = need_hi ? k + 1u : k;
+    // pfx[b] = keys in bins 0..b, written by this warp in lean_serve (the __syncwarp()s there order it)
+    // ---- the median's bin and its position inside it
+    float u = (__double2float_rn(med) - lo) * scale;
+    if (!(u >= 0.0f && u < (float)kSelBins)) return false;
+    const float uf = floorf(u);
+    const int bm = (int)uf + 1;
+    const bool left_first = (u - uf) < 0.5f;
+    // ---- first state whose bins hold rank k_top
+    int s_star = -1;
+    uint32_t votes[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int s = 32 * q + lane;
+        const int a = (s + 1) >> 1, b = s >> 1;
+        const int bl = bm - (left_first ? a : b), bh = bm + (left_first ? b : a);
+        const bool in_range = bl >= 1 && bh <= kSelBins;
+        const uint32_t total = in_range ? pfx[bh] - pfx[bl - 1] : 0u;
+        votes[q] = __ballot_sync(ICP_FULL_MASK, in_range && total > k_top);
+    }
+#pragma unroll
+    for (int q = 3; q >= 0; --q)
+        if (votes[q]) s_star = 32 * q + __ffs((int)votes[q]) - 1;
+    if (s_star < 0) return false;
+    // bins of state s* and of the state after it: the answer is reached in one of the two (by the end
+    // of s*+1 the window covers every point of s*'s bins, more than the rank needs)
+    const int sa = (s_star + 1) >> 1, sb = s_star >> 1, na = (s_star + 2) >> 1, nb = (s_star + 1) >> 1;
+    const int bl = bm - (left_first ? sa : sb), bh = bm + (left_first ? sb : sa);
+    const int nl = bm - (left_first ? na : nb), nh = bm + (left_first ? nb : na);
+    if (nl < 1 || nh > kSelBins) return false;
+    const uint32_t inside = bh > bl ? pfx[bh - 1] - pfx[bl] : 0u;
+    // candidate bins, ascending, duplicates with count 0: nl (<= bl), bl, bh (>= bl), nh (>= bh)
+    const uint32_t c0 = nl < bl ? pfx[nl] - pfx[nl - 1] : 0u;
+    const uint32_t c1 = pfx[bl] - pfx[bl - 1];
+    const uint32_t c2 = bh > bl ? pfx[bh] - pfx[bh - 1] : 0u;
+    const uint32_t c3 = nh > bh ? pfx[nh] - pfx[nh - 1] : 0u;
+    const uint32_t count = c0 + c1 + c2 + c3;
+    const uint32_t cap = (uint32_t)kLeanCap;
+    if (!(inside <= k && count <= (uint32_t)kSelCap && c0 <= cap && c1 <= cap && c2 <= cap && c3 <= cap &&
+          (uint32_t)(nl - kLeanWinLo) < (uint32_t)kLeanWin && (uint32_t)(nh - kLeanWinLo) < (uint32_t)kLeanWin))
+        return false;
+    // ---- rank the points of those bins on their exact |r - med|
+    double mine = 0.;
+    if ((uint32_t)lane < count) {
+        uint32_t o = (uint32_t)lane;
+        int bin = nl;
+        if (o >= c0) { o -= c0; bin = bl; if (o >= c1) { o -= c1; bin = bh; if (o >= c2) { o -= c2; bin = nh; } } }
+        const int i = (int)bucket[bin - kLeanWinLo][o];
+        const double2 rr = rows[i];
+        mine = sel_key(axis ? rr.y : rr.x, 1, med);
+        list[lane] = mine;
+    }
+    __syncwarp();
+    uint32_t nlt = 0, nle = 0;
+    for (uint32_t m = 0; m < count; ++m) {
+        const double o = list[m];
+        nlt += (o < mine) ? 1u : 0u;
+        nle += (o <= mine) ? 1u : 0u;
+    }
+    const uint32_t kp = k - inside;
+    const bool have = (uint32_t)lane < count;
+    const uint32_t vote0 = __ballot_sync(ICP_FULL_MASK, have && nlt <= kp && kp < nle);
+    const uint32_t vote1 = __ballot_sync(ICP_FULL_MASK, have && nlt <= kp + 1u && kp + 1u < nle);
+    if (vote0 == 0u || (need_hi && vote1 == 0u)) return false;
+    const double v0 = shfl_f64(mine, __ffs((int)vote0) - 1);
+    const double v1 = need_hi ? shfl_f64(mine, __ffs((int)vote1) - 1) : v0;
+    // ---- verify against the answer (see bound above): the points strictly between bl and bh are
+    // closer than v0, the points beyond nl / nh farther than v1
+    const double e0 = (fabs(med) + v0) * 1e-15, e1 = (fabs(med) + v1) * 1e-15;
+    const bool good = lean_bin((med - v0) + e0, lo, scale) <= (uint32_t)bl && lean_bin((med + v0) - e0, lo, scale) >= (uint32_t)bh &&
+                      lean_bin((med - v1) - e1, lo, scale) >= (uint32_t)nl && lean_bin((med + v1) + e1, lo, scale) <= (uint32_t)nh;
+    if (!good) return false;
+    *out = need_hi ? (v0 + v1) / 2. : v0;
     return true;
 }
 
@@ -495,13 +604,23 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                         __syncthreads();
                         ICP_LT_MARK(2)
                         if (warp < 2) {
-                            double v = 0.;
-                            const bool ok = lean_serve(h0, sel->bucket[warp], binv, r2v, sel->s.list[warp], n, warp, 0, 0., &v);
-                            if (lane == 0) { sel->med[warp] = v; sel->ok[warp] = ok ? 1 : 0; }
+                            double v = 0., dev = 0.;
+                            const float mlo = sel->lo0[warp], msc = sel->sc0[warp];
+                            const bool ok = lean_serve(h0, sel->bucket[warp], binv, r2v, sel->s.list[warp], n, warp, 0, 0., &v,
+                                                       sel->s.hist[warp]);
+                            const bool ok1 = ok && lean_serve_mad(sel->bucket[warp], r2v, sel->s.list[warp], sel->s.hist[warp], n,
+                                                                  warp, v, mlo, msc, &dev);
+                            if (lane == 0) {
+                                sel->med[warp] = v; sel->ok[warp] = ok ? 1 : 0; sel->ok1[warp] = ok1 ? 1 : 0;
+                                if (ok1) lean_publish(sel, warp, v, kPpf34 * dev);   // stats.rs:39-47
+                            }
                         }
                         __syncthreads();
                         ICP_LT_MARK(3)
-                        if (sel->ok[0] & sel->ok[1]) {
+                        if (sel->ok[0] & sel->ok[1] & sel->ok1[0] & sel->ok1[1]) {
+                            served = true;
+                            lean_zero_lh<THREADS>(sel->lh[0]);
+                        } else if (sel->ok[0] & sel->ok[1]) {
 // @region lean_stage1
                             const double m0 = sel->med[0], m1 = sel->med[1];
                             const float l0 = sel->lo1[0], l1 = sel->lo1[1], s0 = sel->sc1[0], s1 = sel->sc1[1];
@@ -535,7 +654,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                     if (!served) {
 // @region lean_general_selection
                         lean_general_selection<THREADS, PPT>(sel, r2v, n);
-                    } else {
+                    } else if (!(sel->ok1[0] & sel->ok1[1])) {
                         lean_zero_lh<THREADS>(sel->lh[1]);
                     }
 // @region lean_accumulate
