@@ -337,6 +337,7 @@ def run_gpu(args, rank, local_rank, world):
             cpu = cpu_baseline(icp, host[0], B)
         peak, peak_src = measured_peaks()
         achieved = BYTES_PER_PAIR * B / (launch_ms * 1e-3) / 1e9
+        fp64 = fp64_roofline(icp, ctx, host[0], B, launch_ms)
         tT = host[0]["true_T"]
         oT = host[0]["out"].numpy()
         line = {
@@ -357,7 +358,9 @@ def run_gpu(args, rank, local_rank, world):
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if args.ordered else profiled_traffic("icp_lean_kernel", B),
                          "peak_source": peak_src, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": BYTES_PER_PAIR * B,
-                         "note": "latency/FP64-chain bound by design (34.7 KB per pair, ~190 Gauss-Newton evaluations per pair); see DESIGN.md"},
+                         "fp64": fp64,
+                         "note": "latency/FP64-chain bound by design (34.7 KB per pair, ~180 Gauss-Newton evaluations per pair); "
+                                 "the FP64 pipe is the nearer ceiling (see fp64); see DESIGN.md"},
             "reduction_mode": "ordered sums (bit-exact transforms)" if args.ordered else "warp-tree reductions (default)",
             "ordered_sums_mode": other,
             "nn_search": nn,
@@ -444,6 +447,38 @@ def bench_config3(icp, ctx, scans_n=16384):
     return {"workload": f"config3: {scans_n} scans x {BEAMS} points vs one shared 100000-point map, {MAX_ITER} outer iterations",
             "value": scans_n / (best[1] * 1e-3), "unit": "pairs/s", "kernel_ms": best[1],
             "host_call_pairs_per_s": scans_n / best[0], "status_ok": bool((g["status"] == 0).all())}
+
+
+FP64_FLOPS_PER_POINT_EVAL = 80      # residual 10 + 2 rows x (weight, c, 3 jtr, 6 jtj products and sums)
+FP64_FLOPS_PER_POINT_STEP = 15      # huber_error per accepted step
+FP64_FLOPS_PER_POINT_OUTER = 8 + 6 * 6   # transform + ~6 exact candidate distances of the seeded search
+
+
+def fp64_roofline(icp, ctx, h, B, launch_ms, sample=256):
+    """Secondary roofline of the fused kernel: algorithmic FP64 flops against the FP64
+    rate measured on this pool's B200s for the reference's arithmetic (separate multiply and add, no
+    FMA: tools/fp64/fp64_peak.cu -> profiles/r01_fp64_peak.json).  Evaluations per pair are counted
+    from the inner-iteration table of an untimed call over the first `sample` pairs."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json")) as f:
+            pk = json.load(f)
+        n = min(B, sample)
+        off = (np.arange(n + 1, dtype=np.uint64) * BEAMS).astype(np.uint32)
+        g = ctx.estimate_batch(h["src"].numpy()[:n * BEAMS], off, h["dst"].numpy()[:n * BEAMS], off, h["T0"].numpy()[:n],
+                               MAX_ITER, want_inner=True, want_hash=False)
+        acc = (g["inner"] & 0xffff).astype(np.int64)
+        why = (g["inner"] >> 16).astype(np.int64)
+        evals = float((acc + (why != icp.BREAK_CAP)).sum(axis=1).mean())
+        steps = float(acc.sum(axis=1).mean())
+        flops_pair = BEAMS * (evals * FP64_FLOPS_PER_POINT_EVAL + steps * FP64_FLOPS_PER_POINT_STEP
+                              + MAX_ITER * FP64_FLOPS_PER_POINT_OUTER)
+        tf = flops_pair * B / (launch_ms * 1e-3) / 1e12
+        return {"achieved": tf, "peak": pk["fp64_dmul_dadd_tflops"], "unit": "TFLOP/s", "frac": tf / pk["fp64_dmul_dadd_tflops"],
+                "peak_source": "measured, separate DMUL+DADD (profiles/r01_fp64_peak.json; DFMA: %.1f)" % pk["fp64_dfma_tflops"],
+                "gn_evaluations_per_pair": evals, "algorithmic_flops_per_pair": flops_pair,
+                "note": "algorithmic flops exclude the exact selections, sqrt/div expansions and index work"}
+    except Exception as e:  # pragma: no cover
+        return {"error": repr(e)}
 
 
 def cpu_baseline(icp, h, B):

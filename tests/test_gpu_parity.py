@@ -401,3 +401,20 @@ def test_multi_hypothesis_front_end(ctx, icp, scans2d):
         costs.append(oracle.huber_error(o["T"], src, m))
     assert np.allclose(r["cost"], costs, rtol=1e-6)
     assert r["best"] == int(np.argmin(costs))
+
+
+def test_config3_queries_full_map(ctx, icp):
+    """BASELINE config 3 at full map size: 100k-point map, the queries 400 scans issue from their
+    perturbed poses (432k queries) + exact duplicates of map points; every index equals the oracle's
+    exact kd-tree (lowest index on ties), through the seeded disc search of icp_target_nn.cuh."""
+    m = icp.synth_map(100_000, seed=7)
+    scans, off, T0 = icp.synth_map_scans(400, beams=1080, seed=7)
+    q = np.concatenate([scans[off[b]:off[b + 1]] @ T0[b, :4].reshape(2, 2).T + T0[b, 4:6] for b in range(400)]
+                       + [m[::500], m[::333] + 1e-7])
+    t = icp.Target(m, ctx)
+    got = t.search(q)
+    t.close()
+    exp = oracle.nn_search(m, q, oracle.NN_KDTREE)
+    assert np.array_equal(got, exp)
+    brute = oracle.nn_search(m, q[:3000], oracle.NN_BRUTE)
+    assert np.array_equal(exp[:3000], brute)
