@@ -299,6 +299,7 @@ ICP_DEV bool lean_serve_mad(const uint16_t (*bucket)[kLeanCap], const double2* r
           (uint32_t)(nl - kLeanWinLo) < (uint32_t)kLeanWin && (uint32_t)(nh - kLeanWinLo) < (uint32_t)kLeanWin))
         return false;
     // ---- rank the points of those bins on their exact |r - med|
+    __syncwarp();   // list[] still holds the median's candidates: every lane has finished reading them
     double mine = 0.;
     if ((uint32_t)lane < count) {
         uint32_t o = (uint32_t)lane;
