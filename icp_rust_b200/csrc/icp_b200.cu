@@ -79,6 +79,7 @@ struct icp_b200_context {
     int cell_budget = 4096;
     int force_instance = -1;
     int use_lean = 1;       // ICP_B200_LEAN=0: warp-tree batches on the icp_fused.cuh schedule instead of icp_lean.cuh
+    int stream_cells_per_point = 8;   // ICP_B200_STREAM_CELLS_PER_POINT: cell budget of the streaming kernel's per-pair grids
     int force_stream = 0;   // ICP_B200_FORCE_STREAM=1: route every warp-tree batch to the streaming kernel (tests)
 };
 
@@ -175,7 +176,7 @@ int plan_launch(icp_b200_context* ctx, uint32_t dim, bool shared_target, bool or
         plan->stream = true;
         plan->n_cap = std::max<uint32_t>(8u, (max_n + 7u) & ~7u);
         plan->m_cap = shared_target ? 0u : std::max<uint32_t>(8u, (max_m + 7u) & ~7u);
-        plan->c_cap = shared_target ? 0u : std::max<uint32_t>(64u, 2u * plan->m_cap);
+        plan->c_cap = shared_target ? 0u : std::max<uint32_t>(64u, (uint32_t)ctx->stream_cells_per_point * plan->m_cap);
         plan->slayout = stream_layout((int)dim, plan->n_cap, plan->m_cap, plan->c_cap, shared_target);
         plan->ws_stride = plan->slayout.total;
         plan->skernel = kStreamInstance.k[dim - 2][shared_target ? 1 : 0];
@@ -241,6 +242,7 @@ int launch_range(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_
     if (plan.stream) {
         StreamParams sp{};
         sp.f = p; sp.n_cap = plan.n_cap; sp.m_cap = plan.m_cap; sp.c_cap = plan.c_cap;
+        sp.cells_per_point = (uint32_t)ctx->stream_cells_per_point;
         plan.skernel<<<grid, plan.threads, plan.smem, stream>>>(sp);
     } else {
         plan.kernel<<<grid, plan.threads, plan.smem, stream>>>(p);
@@ -495,6 +497,7 @@ int icp_b200_create(int device, icp_b200_context** out)
     }
     ctx->cell_budget = std::max(16, std::min(65000, env_int("ICP_B200_CELL_BUDGET", 4096)));
     ctx->force_instance = env_int("ICP_B200_FORCE_INSTANCE", -1);
+    ctx->stream_cells_per_point = std::max(1, std::min(256, env_int("ICP_B200_STREAM_CELLS_PER_POINT", 8)));
     ctx->force_stream = env_int("ICP_B200_FORCE_STREAM", 0);
     ctx->use_lean = env_int("ICP_B200_LEAN", 1);
     *out = ctx;

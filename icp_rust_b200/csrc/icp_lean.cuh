@@ -534,8 +534,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                     gv.idx = reinterpret_cast<const uint16_t*>(U + L.nn_idx);
                     gv.cstart = reinterpret_cast<const uint16_t*>(U + L.nn_cell);
                     gv.g = geom;
-                    const NnResult<DIM, uint16_t, uint16_t> r =
-                        seed >= 0 ? grid_nn_search_seeded(gv, q.x, q.y, pz, seed) : grid_nn_search(gv, q.x, q.y, pz);
+                    const NnResult<DIM, uint16_t, uint16_t> r = grid_nn_search_auto(gv, q.x, q.y, pz, seed);
                     d.x = gv.x[r.pos]; d.y = gv.y[r.pos];
                     idx = r.idx;
                     prev_pos[i] = (uint32_t)r.pos;

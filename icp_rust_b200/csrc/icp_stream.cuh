@@ -48,6 +48,7 @@ ICP_HD StreamLayout stream_layout(int dim, uint32_t n_cap, uint32_t m_cap, uint3
 struct StreamParams {
     FusedParams f;          // same batch description as the fused kernel (workspace/ws_stride = slabs)
     uint32_t n_cap, m_cap, c_cap;
+    uint32_t cells_per_point;   // cell budget of a pair's own grid = cells_per_point * m, at most c_cap (0: 2)
 };
 
 // residual keys recomputed from the streamed state (lib.rs:34-36)
@@ -200,7 +201,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, 1) icp_stream_kernel(StreamParams sp)
                         mx[d] = fmax(mx[d], ctl->red[w][3 + d]);
                     }
                 }
-                long long budget = 2ll * m;
+                long long budget = (long long)(sp.cells_per_point ? sp.cells_per_point : 2u) * m;
                 if (budget < 64) budget = 64;
                 if (budget > (long long)sp.c_cap) budget = (long long)sp.c_cap;
                 const GridGeom g = grid_make_geom(mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], DIM, (int)budget);
@@ -243,7 +244,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, 1) icp_stream_kernel(StreamParams sp)
                 const int seed = (it > 0) ? (int)spos[i] : -1;
                 const NnResult<DIM, uint32_t, uint32_t> r =
                     SHARED_TARGET ? target_nn_search<DIM>(p.target, s.x, s.y, pz, seed)
-                                  : (seed >= 0 ? grid_nn_search_seeded(gv, s.x, s.y, pz, seed) : grid_nn_search(gv, s.x, s.y, pz));
+                                  : grid_nn_search_auto(gv, s.x, s.y, pz, seed);
                 spos[i] = (uint32_t)r.pos;
                 double2 d;
                 d.x = gv.x[r.pos]; d.y = gv.y[r.pos];   // get_xy (lib.rs:86-89)

@@ -349,6 +349,24 @@ ICP_DEV NnResult<DIM, IdxT, CellT> grid_nn_search_seeded(const GridView<DIM, Idx
     return best;
 }
 
+// Search of a per-pair grid with whatever seed is at hand: the previous match (seed_pos >= 0), else
+// the first point of the query's own cell, else (empty cell) the ring search.
+template <int DIM, typename IdxT, typename CellT>
+ICP_DEV NnResult<DIM, IdxT, CellT> grid_nn_search_auto(const GridView<DIM, IdxT, CellT>& gv, double qx, double qy,
+                                                       double qz, int seed_pos)
+{
+    if (seed_pos < 0) {
+        const GridGeom& g = gv.g;
+        const int cx = grid_coord(qx, g.ox, g.inv_h, g.gx);
+        const int cy = grid_coord(qy, g.oy, g.inv_h, g.gy);
+        const int cz = (DIM == 3) ? grid_coord(qz, g.oz, g.inv_h, g.gz) : 0;
+        const int c = (cz * g.gy + cy) * g.gx + cx;
+        const int p0 = (int)gv.cstart[c], p1 = (int)gv.cstart[c + 1];
+        if (p1 > p0) seed_pos = p0;
+    }
+    return seed_pos >= 0 ? grid_nn_search_seeded(gv, qx, qy, qz, seed_pos) : grid_nn_search(gv, qx, qy, qz);
+}
+
 // seed_pos >= 0: a sorted position of the target (the previous outer iteration's match); -1: none
 template <int DIM>
 ICP_DEV NnResult<DIM, uint32_t, uint32_t> target_nn_search(const TargetView& tv, double qx, double qy, double qz,
