@@ -181,6 +181,60 @@ extern "C" int simt_target_search(int dim, const double* pts, uint32_t m, long l
     return 0;
 }
 
+// Seeded search of icp_target_nn.cuh (grid_nn_search_auto) on a sorted cell list built by the target
+// kernels, one emulated thread per query.  seeds[q]: ORIGINAL index of any target point, or -1
+// (own-cell seed / ring search).  2-D and 3-D.
+template <int DIM>
+static void seeded_kernel(GridView<DIM, uint32_t, uint32_t> gv, const double* queries, const int32_t* seed_pos,
+                          unsigned long long nq, int32_t* out_idx)
+{
+    for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq;
+         q += (unsigned long long)gridDim.x * blockDim.x) {
+        const double qz = DIM == 3 ? queries[q * DIM + 2] : 0.0;
+        const NnResult<DIM, uint32_t, uint32_t> r = grid_nn_search_auto(gv, queries[q * DIM], queries[q * DIM + 1], qz, seed_pos[q]);
+        out_idx[q] = r.idx;
+    }
+}
+
+extern "C" int simt_grid_seeded_search(int dim, const double* pts, uint32_t m, long long budget, const double* queries,
+                                       const int32_t* seeds, uint64_t nq, int32_t* out_idx)
+{
+    if (m == 0 || (dim != 2 && dim != 3)) return -1;
+    double mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+    for (int d = 0; d < dim; ++d) {
+        mn[d] = mx[d] = pts[d];
+        for (uint32_t j = 1; j < m; ++j) {
+            mn[d] = std::min(mn[d], pts[(size_t)j * dim + d]);
+            mx[d] = std::max(mx[d], pts[(size_t)j * dim + d]);
+        }
+    }
+    const GridGeom g = grid_make_geom(mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], dim, (int)budget);
+    const uint32_t ncells = (uint32_t)(g.gx * g.gy * g.gz);
+    std::vector<uint32_t> cnt(ncells, 0u), slot(m), cstart(ncells + 1), idx(m), where(m);
+    std::vector<double> x(m), y(m), z(m);
+    TargetBuild tb{};
+    tb.pts = pts; tb.m = m; tb.g = g; tb.cnt = cnt.data(); tb.slot = slot.data(); tb.cstart = cstart.data();
+    tb.x = x.data(); tb.y = y.data(); tb.z = z.data(); tb.idx = idx.data(); tb.pf = nullptr;
+    if (dim == 2) simt::launch(2, 256, 0, [&] { target_count_kernel<2>(tb); });
+    else simt::launch(2, 256, 0, [&] { target_count_kernel<3>(tb); });
+    simt::launch(1, 1024, 128, [&] { target_scan_kernel(tb, ncells); });
+    if (dim == 2) simt::launch(2, 256, 0, [&] { target_scatter_kernel<2>(tb); });
+    else simt::launch(2, 256, 0, [&] { target_scatter_kernel<3>(tb); });
+    for (uint32_t p = 0; p < m; ++p) where[idx[p]] = p;   // original index -> sorted position
+    std::vector<int32_t> seed_pos(nq);
+    for (uint64_t q = 0; q < nq; ++q) seed_pos[q] = seeds[q] < 0 ? -1 : (int32_t)where[(uint32_t)seeds[q] % m];
+    if (dim == 2) {
+        GridView<2, uint32_t, uint32_t> gv;
+        gv.x = x.data(); gv.y = y.data(); gv.z = z.data(); gv.idx = idx.data(); gv.cstart = cstart.data(); gv.g = g;
+        simt::launch(2, 128, 0, [&] { seeded_kernel<2>(gv, queries, seed_pos.data(), nq, out_idx); });
+    } else {
+        GridView<3, uint32_t, uint32_t> gv;
+        gv.x = x.data(); gv.y = y.data(); gv.z = z.data(); gv.idx = idx.data(); gv.cstart = cstart.data(); gv.g = g;
+        simt::launch(2, 128, 0, [&] { seeded_kernel<3>(gv, queries, seed_pos.data(), nq, out_idx); });
+    }
+    return 0;
+}
+
 extern "C" void simt_nn_counters(unsigned long long* out6, int reset)
 {
     NnCounters& c = nn_counters();

@@ -112,3 +112,18 @@ def nn_counters(reset=True):
     out = (C.c_ulonglong * 8)()
     lib().simt_nn_counters(out, C.c_int(1 if reset else 0))
     return dict(zip(("queries", "rows", "spans", "candidates", "pass2_queries", "exact_evals", "prescan"), [int(v) for v in out]))
+
+
+def grid_seeded_search(dst, queries, seeds, budget):
+    """grid_nn_search_auto (icp_target_nn.cuh) on a cell list built by the target kernels.
+    seeds: original index of any target point per query, or -1."""
+    d = np.ascontiguousarray(dst, dtype=np.float64)
+    q = np.ascontiguousarray(queries, dtype=np.float64)
+    s = np.ascontiguousarray(seeds, dtype=np.int32)
+    out = np.full(q.shape[0], -1, dtype=np.int32)
+    rc = lib().simt_grid_seeded_search(C.c_int(d.shape[1]), d.ctypes.data_as(_dp), C.c_uint32(d.shape[0]),
+                                       C.c_longlong(int(budget)), q.ctypes.data_as(_dp),
+                                       s.ctypes.data_as(C.POINTER(C.c_int32)), C.c_uint64(q.shape[0]),
+                                       out.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == 0
+    return out

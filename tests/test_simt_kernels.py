@@ -251,3 +251,58 @@ def test_target_search_fast_path_odd_geometries():
         exp = oracle.nn_search(d, q, oracle.NN_BRUTE)
         for cpp in (4, 64):
             assert np.array_equal(E.target_search(d, q, budget=max(64, len(d) * cpp), fast=True), exp)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_seeded_disc_walk_is_exact_for_any_seed(dim):
+    """grid_nn_search_seeded / _auto: whatever point seeds the disc (the true neighbour, a far point,
+    none), whatever the cell size, scale and offset of the cloud, the result is the brute-force one."""
+    rng = np.random.default_rng(100 + dim)
+    for trial in range(14):
+        m = int(rng.integers(1, 1500))
+        scale = 10.0 ** rng.uniform(-6, 6)
+        offset = rng.normal(0, 1, dim) * scale * 10.0 ** rng.uniform(-1, 3)
+        aniso = 10.0 ** rng.uniform(-2, 0, dim)
+        kind = trial % 4
+        if kind == 0:
+            d = rng.normal(0, 1, (m, dim))
+        elif kind == 1:                                   # points on a curve (scan-like), dense
+            t = np.sort(rng.uniform(0, 6.28, m))
+            d = np.stack([np.cos(t), np.sin(2 * t)] + ([0.1 * np.sin(5 * t)] if dim == 3 else []), axis=1)
+            d += rng.normal(0, 1e-3, d.shape)
+        elif kind == 2:                                   # lattice: exact ties
+            side = int(np.ceil(m ** (1.0 / dim)))
+            d = np.stack(np.meshgrid(*[np.arange(float(side))] * dim), -1).reshape(-1, dim)[:m]
+        else:                                             # clusters with duplicates
+            d = rng.normal(0, 1, (m, dim))
+            d[rng.integers(0, m, m // 3)] = d[rng.integers(0, m, 1)]
+        d = d * aniso * scale + offset
+        m = len(d)
+        span = np.ptp(d, axis=0).max() + scale
+        q = np.concatenate([d[rng.integers(0, m, 120)] + rng.normal(0, span * 1e-3, (120, dim)),
+                            d[rng.integers(0, m, 40)],
+                            d.mean(0) + rng.normal(0, span, (60, dim)),
+                            d[rng.integers(0, m, 30)] + ([0.5] * dim if kind == 2 else [0.0] * dim) * np.array(aniso) * scale])
+        exp = oracle.nn_search(d, q, oracle.NN_BRUTE)
+        seeds = np.concatenate([exp[:60], rng.integers(0, m, 130), np.full(len(q) - 190, -1)])
+        budget = int(max(8, m * 10.0 ** rng.uniform(-1, 1.5)))
+        got = E.grid_seeded_search(d, q, seeds, min(budget, 1 << 20))
+        assert np.array_equal(got, exp), f"trial {trial} dim {dim} m {m} budget {budget}"
+
+
+def test_target_search_random_geometries():
+    """Seeded disc + binary32 filter on shared 2-D targets across scales, offsets and cell sizes."""
+    rng = np.random.default_rng(77)
+    for trial in range(10):
+        m = int(rng.integers(2, 3000))
+        scale = 10.0 ** rng.uniform(-5, 7)
+        offset = rng.normal(0, 1, 2) * scale * 10.0 ** rng.uniform(-1, 4)
+        t = np.sort(rng.uniform(0, 6.28, m))
+        d = np.stack([np.cos(t) * (1 + 0.3 * np.sin(7 * t)), np.sin(t)], axis=1) + rng.normal(0, 10.0 ** rng.uniform(-6, -2), (m, 2))
+        d[rng.integers(0, m, m // 10)] = d[rng.integers(0, m, 1)]
+        d = d * scale + offset
+        q = np.concatenate([d[rng.integers(0, m, 150)] * (1 + rng.normal(0, 1e-3, (150, 1))), d[rng.integers(0, m, 50)],
+                            d.mean(0) + rng.normal(0, 3 * scale, (80, 2))])
+        exp = oracle.nn_search(d, q, oracle.NN_BRUTE)
+        cpp = float(10.0 ** rng.uniform(0, 2))
+        assert np.array_equal(E.target_search(d, q, budget=max(64, int(m * cpp)), fast=True), exp), f"trial {trial}"
