@@ -212,9 +212,17 @@ ICP_DEV void nn_walk(const TargetView& tv, const NnQuery& Q, Visit&& visit)
                 if (!nn_row_span(Q, yy, gx, &xa, &xb)) { ++yy; continue; }
                 ICP_NN_COUNT(rows, 1);
                 row = yy * gx;
-                if (tv.cstart[row + xa] == tv.cstart[row + xb + 1]) { ++yy; continue; }   // nothing in the whole span
+                const int r0 = (int)tv.cstart[row + xa], r1 = (int)tv.cstart[row + xb + 1];
+                if (r0 == r1) { ++yy; continue; }   // nothing in the whole span
                 qry = nn_block_offset(Q.ty, yy);
                 xs = xa;
+                if ((xa >> kNnBlockShift) == (xb >> kNnBlockShift)) {   // one block: the span is the segment
+                    p0 = r0; p1 = r1;
+                    qrx = nn_block_offset(Q.tx, xa);
+                    ICP_NN_COUNT(spans, 1);
+                    ++yy;
+                    break;
+                }
                 have_row = true;
             }
             const int xe_blk = xs | (kNnBlockCells - 1);
