@@ -335,6 +335,7 @@ def run_gpu(args, rank, local_rank, world):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(icp, host[0], B)
+            cpu["single_pair_latency"] = single_pair_latency(icp, ctx)
         peak, peak_src = measured_peaks()
         achieved = BYTES_PER_PAIR * B / (launch_ms * 1e-3) / 1e9
         fp64 = fp64_roofline(icp, ctx, host[0], B, launch_ms)
@@ -477,6 +478,34 @@ def fp64_roofline(icp, ctx, h, B, launch_ms, sample=256):
                 "peak_source": "measured, separate DMUL+DADD (profiles/r01_fp64_peak.json; DFMA: %.1f)" % pk["fp64_dfma_tflops"],
                 "gn_evaluations_per_pair": evals, "algorithmic_flops_per_pair": flops_pair,
                 "note": "algorithmic flops exclude the exact selections, sqrt/div expansions and index work"}
+    except Exception as e:  # pragma: no cover
+        return {"error": repr(e)}
+
+
+def single_pair_latency(icp, ctx, reps=20):
+    """Latency of ONE reference call, Icp2d::new(dst).estimate(src, identity, 20) on a bundled scan pair
+    (tests/golden/scans2d.npz: 001 -> 002): the oracle on one host thread against the
+    single-pair entry of the C ABI (host buffers, ordered sums).  The device path is a throughput
+    design; this is the honest other end of it."""
+    try:
+        import oracle
+        z = np.load(os.path.join(ROOT, "tests", "golden", "scans2d.npz"))
+        pts, off = z["points"], z["offsets"]
+        src, dst = pts[off[1]:off[2]].copy(), pts[off[2]:off[3]].copy()
+        I = icp.Transform.identity()
+        t = time.perf_counter()
+        for _ in range(reps):
+            o = oracle.icp_estimate(src, dst, None, MAX_ITER, nn_mode=oracle.NN_KDTREE)
+        cpu_ms = (time.perf_counter() - t) / reps * 1e3
+        est = icp.Icp2d.new(dst, ctx)
+        est.estimate(src, I, MAX_ITER)
+        t = time.perf_counter()
+        for _ in range(reps):
+            T = est.estimate(src, I, MAX_ITER)
+        gpu_ms = (time.perf_counter() - t) / reps * 1e3
+        return {"pair": "bundled 2-D scans 001 -> 002 (%d / %d points), 20 iterations" % (len(src), len(dst)),
+                "cpu_oracle_ms": cpu_ms, "c_abi_single_pair_ms": gpu_ms,
+                "bit_identical": bool(np.array_equal(T.to_array(), o["T"]))}
     except Exception as e:  # pragma: no cover
         return {"error": repr(e)}
 
