@@ -1,5 +1,6 @@
-// icp_target_nn.cuh — correspondence search on a large shared target (the `Icp2d<'a>` value kept on
-// the device, src/lib.rs:91-102; KdTree::search per query, src/lib.rs:121).
+// icp_target_nn.cuh — seeded correspondence search: on a large shared target (the `Icp2d<'a>` value
+// kept on the device, src/lib.rs:91-102; KdTree::search per query, src/lib.rs:121) and, seeded with
+// the previous outer iteration's match, on per-pair grids (grid_nn_search_seeded, end of file).
 //
 // Contract (identical to icp_grid.cuh and the oracle's brute force): exact Euclidean 1-NN on the
 // COMPUTED d2 = dx*dx + dy*dy (binary64, dx = q.x - p.x, no FMA), lowest original index on equal d2.
@@ -24,7 +25,8 @@
 // One thread per query, in nn_search_kernel and in the fused kernels alike.  A warp-collective form
 // that pooled the candidates of 32 queries in shared memory (chunks of 8, folded into their owners'
 // slots with shared-memory atomics) ran the candidate loop at 30 of 32 lanes but lost more in list
-// upkeep than it won: 4.7 against 5.5 G queries/s on B200 (profiles/r01_nn_sweep.md); removed.
+// upkeep than it won: 4.7 against 5.5 G queries/s on B200 (profiles/r01_nn_pooled_variant.jsonl,
+// profiles/r01_ncu_full_summary.md); removed.
 #pragma once
 #include "icp_grid.cuh"
 
@@ -78,7 +80,7 @@ ICP_DEV int nn_floor_clamp(float v, int hi)
 
 #ifdef ICP_SIMT_EMULATE
 // emulator-only work counters (tests/simt): queries, rows, spans, candidates of pass 1, pass-2 queries
-struct NnCounters { unsigned long long q, rows, spans, cand, pass2, exact, pre; };
+struct NnCounters { unsigned long long q, rows, spans, cand, pass2, exact; };
 inline NnCounters& nn_counters() { static NnCounters c{}; return c; }
 #define ICP_NN_COUNT(field, v) (nn_counters().field += (v))
 #else

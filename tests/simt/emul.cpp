@@ -238,7 +238,7 @@ extern "C" int simt_grid_seeded_search(int dim, const double* pts, uint32_t m, l
 extern "C" void simt_nn_counters(unsigned long long* out6, int reset)
 {
     NnCounters& c = nn_counters();
-    out6[0] = c.q; out6[1] = c.rows; out6[2] = c.spans; out6[3] = c.cand; out6[4] = c.pass2; out6[5] = c.exact; out6[6] = c.pre;
+    out6[0] = c.q; out6[1] = c.rows; out6[2] = c.spans; out6[3] = c.cand; out6[4] = c.pass2; out6[5] = c.exact;
     if (reset) c = NnCounters{};
 }
 

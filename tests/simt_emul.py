@@ -111,7 +111,7 @@ def nn_counters(reset=True):
     """Work counters of the fast shared-target search since the last reset (emulator only)."""
     out = (C.c_ulonglong * 8)()
     lib().simt_nn_counters(out, C.c_int(1 if reset else 0))
-    return dict(zip(("queries", "rows", "spans", "candidates", "pass2_queries", "exact_evals", "prescan"), [int(v) for v in out]))
+    return dict(zip(("queries", "rows", "spans", "candidates", "pass2_queries", "exact_evals"), [int(v) for v in out]))
 
 
 def grid_seeded_search(dst, queries, seeds, budget):
