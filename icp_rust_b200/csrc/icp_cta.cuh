@@ -107,7 +107,7 @@ struct SelShared {
     // (at most 65535 keys per axis, so the halves never carry into each other)
     uint32_t hist[2][kSelHistPad];
     uint32_t lcnt[2];
-    double list[2][kSelCap];
+    alignas(16) double list[2][kSelCap];   // 16-byte aligned: the service warps read keys in pairs
     SelDecision dec[2];          // written by the axis' service warp, read by every thread
     double out_lo[2], out_hi[2];
 };

@@ -126,6 +126,24 @@ ICP_DEV void lean_find_rank(const uint32_t c[8], uint32_t incl, uint32_t tot, ui
     *count = __shfl_sync(ICP_FULL_MASK, bc, owner);
 }
 
+// Rank of `mine` among list[0..count): keys below it and keys not above it.  Keys are read two at a
+// time; the writer pads an odd count with +inf (ranks of finite keys are unaffected).
+ICP_DEV void lean_rank(const double* list, uint32_t count, double mine, uint32_t* nlt, uint32_t* nle)
+{
+    const double2* l2 = reinterpret_cast<const double2*>(list);
+    uint32_t a = 0, b = 0;
+    for (uint32_t m = 0; m < count; m += 2) {
+        const double2 o = l2[m >> 1];
+        a += ((o.x < mine) ? 1u : 0u) + ((o.y < mine) ? 1u : 0u);
+        b += ((o.x <= mine) ? 1u : 0u) + ((o.y <= mine) ? 1u : 0u);
+    }
+    *nlt = a; *nle = b;
+}
+ICP_DEV void lean_pad_list(double* list, uint32_t count, int lane)
+{
+    if ((uint32_t)lane == count && (count & 1u) && count < (uint32_t)kSelCap) list[count] = 1.0 / 0.0;
+}
+
 // One warp serves one axis of one selection stage: returns true and the exact median of the
 // axis' keys (stats.rs:11-28: (b + c) / 2 for even n), or false when the short path cannot
 // decide (caller falls back to block_median2).  Keys: stage 0 r[i].axis, stage 1
@@ -194,6 +212,7 @@ ICP_DEV bool lean_serve(const uint32_t* h, const uint16_t (*bucket)[kLeanCap], c
             mine = sel_key(axis ? rr.y : rr.x, absdev, centre);
             list[lane] = mine;
         }
+        lean_pad_list(list, count, lane);
         __syncwarp();
     } else {
         uint32_t cnt = 0;
@@ -212,16 +231,13 @@ ICP_DEV bool lean_serve(const uint32_t* h, const uint16_t (*bucket)[kLeanCap], c
                 cnt += (uint32_t)__popc(m);
             }
         }
+        lean_pad_list(list, count, lane);
         __syncwarp();
         if ((uint32_t)lane < count) mine = list[lane];
     }
     // ---- rank: lt = keys below mine, le = keys not above; the key of rank r satisfies lt <= r < le
     uint32_t nlt = 0, nle = 0;
-    for (uint32_t m = 0; m < count; ++m) {
-        const double o = list[m];
-        nlt += (o < mine) ? 1u : 0u;
-        nle += (o <= mine) ? 1u : 0u;
-    }
+    lean_rank(list, count, mine, &nlt, &nle);
     const uint32_t kp = k - below;
     const bool have = (uint32_t)lane < count;
     const uint32_t vote0 = __ballot_sync(ICP_FULL_MASK, have && nlt <= kp && kp < nle);
@@ -310,13 +326,10 @@ ICP_DEV bool lean_serve_mad(const uint16_t (*bucket)[kLeanCap], const double2* r
         mine = sel_key(axis ? rr.y : rr.x, 1, med);
         list[lane] = mine;
     }
+    lean_pad_list(list, count, lane);
     __syncwarp();
     uint32_t nlt = 0, nle = 0;
-    for (uint32_t m = 0; m < count; ++m) {
-        const double o = list[m];
-        nlt += (o < mine) ? 1u : 0u;
-        nle += (o <= mine) ? 1u : 0u;
-    }
+    lean_rank(list, count, mine, &nlt, &nle);
     const uint32_t kp = k - inside;
     const bool have = (uint32_t)lane < count;
     const uint32_t vote0 = __ballot_sync(ICP_FULL_MASK, have && nlt <= kp && kp < nle);
