@@ -578,6 +578,9 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
         const int npad = ((n + 2 * kChainUnroll - 1) / (2 * kChainUnroll)) * (2 * kChainUnroll);
         const uint64_t corr_base = (uint64_t)p.src_off[pair] * (p.corr_mode == 2 ? p.max_iter : 1u);
 
+        int ppos[PPT];   // sorted position of each point's match in the previous outer iteration (ordered mode)
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) ppos[k] = -1;
         for (uint32_t it = 0; it < p.max_iter; ++it) {
             // ---- stage the sorted target (the union region was overwritten by the IRLS rows)
             if (ORDERED && !SHARED_TARGET && it > 0 && m > 0) {
@@ -589,13 +592,16 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
             // ---- transform (lib.rs:113-116) + correspondence search (lib.rs:118-124)
             double sx[PPT], sy[PPT], dx[PPT], dy[PPT];
             uint64_t hpart = 0;
-            auto search_one = [&](int i, double qx, double qy, double* ox, double* oy) {
+            // *pos: in, the sorted position of the point's previous match (-1: none) — the seed of
+            // the search (icp_target_nn.cuh); out, the position of this iteration's match
+            auto search_one = [&](int i, double qx, double qy, double* ox, double* oy, int* pos) {
                 const double pz = (DIM == 3) ? src[(size_t)i * DIM + 2] : 0.0;  // transform_xy keeps z (lib.rs:52-57)
                 int idx;
                 if (SHARED_TARGET) {
-                    const NnResult<DIM, uint32_t, uint32_t> r = target_nn_search<DIM>(p.target, qx, qy, pz);
+                    const NnResult<DIM, uint32_t, uint32_t> r = target_nn_search<DIM>(p.target, qx, qy, pz, *pos);
                     *ox = p.target.x[r.pos]; *oy = p.target.y[r.pos];
                     idx = r.idx;
+                    *pos = r.pos;
                 } else {
                     GridView<DIM, uint16_t, uint16_t> gv;
                     gv.x = reinterpret_cast<const double*>(U + L.nn_x);
@@ -604,9 +610,10 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                     gv.idx = reinterpret_cast<const uint16_t*>(U + L.nn_idx);
                     gv.cstart = reinterpret_cast<const uint16_t*>(U + L.nn_cell);
                     gv.g = geom;
-                    NnResult<DIM, uint16_t, uint16_t> r = grid_nn_search(gv, qx, qy, pz);
+                    NnResult<DIM, uint16_t, uint16_t> r = grid_nn_search_auto(gv, qx, qy, pz, *pos);
                     *ox = gv.x[r.pos]; *oy = gv.y[r.pos];
                     idx = r.idx;
+                    *pos = r.pos;
                 }
                 hpart += mix64(((uint64_t)(uint32_t)i << 32) | (uint64_t)(uint32_t)idx);
                 if (p.out_corr) {
@@ -621,7 +628,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                     sx[k] = 0.; sy[k] = 0.; dx[k] = 0.; dy[k] = 0.;
                     if (i < n) {
                         transform_apply(T, src[(size_t)i * DIM + 0], src[(size_t)i * DIM + 1], &sx[k], &sy[k]);
-                        search_one(i, sx[k], sy[k], &dx[k], &dy[k]);
+                        search_one(i, sx[k], sy[k], &dx[k], &dy[k], &ppos[k]);
                     }
                 }
             } else {
@@ -642,7 +649,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                 for (int i = tid; i < n; i += THREADS) {
                     const double2 q = r2v[i];
                     double2 d;
-                    search_one(i, q.x, q.y, &d.x, &d.y);
+                    int none = -1;
+                    search_one(i, q.x, q.y, &d.x, &d.y, &none);
                     r2v[i] = d;
                 }
 #pragma unroll
