@@ -494,7 +494,6 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
     unsigned char* U = smem;
     SelShared* sel = reinterpret_cast<SelShared*>(smem + L.off_sel);
     FusedCtl* ctl = reinterpret_cast<FusedCtl*>(smem + L.off_ctl);
-    double* r2 = reinterpret_cast<double*>(U + L.gn_r);
     double* rho = reinterpret_cast<double*>(U + L.gn_rho);
     double2* r2v = reinterpret_cast<double2*>(U + L.gn_r);
     double2* c2v = reinterpret_cast<double2*>(U + L.gn_c);
