@@ -327,32 +327,64 @@ ICP_DEV NnResult<DIM, IdxT, CellT> grid_nn_search_seeded(const GridView<DIM, Idx
     const float Uc = sqrtf(Q.Uc2) * 1.000001f;
     Q.sx = (fabsf(Q.txf) + 1.0f) * 3.6e-7f;
     Q.sy = (fabsf(Q.tyf) + 1.0f) * 3.6e-7f;
-    if (DIM == 2) {
+    if (DIM == 2) {   // one to three rows: plain loops are the cheapest
         const int ya = nn_floor_clamp(Q.tyf - Uc - Q.sy, g.gy - 1);     // bound (rows)
-        const int yb = nn_floor_clamp(Q.tyf + Uc + Q.sy, g.gy - 1);
-        for (int yy = ya; yy <= yb; ++yy) {
+        const int yb2 = nn_floor_clamp(Q.tyf + Uc + Q.sy, g.gy - 1);
+        for (int y2 = ya; y2 <= yb2; ++y2) {
             int xa, xb;
-            if (!nn_row_span(Q, yy, g.gx, &xa, &xb)) continue;          // bound (columns)
-            grid_scan_cells(gv, yy * g.gx, xa, xb, qx, qy, qz, best);
+            if (!nn_row_span(Q, y2, g.gx, &xa, &xb)) continue;          // bound (columns)
+            grid_scan_cells(gv, y2 * g.gx, xa, xb, qx, qy, qz, best);
         }
-    } else {
-        const float sz = (fabsf(tzf) + 1.0f) * 3.6e-7f;
-        const int za = nn_floor_clamp(tzf - Uc - sz, g.gz - 1);
-        const int zb = nn_floor_clamp(tzf + Uc + sz, g.gz - 1);
-        const float Uc2 = Q.Uc2;
-        for (int zz = za; zz <= zb; ++zz) {
-            const float zf = (float)zz;
-            const float zdc = fmaxf(fmaxf(zf - tzf, tzf - (zf + 1.0f)) - sz, 0.0f) * 0.999999f;
-            const float rem2 = Uc2 - zdc * zdc;
-            if (rem2 < 0.0f) continue;
-            const float ry = sqrtf(rem2) * 1.000001f + Q.sy;
-            const int ya = nn_floor_clamp(Q.tyf - ry, g.gy - 1);
-            const int yb = nn_floor_clamp(Q.tyf + ry, g.gy - 1);
-            Q.Uc2 = rem2;   // nn_row_span then tests wc^2 + ydc^2 against Uc2 - zdc^2
-            for (int yy = ya; yy <= yb; ++yy) {
-                int xa, xb;
-                if (!nn_row_span(Q, yy, g.gx, &xa, &xb)) continue;
-                grid_scan_cells(gv, (zz * g.gy + yy) * g.gx, xa, xb, qx, qy, qz, best);
+        return best;
+    }
+    // 3-D walk shaped like nn_walk: each trip advances to the next non-empty span (slab zz, row yy),
+    // then scans its candidates, so that the lanes of a warp run their candidate loops together.
+    const float sz = (DIM == 3) ? (fabsf(tzf) + 1.0f) * 3.6e-7f : 0.0f;
+    const float Uc2 = Q.Uc2;
+    int zz = 0, zb = 0;
+    if (DIM == 3) {
+        zz = nn_floor_clamp(tzf - Uc - sz, g.gz - 1);                   // bound (slabs)
+        zb = nn_floor_clamp(tzf + Uc + sz, g.gz - 1);
+    }
+    int yy = 1, yb = 0;          // rows of the current slab still to visit
+    bool slab_open = false;
+    for (;;) {
+        int p0 = 0, p1 = 0;
+        while (p1 == p0 && zz <= zb) {
+            if (!slab_open) {
+                float rem2 = Uc2, ry = Uc;
+                if (DIM == 3) {
+                    const float zf = (float)zz;
+                    const float zdc = fmaxf(fmaxf(zf - tzf, tzf - (zf + 1.0f)) - sz, 0.0f) * 0.999999f;
+                    rem2 = Uc2 - zdc * zdc;
+                    if (rem2 < 0.0f) { ++zz; continue; }
+                    ry = sqrtf(rem2) * 1.000001f;
+                }
+                Q.Uc2 = rem2;    // nn_row_span tests wc^2 + ydc^2 against Uc2 - zdc^2
+                yy = nn_floor_clamp(Q.tyf - ry - Q.sy, g.gy - 1);       // bound (rows)
+                yb = nn_floor_clamp(Q.tyf + ry + Q.sy, g.gy - 1);
+                slab_open = true;
+            }
+            if (yy > yb) { slab_open = false; ++zz; continue; }
+            int xa, xb;
+            if (nn_row_span(Q, yy, g.gx, &xa, &xb)) {                    // bound (columns)
+                const int base = (zz * g.gy + yy) * g.gx;
+                p0 = (int)gv.cstart[base + xa];
+                p1 = (int)gv.cstart[base + xb + 1];
+            }
+            ++yy;
+        }
+        if (p1 == p0) break;
+        for (int p = p0; p < p1; ++p) {
+            const double dx = qx - gv.x[p], dy = qy - gv.y[p];
+            double d2 = dx * dx + dy * dy;
+            if (DIM == 3) {
+                const double dz = qz - gv.z[p];
+                d2 = d2 + dz * dz;
+            }
+            if (d2 <= best.d2) {
+                const int id = (int)gv.idx[p];
+                if (d2 < best.d2 || id < best.idx) { best.d2 = d2; best.idx = id; best.pos = p; }
             }
         }
     }
