@@ -28,3 +28,17 @@ for rep in range(3):
     info = ctx.call_info()
     print(f"config4 shape: {B} pairs x 16384 pts: wall {dt*1e3:.1f} ms, kernel {info['kernel_ms']:.1f} ms -> {B/(info['kernel_ms']*1e-3):.0f} pairs/s (kernel), {B*16384*20/(info['kernel_ms']*1e-3)/1e9:.2f} G NN queries/s incl. solve; grid {info['grid_ctas']}x{info['block_threads']}")
 print("accepted per outer iteration:", (g["inner"] & 0xffff).mean(), "status ok:", (g["status"] == 0).all())
+
+# CPU oracle on the first pairs of the same batch (exact kd-tree, one pair per host thread): parity at
+# this size and a baseline for the shape
+import oracle
+nchk = min(B, os.cpu_count() or 1)
+oo = (np.arange(nchk + 1, dtype=np.uint64) * 16384).astype(np.uint32)
+t = time.time()
+o = oracle.icp_estimate_batch(3, src[:nchk * 16384], oo, dst[:nchk * 16384], oo, np.array(T0)[:nchk], 20,
+                              nn_mode=oracle.NN_KDTREE, nthreads=nchk)
+dt = time.time() - t
+print(f"oracle: {nchk} pairs on {nchk} host threads in {dt:.2f} s -> {nchk / dt:.1f} pairs/s; "
+      f"max |T_gpu - T_oracle| = {np.abs(o['T'] - g['T'][:nchk]).max():.3e}; "
+      f"inner counts equal: {bool(np.array_equal(o['inner'], g['inner'][:nchk]))}; "
+      f"correspondence hashes equal: {bool(np.array_equal(o['corr_hash'], g['corr_hash'][:nchk]))}")
