@@ -288,7 +288,8 @@ def nn_search(dst, queries, mode=NN_BRUTE):
 class _Trace(C.Structure):
     _fields_ = [("nn_mode", C.c_int), ("corr_mode", C.c_int),
                 ("corr", C.POINTER(C.c_int32)), ("inner", C.POINTER(C.c_uint32)),
-                ("corr_hash", C.POINTER(C.c_uint64))]
+                ("corr_hash", C.POINTER(C.c_uint64)), ("shared_tree", C.c_void_p),
+                ("final_cost", C.POINTER(C.c_double)), ("margins", C.POINTER(C.c_double))]
 
 
 def icp_estimate(src, dst, init_T=None, max_iter=20, nn_mode=NN_BRUTE, corr_mode=CORR_NONE):
@@ -305,14 +306,15 @@ def icp_estimate(src, dst, init_T=None, max_iter=20, nn_mode=NN_BRUTE, corr_mode
     ncorr = n * max_iter if corr_mode == CORR_ALL else n
     corr = np.full(max(ncorr, 1), -1, dtype=np.int32)
     h = C.c_uint64(0)
+    cost = C.c_double(0.)
     tr = _Trace(nn_mode, corr_mode, corr.ctypes.data_as(C.POINTER(C.c_int32)),
-                inner.ctypes.data_as(C.POINTER(C.c_uint32)), C.pointer(h))
+                inner.ctypes.data_as(C.POINTER(C.c_uint32)), C.pointer(h), None, C.pointer(cost), None)
     fn = lib().orc_icp2d_estimate if dim == 2 else lib().orc_icp3d_estimate
     st = fn(ps, C.c_size_t(n), pd, C.c_size_t(m), T0.ctypes.data_as(_dp), C.c_uint32(max_iter),
             out.ctypes.data_as(_dp), C.byref(tr))
     inner = inner[:max_iter]
     res = {"T": out, "status": st, "accepted": inner & 0xFFFF, "reason": inner >> 16,
-           "inner": inner, "corr_hash": h.value}
+           "inner": inner, "corr_hash": h.value, "cost": cost.value}
     if corr_mode == CORR_ALL:
         res["corr"] = corr[:ncorr].reshape(max_iter, n)
     elif corr_mode == CORR_LAST:
@@ -321,25 +323,42 @@ def icp_estimate(src, dst, init_T=None, max_iter=20, nn_mode=NN_BRUTE, corr_mode
 
 
 def icp_estimate_batch(dim, src, src_off, dst, dst_off, init_T, max_iter=20, nn_mode=NN_KDTREE,
-                       nthreads=None):
-    """Ragged batch over pthreads; returns dict(T, inner, corr_hash, status, threads)."""
+                       nthreads=None, want_cost=False, want_margins=False):
+    """Ragged batch over pthreads; returns dict(T, inner, corr_hash, status, threads).
+    dst_off=None: every pair is estimated against the one shared target `dst` (kd-tree built once,
+    as Icp2d::new(&dst) followed by many estimate calls).  want_cost: huber_error of the last inner
+    solve (see orc_trace.final_cost).  want_margins: (B,2) smallest relative distance of a
+    delta-norm / error break test from its threshold."""
     s, ps = _d(np.asarray(src).reshape(-1))
     d, pd = _d(np.asarray(dst).reshape(-1))
     so, pso = _u32(src_off)
-    do, pdo = _u32(dst_off)
     B = so.size - 1
+    if dst_off is None:
+        pdo, shared_m = None, d.size // dim
+    else:
+        do, pdo = _u32(dst_off)
+        shared_m = 0
     T0, pT0 = _d(np.asarray(init_T).reshape(-1))
     assert T0.size == 6 * B
     out = np.zeros((B, 6))
     inner = np.zeros((B, max_iter), dtype=np.uint32)
     hashes = np.zeros(B, dtype=np.uint64)
     status = np.zeros(B, dtype=np.int32)
+    cost = np.zeros(B) if want_cost else None
+    margins = np.zeros((B, 2)) if want_margins else None
     if nthreads is None:
         nthreads = os.cpu_count() or 1
-    used = lib().orc_icp_estimate_batch(
-        C.c_int(dim), ps, pso, pd, pdo, pT0, C.c_uint32(B), C.c_uint32(max_iter),
+    used = lib().orc_icp_estimate_batch_ex(
+        C.c_int(dim), ps, pso, pd, pdo, C.c_size_t(shared_m), pT0, C.c_uint32(B), C.c_uint32(max_iter),
         C.c_int(nn_mode), C.c_int(nthreads), out.ctypes.data_as(_dp),
         inner.ctypes.data_as(C.POINTER(C.c_uint32)),
         hashes.ctypes.data_as(C.POINTER(C.c_uint64)),
-        status.ctypes.data_as(C.POINTER(C.c_int32)))
-    return {"T": out, "inner": inner, "corr_hash": hashes, "status": status, "threads": used}
+        status.ctypes.data_as(C.POINTER(C.c_int32)),
+        cost.ctypes.data_as(_dp) if cost is not None else None,
+        margins.ctypes.data_as(_dp) if margins is not None else None)
+    res = {"T": out, "inner": inner, "corr_hash": hashes, "status": status, "threads": used}
+    if cost is not None:
+        res["cost"] = cost
+    if margins is not None:
+        res["margins"] = margins
+    return res

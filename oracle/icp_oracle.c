@@ -642,8 +642,11 @@ int orc_weighted_gauss_newton_update(const double T[6], const double *src, const
 }
 
 /* src/lib.rs:59-84 */
-void orc_estimate_transform(const double *src, const double *dst, size_t n, double T[6],
-                            uint32_t *accepted, uint32_t *reason)
+/* margins (nullable, test diagnostics only): [0] = smallest |delta.delta - 1e-6| / 1e-6 and
+ * [1] = smallest |error - prev_error| / max(error, prev_error) over the decisions taken; the
+ * caller initialises both to +inf.  They say how close a break test came to its threshold. */
+static void estimate_transform_ex(const double *src, const double *dst, size_t n, double T[6],
+                                  uint32_t *accepted, uint32_t *reason, double *margins)
 {
     const double delta_norm_threshold = 1e-6; /* lib.rs:60 */
     const uint32_t max_iter = 200;            /* lib.rs:61 */
@@ -656,12 +659,22 @@ void orc_estimate_transform(const double *src, const double *dst, size_t n, doub
             why = ORC_BREAK_NONE;
             break; /* lib.rs:67-69 */
         }
+        if (margins) {
+            double dd = (delta[0] * delta[0] + delta[1] * delta[1]) + delta[2] * delta[2];
+            double mg = fabs(dd - delta_norm_threshold) / delta_norm_threshold;
+            if (mg < margins[0]) margins[0] = mg;
+        }
         if ((delta[0] * delta[0] + delta[1] * delta[1]) + delta[2] * delta[2] <
             delta_norm_threshold) {
             why = ORC_BREAK_DELTA;
             break; /* lib.rs:71-73 */
         }
         error = orc_huber_error(T, src, dst, n); /* lib.rs:75 */
+        if (margins && prev_error != DBL_MAX) {
+            double big = error > prev_error ? error : prev_error;
+            double mg = big > 0. ? fabs(error - prev_error) / big : 0.;
+            if (mg < margins[1]) margins[1] = mg;
+        }
         if (error > prev_error) {
             why = ORC_BREAK_ERROR;
             break; /* lib.rs:76-78 */
@@ -674,6 +687,12 @@ void orc_estimate_transform(const double *src, const double *dst, size_t n, doub
     }
     if (accepted) *accepted = acc;
     if (reason) *reason = why;
+}
+
+void orc_estimate_transform(const double *src, const double *dst, size_t n, double T[6],
+                            uint32_t *accepted, uint32_t *reason)
+{
+    estimate_transform_ex(src, dst, n, T, accepted, reason, NULL);
 }
 
 /* =====================================================================================
@@ -874,7 +893,10 @@ static int icp_estimate(int dim, const double *src, size_t n, const double *dst,
     memcpy(out, init, sizeof(T));
     if (m == 0 && n > 0 && max_iter > 0)
         return 1; /* reference: index.unwrap() panics (lib.rs:122,165) */
-    if (nn_mode == ORC_NN_KDTREE)
+    if (tr && tr->final_cost) *tr->final_cost = 0.;
+    if (tr && tr->shared_tree)
+        tree = (orc_kdtree *)tr->shared_tree; /* one Icp2d::new(dst), many estimate() calls */
+    else if (nn_mode == ORC_NN_KDTREE)
         tree = orc_kdtree_new(dst, m, dim); /* Icp2d::new / Icp3d::new, lib.rs:97-102,139-144 */
     src_t = (double *)malloc((n ? n : 1) * (size_t)dim * sizeof(double));
     s2 = (double *)malloc((n ? n : 1) * 2 * sizeof(double));
@@ -904,9 +926,11 @@ static int icp_estimate(int dim, const double *src, size_t n, const double *dst,
             }
         }
         H = H * 0x100000001B3ull + h;
-        orc_estimate_transform(s2, d2, n, dT, &acc, &why); /* lib.rs:125,168 */
+        estimate_transform_ex(s2, d2, n, dT, &acc, &why, tr ? tr->margins : NULL); /* lib.rs:125,168 */
         if (tr && tr->inner)
             tr->inner[it] = acc | (why << 16);
+        if (tr && tr->final_cost && it + 1 == max_iter) /* huber_error (lib.rs:45-50) of the last inner solve */
+            *tr->final_cost = orc_huber_error(dT, s2, d2, n);
         orc_transform_mul(dT, T, Tn); /* lib.rs:127,170 */
         memcpy(T, Tn, sizeof(T));
     }
@@ -916,7 +940,7 @@ static int icp_estimate(int dim, const double *src, size_t n, const double *dst,
     free(src_t);
     free(s2);
     free(d2);
-    orc_kdtree_free(tree);
+    if (!(tr && tr->shared_tree)) orc_kdtree_free(tree);
     return 0;
 }
 
@@ -941,6 +965,8 @@ typedef struct {
     uint32_t B, max_iter;
     int nn_mode;
     double *out_T; uint32_t *inner; uint64_t *corr_hash; int32_t *status;
+    const orc_kdtree *shared_tree; size_t shared_m;   /* non-NULL: every pair searches this one target */
+    double *final_cost, *margins;                     /* nullable [B], [B*2] */
     volatile uint32_t next;
 } batch_job;
 
@@ -956,6 +982,17 @@ static void *batch_worker(void *arg)
         tr.nn_mode = jb->nn_mode;
         tr.inner = jb->inner ? jb->inner + (size_t)b * jb->max_iter : NULL;
         tr.corr_hash = jb->corr_hash ? jb->corr_hash + b : NULL;
+        tr.final_cost = jb->final_cost ? jb->final_cost + b : NULL;
+        if (jb->margins) {
+            tr.margins = jb->margins + (size_t)b * 2;
+            tr.margins[0] = tr.margins[1] = HUGE_VAL;
+        }
+        if (jb->shared_tree || jb->dst_off == NULL) {
+            tr.shared_tree = jb->shared_tree;
+            st = icp_estimate(jb->dim, jb->src + (size_t)jb->src_off[b] * (size_t)jb->dim,
+                              jb->src_off[b + 1] - jb->src_off[b], jb->dst, jb->shared_m,
+                              jb->init_T + (size_t)b * 6, jb->max_iter, jb->out_T + (size_t)b * 6, &tr);
+        } else
         st = icp_estimate(jb->dim, jb->src + (size_t)jb->src_off[b] * (size_t)jb->dim,
                           jb->src_off[b + 1] - jb->src_off[b],
                           jb->dst + (size_t)jb->dst_off[b] * (size_t)jb->dim,
@@ -971,9 +1008,25 @@ int orc_icp_estimate_batch(int dim, const double *src, const uint32_t *src_off,
                            uint32_t B, uint32_t max_iter, int nn_mode, int nthreads,
                            double *out_T, uint32_t *inner, uint64_t *corr_hash, int32_t *status)
 {
+    return orc_icp_estimate_batch_ex(dim, src, src_off, dst, dst_off, 0, init_T, B, max_iter, nn_mode,
+                                     nthreads, out_T, inner, corr_hash, status, NULL, NULL);
+}
+
+int orc_icp_estimate_batch_ex(int dim, const double *src, const uint32_t *src_off,
+                              const double *dst, const uint32_t *dst_off, size_t shared_m,
+                              const double *init_T, uint32_t B, uint32_t max_iter, int nn_mode,
+                              int nthreads, double *out_T, uint32_t *inner, uint64_t *corr_hash,
+                              int32_t *status, double *final_cost, double *margins)
+{
     batch_job jb;
     pthread_t *th;
+    orc_kdtree *shared = NULL;
     int i, started = 0;
+    jb.shared_tree = NULL; jb.shared_m = shared_m; jb.final_cost = final_cost; jb.margins = margins;
+    if (dst_off == NULL && nn_mode == ORC_NN_KDTREE && shared_m > 0) {
+        shared = orc_kdtree_new(dst, shared_m, dim); /* Icp2d::new once (lib.rs:97-102) */
+        jb.shared_tree = shared;
+    }
     if (nthreads < 1) nthreads = 1;
     if ((uint32_t)nthreads > B && B > 0) nthreads = (int)B;
     jb.dim = dim; jb.src = src; jb.src_off = src_off; jb.dst = dst; jb.dst_off = dst_off;
@@ -983,6 +1036,7 @@ int orc_icp_estimate_batch(int dim, const double *src, const uint32_t *src_off,
     if (inner) memset(inner, 0, (size_t)B * max_iter * sizeof(uint32_t));
     if (nthreads == 1) {
         batch_worker(&jb);
+        orc_kdtree_free(shared);
         return 1;
     }
     th = (pthread_t *)malloc((size_t)nthreads * sizeof(pthread_t));
@@ -991,5 +1045,6 @@ int orc_icp_estimate_batch(int dim, const double *src, const uint32_t *src_off,
     if (started == 0) batch_worker(&jb);
     for (i = 0; i < started; i++) pthread_join(th[i], NULL);
     free(th);
+    orc_kdtree_free(shared);
     return started ? started : 1;
 }

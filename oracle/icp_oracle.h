@@ -115,6 +115,12 @@ typedef struct {
     int32_t *corr;          /* [n] (LAST) or [max_iter*n] (ALL); nullable */
     uint32_t *inner;        /* [max_iter]: accepted | reason<<16; nullable */
     uint64_t *corr_hash;    /* one value; nullable.  Definition: see orc_corr_hash_step */
+    const void *shared_tree;/* nullable: an orc_kdtree built once over dst (Icp2d::new once, many estimates) */
+    double *final_cost;     /* nullable: huber_error (lib.rs:45-50) of the LAST inner solve's transform over the
+                               last outer iteration's (transformed source, matched target) points; 0 when no
+                               outer iteration ran */
+    double *margins;        /* nullable [2], caller-initialised to +inf: smallest relative distance of a
+                               delta-norm / error break test (lib.rs:71,76) from its threshold */
 } orc_trace;
 
 /* status: 0 ok, 1 = empty target with non-empty source (reference panics, lib.rs:122,165) */
@@ -135,6 +141,15 @@ int orc_icp_estimate_batch(int dim, const double *src, const uint32_t *src_off,
                            const double *dst, const uint32_t *dst_off, const double *init_T,
                            uint32_t B, uint32_t max_iter, int nn_mode, int nthreads,
                            double *out_T, uint32_t *inner, uint64_t *corr_hash, int32_t *status);
+
+/* Same, plus: dst_off == NULL -> every pair is estimated against the ONE target dst[0..shared_m)
+ * (kd-tree built once, as `Icp2d::new(&dst)` followed by many `estimate` calls);
+ * final_cost (nullable) = B, margins (nullable) = B*2: see orc_trace. */
+int orc_icp_estimate_batch_ex(int dim, const double *src, const uint32_t *src_off,
+                              const double *dst, const uint32_t *dst_off, size_t shared_m,
+                              const double *init_T, uint32_t B, uint32_t max_iter, int nn_mode,
+                              int nthreads, double *out_T, uint32_t *inner, uint64_t *corr_hash,
+                              int32_t *status, double *final_cost, double *margins);
 
 #ifdef __cplusplus
 }

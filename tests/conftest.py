@@ -28,3 +28,10 @@ def scans3d():
     z = np.load(os.path.join(ROOT, "tests", "golden", "scans3d.npz"))
     pts, off = z["points"], z["offsets"]
     return [pts[off[k]:off[k + 1]].copy() for k in range(len(off) - 1)]
+
+
+@pytest.fixture(scope="session")
+def frames3d_20():
+    """All 20 bundled 3-D frames cut to 16,384 points (tests/golden/scans3d_20.npz): config 4."""
+    from icp_rust_b200.workloads import load_frames3d_20
+    return load_frames3d_20()

@@ -418,3 +418,86 @@ def test_config3_queries_full_map(ctx, icp):
     assert np.array_equal(got, exp)
     brute = oracle.nn_search(m, q[:3000], oracle.NN_BRUTE)
     assert np.array_equal(exp[:3000], brute)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs at their full size (configs 1, 3, 4 were sampled, not run)
+@pytest.mark.parametrize("ordered", [True, False])
+def test_config1_whole_chain_and_batch(ctx, icp, scans2d, ordered):
+    """BASELINE config 1 in full: examples/scan2d.rs:62-88 — src = 001 fixed, dst = 002 ... 209,
+    warm start, 20 iterations — every frame of the recording, (a) as the chain the example runs and
+    (b) as one 208-pair batch from identity."""
+    src = scans2d[1]
+    ids = list(range(2, 210))
+    # (a) the chain.  Each frame starts from the ORACLE's previous transform so that every one of
+    # the 208 estimates is compared on identical inputs; the device's own chain is carried beside it.
+    T_or, T_dev = I6.copy(), I6.copy()
+    so = np.array([0, len(src)], np.uint32)
+    for k in ids:
+        dst = scans2d[k]
+        do = np.array([0, len(dst)], np.uint32)
+        o = oracle.icp_estimate(src, dst, T_or, 20, nn_mode=oracle.NN_KDTREE)
+        g = ctx.estimate_batch(src, so, dst, do, T_or[None], 20, ordered=ordered)
+        assert np.array_equal(g["inner"][0], o["inner"]), f"frame {k}: inner iteration counts differ"
+        assert int(g["corr_hash"][0]) == int(o["corr_hash"]), f"frame {k}: correspondences differ"
+        if ordered:
+            assert np.array_equal(g["T"][0], o["T"]), f"frame {k}"
+        else:
+            assert np.abs(g["T"][0] - o["T"]).max() <= TOL, f"frame {k}"
+        T_dev = ctx.estimate_batch(src, so, dst, do, T_dev[None], 20, ordered=ordered, want_inner=False,
+                                   want_hash=False)["T"][0].copy()
+        T_or = o["T"].copy()
+        assert np.abs(T_dev - T_or).max() <= TOL, f"frame {k}: the device's own chain drifted"
+    if ordered:
+        assert np.array_equal(T_dev, T_or)
+    # (b) the same 208 pairs as one batch from identity
+    srcs = [src] * len(ids)
+    dsts = [scans2d[k] for k in ids]
+    s, so = _cat(srcs, 2)
+    d, do = _cat(dsts, 2)
+    T0 = np.tile(I6, (len(ids), 1))
+    g = ctx.estimate_batch(s, so, d, do, T0, 20, ordered=ordered)
+    o = oracle.icp_estimate_batch(2, s, so, d, do, T0, 20, nn_mode=oracle.NN_KDTREE)
+    assert np.array_equal(g["inner"], o["inner"]) and np.array_equal(g["corr_hash"], o["corr_hash"])
+    assert (g["status"] == 0).all()
+    if ordered:
+        assert np.array_equal(g["T"], o["T"])
+    else:
+        assert np.abs(g["T"] - o["T"]).max() <= TOL
+
+
+def test_config3_icp_loop_full_map(ctx, icp):
+    """BASELINE config 3 at full map size inside the ICP loop: 1024 scans x 1080 points, each against
+    the WHOLE shared 100,000-point map, 20 iterations; oracle = one kd-tree (Icp2d::new once), one
+    estimate per scan.  Default mode on all 1024, ordered sums on the first 128."""
+    m = icp.synth_map(100_000, seed=7)
+    B = 1024
+    scans, off, T0 = icp.synth_map_scans(B, beams=1080, seed=7)
+    o = oracle.icp_estimate_batch(2, scans, off, m, None, T0, 20, nn_mode=oracle.NN_KDTREE)
+    t = icp.Target(m, ctx)
+    g = t.estimate_batch(scans, off, T0, 20)
+    assert (g["status"] == 0).all()
+    assert np.array_equal(g["inner"], o["inner"])
+    assert np.array_equal(g["corr_hash"], o["corr_hash"])
+    assert np.abs(g["T"] - o["T"]).max() <= TOL
+    n = 128
+    g = t.estimate_batch(scans[:n * 1080], off[:n + 1], T0[:n], 20, ordered=True)
+    assert np.array_equal(g["inner"], o["inner"][:n]) and np.array_equal(g["corr_hash"], o["corr_hash"][:n])
+    assert np.array_equal(g["T"], o["T"][:n])
+    t.close()
+
+
+def test_config4_baseline_shape(ctx, icp, frames3d_20):
+    """BASELINE config 4 at its own shape: pairs (frame i, frame i+1 mod 20) of the bundled 3-D
+    recording (examples/scan3d.rs:104-131), 16,384 points per cloud, seeded initial perturbation,
+    20 iterations; 80 pairs = every frame pair four times with different initial transforms."""
+    from icp_rust_b200.workloads import config4_pairs
+    B = 80
+    src, dst, off, T0 = config4_pairs(B, frames=frames3d_20)
+    o = oracle.icp_estimate_batch(3, src, off, dst, off, T0, 20, nn_mode=oracle.NN_KDTREE)
+    g = ctx.estimate_batch(src, off, dst, off, T0, 20, dim=3)
+    assert ctx.call_info()["block_threads"] == 512
+    assert (g["status"] == 0).all()
+    assert np.array_equal(g["inner"], o["inner"])
+    assert np.array_equal(g["corr_hash"], o["corr_hash"])
+    assert np.abs(g["T"] - o["T"]).max() <= TOL
