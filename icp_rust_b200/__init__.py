@@ -20,7 +20,9 @@ from ._lib import Batch, CallInfo, MissingNativeLibrary, cuda_lib, synth_lib, EX
 
 CORR_NONE, CORR_LAST, CORR_ALL = 0, 1, 2
 FLAG_ORDERED_SUMS = 1  # ICP_B200_FLAG_ORDERED_SUMS: reference-order sums, bit-identical transforms
-ABI_VERSION = 2
+FLAG_SHARED_SOURCE = 2  # one source scan, `batch` initial transforms
+FLAG_NO_GUARD = 4  # default mode without the knife-edge guard / ordered re-run
+ABI_VERSION = 3
 BREAK_CAP, BREAK_NONE, BREAK_DELTA, BREAK_ERROR = 0, 1, 2, 3
 PAIR_OK, PAIR_EMPTY_TARGET, PAIR_TOO_LARGE, PAIR_NON_FINITE = 0, 1, 2, 3
 ERR_EMPTY_TARGET, ERR_NON_FINITE, ERR_TOO_LARGE = 4, 5, 6
@@ -124,20 +126,26 @@ class Context:
 
     # ------------------------------------------------------------------ batched estimate (host arrays)
     def estimate_batch(self, src, src_off, dst, dst_off, init_T, max_iter=20, *, dim=None, corr_mode=CORR_NONE,
-                       want_inner=True, want_hash=True, target=None, raise_on_pair_error=True, ordered=False):
+                       want_inner=True, want_hash=True, target=None, raise_on_pair_error=True, ordered=False,
+                       want_cost=False, shared_source=False, guard=True):
         """B independent `IcpD::new(dst_b).estimate(src_b, init_b, max_iter)` calls.
-        src/dst: concatenated (P, dim) float64; *_off: (B+1,) uint32.  Returns a dict."""
+        src/dst: concatenated (P, dim) float64; *_off: (B+1,) uint32.  Returns a dict.
+        shared_source: `src` is ONE scan (src_off = [0, n]) aligned from every row of init_T.
+        want_cost: also return the final huber_error per pair (icp_b200_batch.out_cost).
+        guard=False: ICP_B200_FLAG_NO_GUARD."""
         src = np.ascontiguousarray(src, dtype=np.float64)
         if dim is None:
             dim = src.shape[1] if src.ndim == 2 else 2
         src_off = np.ascontiguousarray(src_off, dtype=np.uint32)
-        B = src_off.size - 1
-        init_T = np.ascontiguousarray(init_T, dtype=np.float64).reshape(B, 6)
+        init_T = np.ascontiguousarray(init_T, dtype=np.float64).reshape(-1, 6)
+        B = init_T.shape[0] if shared_source else src_off.size - 1
+        assert init_T.shape[0] == B and (not shared_source or src_off.size == 2)
         out_T = np.zeros((B, 6))
         inner = np.zeros((B, max(max_iter, 1)), dtype=np.uint32) if want_inner else None
         hashes = np.zeros(B, dtype=np.uint64) if want_hash else None
         status = np.zeros(B, dtype=np.int32)
-        nsrc = int(src_off[-1])
+        cost = np.zeros(B) if want_cost else None
+        nsrc = int(src_off[-1]) * (B if shared_source else 1)
         corr = None
         if corr_mode == CORR_ALL:
             corr = np.full(max(nsrc * max_iter, 1), -1, dtype=np.int32)
@@ -145,9 +153,11 @@ class Context:
             corr = np.full(max(nsrc, 1), -1, dtype=np.int32)
         b = Batch()
         b.dim, b.batch, b.max_iter, b.corr_mode = dim, B, max_iter, corr_mode
-        b.flags = FLAG_ORDERED_SUMS if ordered else 0
+        b.flags = (FLAG_ORDERED_SUMS if ordered else 0) | (FLAG_SHARED_SOURCE if shared_source else 0) | \
+                  (0 if guard else FLAG_NO_GUARD)
         b.src = src.ctypes.data if src.size else None
         b.src_off = src_off.ctypes.data
+        b.out_cost = cost.ctypes.data if cost is not None else None
         if target is None:
             dst = np.ascontiguousarray(dst, dtype=np.float64)
             dst_off = np.ascontiguousarray(dst_off, dtype=np.uint32)
@@ -173,19 +183,22 @@ class Context:
             res["corr_hash"] = hashes
         if corr is not None:
             res["corr"] = corr
+        if cost is not None:
+            res["cost"] = cost
+        res["redo_pairs"] = self.call_info()["redo_pairs"]
         return res
 
     # ------------------------------------------------------------------ device-resident batch
     def estimate_batch_device(self, ptrs: dict, B, max_iter, dim=2, corr_mode=CORR_NONE, max_src=0, max_dst=0,
-                              stream=None, synchronize=True, target=None, ordered=False):
+                              stream=None, synchronize=True, target=None, ordered=False, flags=0):
         """ptrs: device addresses (ints) for src, src_off, dst, dst_off, init_T, out_T and optionally
         out_inner, out_corr, out_corr_hash, out_status.  Used with torch tensors' data_ptr()."""
         b = Batch()
         b.dim, b.batch, b.max_iter, b.corr_mode = dim, B, max_iter, corr_mode
         b.max_src_points, b.max_dst_points = max_src, max_dst
-        b.flags = FLAG_ORDERED_SUMS if ordered else 0
+        b.flags = (FLAG_ORDERED_SUMS if ordered else 0) | flags
         for k in ("src", "src_off", "dst", "dst_off", "init_T", "out_T", "out_inner", "out_corr", "out_corr_hash",
-                  "out_status"):
+                  "out_status", "out_cost"):
             v = ptrs.get(k)
             setattr(b, k, v if v else None)
         if target is None:
@@ -194,15 +207,16 @@ class Context:
             rc = self._L.icp_b200_target_estimate_batch_device(target._h, C.byref(b), stream, 1 if synchronize else 0)
         return self._check(rc)
 
-    def estimate_batch_host_ptrs(self, ptrs: dict, B, max_iter, dim=2, corr_mode=CORR_NONE, target=None, ordered=False):
+    def estimate_batch_host_ptrs(self, ptrs: dict, B, max_iter, dim=2, corr_mode=CORR_NONE, target=None, ordered=False,
+                                 flags=0):
         """icp_b200_estimate_batch on caller-owned HOST buffers given as addresses (e.g. pinned torch
         tensors): same keys as estimate_batch_device.  Copies in, computes, copies results back and
         returns when they have landed."""
         b = Batch()
         b.dim, b.batch, b.max_iter, b.corr_mode = dim, B, max_iter, corr_mode
-        b.flags = FLAG_ORDERED_SUMS if ordered else 0
+        b.flags = (FLAG_ORDERED_SUMS if ordered else 0) | flags
         for k in ("src", "src_off", "dst", "dst_off", "init_T", "out_T", "out_inner", "out_corr", "out_corr_hash",
-                  "out_status"):
+                  "out_status", "out_cost"):
             v = ptrs.get(k)
             setattr(b, k, v if v else None)
         if target is None:
@@ -300,13 +314,9 @@ class _IcpBase:
         T0 = _as_T6(initial_transform)
         if self._target is not None:
             off = np.array([0, len(src)], dtype=np.uint32)
-            try:      # the reference's exact sums whenever the scan fits the ordered-sums kernel
-                res = self._target.estimate_batch(src, off, T0[None], max_iter, want_inner=False, want_hash=False,
-                                                  ordered=True)
-            except IcpError as e:
-                if e.status != ERR_TOO_LARGE:
-                    raise
-                res = self._target.estimate_batch(src, off, T0[None], max_iter, want_inner=False, want_hash=False)
+            # one pair: the reference's exact sums (any scan size)
+            res = self._target.estimate_batch(src, off, T0[None], max_iter, want_inner=False, want_hash=False,
+                                              ordered=True)
             return Transform.from_array(res["T"][0])
         out = np.zeros(6)
         L = self.ctx._L

@@ -21,6 +21,7 @@ class Batch(C.Structure):
         ("src", C.c_void_p), ("src_off", C.c_void_p), ("dst", C.c_void_p), ("dst_off", C.c_void_p),
         ("init_T", C.c_void_p), ("out_T", C.c_void_p), ("out_inner", C.c_void_p), ("out_corr", C.c_void_p),
         ("out_corr_hash", C.c_void_p), ("out_status", C.c_void_p), ("flags", C.c_uint32),
+        ("out_cost", C.c_void_p),
     ]
 
 
@@ -28,7 +29,7 @@ class CallInfo(C.Structure):
     """icp_b200_call_info"""
     _fields_ = [("kernel_launches", C.c_uint32), ("kernel_ms", C.c_float), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("grid_ctas", C.c_uint32), ("block_threads", C.c_uint32),
-                ("smem_bytes", C.c_uint32)]
+                ("smem_bytes", C.c_uint32), ("redo_pairs", C.c_uint32)]
 
 
 # every symbol include/icp_b200.h declares

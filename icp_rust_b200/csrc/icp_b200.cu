@@ -53,6 +53,12 @@ const Instance* const kInstances[] = {&kFusedInstance0, &kFusedInstance1, &kFuse
                                       &kFusedInstance12, &kFusedInstance13};
 constexpr int kNumInstances = (int)(sizeof(kInstances) / sizeof(kInstances[0]));
 constexpr int kMaxChunks = 64;
+// device counter words of a context: per-chunk work counters | error word | per-chunk work counters
+// of the ordered re-run | per-chunk counts of flagged pairs
+constexpr int kCtrWork = 0, kCtrErr = kMaxChunks, kCtrRedoWork = kMaxChunks + 1, kCtrRedoCount = 2 * kMaxChunks + 1;
+constexpr int kCtrWords = 3 * kMaxChunks + 1;
+// bands of the knife-edge guard (GuardBands, icp_fused.cuh; include/icp_b200.h "flags")
+constexpr double kGuardDet = 1e-10, kGuardDelta = 1e-6, kGuardErr = 1e-10;
 
 int env_int(const char* name, int dflt)
 {
@@ -70,9 +76,12 @@ struct icp_b200_context {
     cudaEvent_t ev[kMaxChunks][2];
     cudaEvent_t ev_ready = nullptr;
     bool events_ok = false;
-    DevBuf src, dst, src_off, dst_off, init_T, out_T, out_inner, out_corr, out_hash, out_status;
-    DevBuf counters;       // kMaxChunks work counters + 1 error word
+    DevBuf src, dst, src_off, dst_off, init_T, out_T, out_inner, out_corr, out_hash, out_status, out_cost;
+    DevBuf counters;       // kCtrWords words (layout above)
     DevBuf workspace[2];
+    DevBuf redo_list, redo_workspace[2];   // flagged pairs of the launch in flight / slabs of their ordered re-run
+    int guard = 1;          // ICP_B200_GUARD=0: no knife-edge guard (as ICP_B200_FLAG_NO_GUARD on every call)
+    double guard_scale = 1.0;   // ICP_B200_GUARD_SCALE: multiplies the guard bands (tests force re-runs with it)
     DevBuf stats_in, stats_off, stats_out;
     icp_b200_call_info info{};
     std::string last_error;
@@ -140,6 +149,7 @@ struct LaunchPlan {
     bool stream = false;              // ... or the streaming kernel for large scans
     StreamKernel skernel = nullptr;
     StreamLayout slayout{};
+    bool stream_ordered = false;
     uint32_t n_cap = 0, m_cap = 0, c_cap = 0;
     int threads = 0;
     uint32_t smem = 0;
@@ -168,20 +178,19 @@ int plan_launch(icp_b200_context* ctx, uint32_t dim, bool shared_target, bool or
     }
     if (ctx->force_stream && !ordered) inst = nullptr;
     if (!inst) {
-        // large scans: streaming kernel, warp-tree sums only
-        if (ordered)
-            return fail(ctx, ICP_B200_ERR_TOO_LARGE,
-                        "scan pair too large for the ordered-sums kernel (3072 source points / shared memory of one SM): clear ICP_B200_FLAG_ORDERED_SUMS");
+        // large scans: streaming kernel (warp-tree sums, or the tiled reference-order chain)
         if (max_n > 65535u) return fail(ctx, ICP_B200_ERR_TOO_LARGE, "source scan larger than 65535 points");
+        plan->inst = nullptr;
         plan->stream = true;
+        plan->stream_ordered = ordered;
         plan->n_cap = std::max<uint32_t>(8u, (max_n + 7u) & ~7u);
         plan->m_cap = shared_target ? 0u : std::max<uint32_t>(8u, (max_m + 7u) & ~7u);
         plan->c_cap = shared_target ? 0u : std::max<uint32_t>(64u, (uint32_t)ctx->stream_cells_per_point * plan->m_cap);
-        plan->slayout = stream_layout((int)dim, plan->n_cap, plan->m_cap, plan->c_cap, shared_target);
+        plan->slayout = stream_layout((int)dim, plan->n_cap, plan->m_cap, plan->c_cap, shared_target, ordered);
         plan->ws_stride = plan->slayout.total;
         plan->skernel = kStreamInstance.k[dim - 2][shared_target ? 1 : 0];
         plan->threads = kStreamInstance.threads;
-        plan->smem = kStreamShared;
+        plan->smem = stream_smem_bytes(ordered);
         int occ = 0;
         ICP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, plan->skernel, plan->threads, plan->smem));
         if (occ < 1) return fail(ctx, ICP_B200_ERR_CUDA, "streaming kernel cannot be resident (occupancy 0)");
@@ -210,27 +219,38 @@ int validate_batch(icp_b200_context* ctx, const icp_b200_batch* b, bool shared_t
     if (!b->src_off || !b->init_T || !b->out_T) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null src_off / init_T / out_T");
     if (!shared_target && !b->dst_off) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null dst_off");
     if (b->corr_mode < 0 || b->corr_mode > 2) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "bad corr_mode");
-    if (b->flags & ~(uint32_t)ICP_B200_FLAG_ORDERED_SUMS) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "unknown flag bits");
+    if (b->flags & ~(uint32_t)(ICP_B200_FLAG_ORDERED_SUMS | ICP_B200_FLAG_SHARED_SOURCE | ICP_B200_FLAG_NO_GUARD))
+        return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "unknown flag bits");
     if (b->corr_mode != ICP_B200_CORR_NONE && !b->out_corr) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "corr_mode set but out_corr is null");
     return ICP_B200_OK;
 }
 
-// Device-pointer launch of pairs [begin, end) on `stream`.
+// Device-pointer launch of pairs [begin, end) on `stream`.  `redo` (tree mode with the knife-edge
+// guard): the plan of the ordered kernel that re-runs, right behind the main kernel on the same
+// stream, the pairs the main kernel flagged (their indices and count stay on the device).
 int launch_range(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_target* tgt, const LaunchPlan& plan,
-                 uint32_t begin, uint32_t end, int chunk_slot, int ws_slot, cudaStream_t stream)
+                 const LaunchPlan* redo, uint32_t begin, uint32_t end, int chunk_slot, int ws_slot, cudaStream_t stream)
 {
     FusedParams p{};
     p.src = b.src; p.src_off = b.src_off; p.dst = b.dst; p.dst_off = b.dst_off; p.init_T = b.init_T;
     p.out_T = b.out_T; p.out_inner = b.out_inner; p.out_corr = b.out_corr; p.out_hash = b.out_corr_hash;
-    p.out_status = b.out_status;
-    p.out_error = ctx->counters.as<int32_t>() + kMaxChunks;
-    p.work_counter = ctx->counters.as<uint32_t>() + chunk_slot;
+    p.out_status = b.out_status; p.out_cost = b.out_cost;
+    p.shared_src = (b.flags & ICP_B200_FLAG_SHARED_SOURCE) ? 1u : 0u;
+    p.out_error = ctx->counters.as<int32_t>() + kCtrErr;
+    p.work_counter = ctx->counters.as<uint32_t>() + kCtrWork + chunk_slot;
     p.workspace = ctx->workspace[ws_slot].as<unsigned char>();
     p.ws_stride = plan.ws_stride;
     p.pair_begin = begin; p.pair_end = end; p.max_iter = b.max_iter; p.corr_mode = b.corr_mode;
     p.cell_budget = ctx->cell_budget; p.mcap = plan.mcap;
     p.ncap = plan.stream ? (int)plan.n_cap : plan.inst->threads * plan.inst->ppt;
     p.sm_count = (uint32_t)ctx->sm_count;
+    if (redo) {
+        p.redo_list = ctx->redo_list.as<uint32_t>() + begin;     // a chunk's flagged pairs fit its own pair range
+        p.redo_count = ctx->counters.as<uint32_t>() + kCtrRedoCount + chunk_slot;
+        p.guard.det = kGuardDet * ctx->guard_scale;
+        p.guard.delta = kGuardDelta * ctx->guard_scale;
+        p.guard.err = kGuardErr * ctx->guard_scale;
+    }
     if (tgt) {
         p.target.x = tgt->x.as<double>(); p.target.y = tgt->y.as<double>(); p.target.z = tgt->z.as<double>();
         p.target.idx = tgt->idx.as<uint32_t>(); p.target.cstart = tgt->cstart.as<uint32_t>();
@@ -238,20 +258,51 @@ int launch_range(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_
         p.target.seed = tgt->seed_ptr; p.target.pf = tgt->seed_ptr ? tgt->pf.as<float2>() : nullptr;
     }
     const uint32_t pairs = end - begin;
+    auto launch = [&](const LaunchPlan& pl, const FusedParams& fp, int grid) {
+        if (pl.stream) {
+            StreamParams sp{};
+            sp.f = fp; sp.n_cap = pl.n_cap; sp.m_cap = pl.m_cap; sp.c_cap = pl.c_cap;
+            sp.cells_per_point = (uint32_t)ctx->stream_cells_per_point;
+            sp.ordered = pl.stream_ordered ? 1u : 0u;
+            pl.skernel<<<grid, pl.threads, pl.smem, stream>>>(sp);
+        } else {
+            pl.kernel<<<grid, pl.threads, pl.smem, stream>>>(fp);
+        }
+    };
     const int grid = (int)std::min<uint32_t>((uint32_t)plan.grid, pairs);
-    if (plan.stream) {
-        StreamParams sp{};
-        sp.f = p; sp.n_cap = plan.n_cap; sp.m_cap = plan.m_cap; sp.c_cap = plan.c_cap;
-        sp.cells_per_point = (uint32_t)ctx->stream_cells_per_point;
-        plan.skernel<<<grid, plan.threads, plan.smem, stream>>>(sp);
-    } else {
-        plan.kernel<<<grid, plan.threads, plan.smem, stream>>>(p);
-    }
+    launch(plan, p, grid);
     ICP_CUDA(ctx, cudaGetLastError());
     ctx->info.kernel_launches += 1;
     ctx->info.grid_ctas = (uint32_t)grid;
     ctx->info.block_threads = (uint32_t)plan.threads;
     ctx->info.smem_bytes = plan.smem;
+    if (redo) {
+        FusedParams r = p;
+        r.pair_list = p.redo_list; r.pair_count = p.redo_count;
+        r.redo_list = nullptr; r.redo_count = nullptr; r.guard = GuardBands{0., 0., 0.};
+        r.work_counter = ctx->counters.as<uint32_t>() + kCtrRedoWork + chunk_slot;
+        r.workspace = ctx->redo_workspace[ws_slot].as<unsigned char>();
+        r.ws_stride = redo->ws_stride;
+        r.pair_begin = 0; r.pair_end = b.batch;
+        r.mcap = redo->mcap;
+        r.ncap = redo->stream ? (int)redo->n_cap : redo->inst->threads * redo->inst->ppt;
+        launch(*redo, r, (int)std::min<uint32_t>((uint32_t)redo->grid, pairs));
+        ICP_CUDA(ctx, cudaGetLastError());
+        ctx->info.kernel_launches += 1;
+    }
+    return ICP_B200_OK;
+}
+
+// The ordered plan that re-runs flagged pairs, when this call wants the guard.
+int plan_redo(icp_b200_context* ctx, const icp_b200_batch* b, bool shared, uint32_t max_n, uint32_t max_m, LaunchPlan* redo,
+              bool* use)
+{
+    *use = false;
+    if ((b->flags & (ICP_B200_FLAG_ORDERED_SUMS | ICP_B200_FLAG_NO_GUARD)) || !ctx->guard) return ICP_B200_OK;
+    int rc = plan_launch(ctx, b->dim, shared, true, max_n, max_m, b->batch, redo);
+    if (rc != ICP_B200_OK) return rc;
+    ICP_CUDA(ctx, ctx->redo_list.ensure((size_t)b->batch * 4));
+    *use = true;
     return ICP_B200_OK;
 }
 
@@ -293,21 +344,28 @@ int estimate_device_impl(icp_b200_context* ctx, const icp_b200_target* tgt, cons
         }
         ctx->info.d2h_bytes += (uint64_t)off.size() * 4 * (shared ? 1 : 2);
     }
-    LaunchPlan plan;
+    LaunchPlan plan, redo;
+    bool use_redo = false;
     rc = plan_launch(ctx, b->dim, shared, (b->flags & ICP_B200_FLAG_ORDERED_SUMS) != 0, max_n, max_m, b->batch, &plan);
     if (rc != ICP_B200_OK) return rc;
-    ICP_CUDA(ctx, ctx->counters.ensure((kMaxChunks + 1) * 4));
+    rc = plan_redo(ctx, b, shared, max_n, max_m, &redo, &use_redo);
+    if (rc != ICP_B200_OK) return rc;
+    ICP_CUDA(ctx, ctx->counters.ensure(kCtrWords * 4));
     ICP_CUDA(ctx, ctx->workspace[0].ensure((size_t)plan.grid * plan.ws_stride + 256));
-    ICP_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, (kMaxChunks + 1) * 4, stream));
+    if (use_redo) ICP_CUDA(ctx, ctx->redo_workspace[0].ensure((size_t)redo.grid * redo.ws_stride + 256));
+    ICP_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, kCtrWords * 4, stream));
     ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], stream));
-    rc = launch_range(ctx, *b, tgt, plan, 0, b->batch, 0, 0, stream);
+    rc = launch_range(ctx, *b, tgt, plan, use_redo ? &redo : nullptr, 0, b->batch, 0, 0, stream);
     if (rc != ICP_B200_OK) return rc;
     ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][1], stream));
     if (synchronize) {
         int32_t err = 0;
-        ICP_CUDA(ctx, cudaMemcpyAsync(&err, ctx->counters.as<int32_t>() + kMaxChunks, 4, cudaMemcpyDeviceToHost, stream));
+        uint32_t nredo = 0;
+        ICP_CUDA(ctx, cudaMemcpyAsync(&err, ctx->counters.as<int32_t>() + kCtrErr, 4, cudaMemcpyDeviceToHost, stream));
+        ICP_CUDA(ctx, cudaMemcpyAsync(&nredo, ctx->counters.as<uint32_t>() + kCtrRedoCount, 4, cudaMemcpyDeviceToHost, stream));
         ICP_CUDA(ctx, cudaStreamSynchronize(stream));
         ICP_CUDA(ctx, cudaEventElapsedTime(&ctx->info.kernel_ms, ctx->ev[0][0], ctx->ev[0][1]));
+        ctx->info.redo_pairs = nredo;
         if (err != 0) return fail(ctx, pair_status_to_error(err), "at least one scan pair was rejected (see out_status)");
     }
     return ICP_B200_OK;
@@ -324,28 +382,37 @@ int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b2
     rc = ensure_events(ctx);
     if (rc != ICP_B200_OK) return rc;
     const uint32_t B = hb->batch, dim = hb->dim;
+    const bool shared_src = (hb->flags & ICP_B200_FLAG_SHARED_SOURCE) != 0;
+    const uint32_t SB = shared_src ? 1u : B;      // entries of the source offset table - 1
     const uint32_t* so = hb->src_off;
     const uint32_t* doff = hb->dst_off;
     uint32_t max_n = 0, max_m = shared ? tgt->m : 0;
     for (uint32_t i = 0; i < B; ++i) {
-        if (so[i + 1] < so[i]) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "src_off not monotone");
-        max_n = std::max(max_n, so[i + 1] - so[i]);
+        if (i < SB) {
+            if (so[i + 1] < so[i]) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "src_off not monotone");
+            max_n = std::max(max_n, so[i + 1] - so[i]);
+        }
         if (!shared) {
             if (doff[i + 1] < doff[i]) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "dst_off not monotone");
             max_m = std::max(max_m, doff[i + 1] - doff[i]);
         }
     }
-    const uint64_t nsrc = so[B], ndst = shared ? 0 : doff[B];
+    const uint64_t nsrc = so[SB], ndst = shared ? 0 : doff[B];
     if ((nsrc && !hb->src) || (ndst && !hb->dst)) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null point array");
-    LaunchPlan plan;
+    LaunchPlan plan, redo;
+    bool use_redo = false;
     rc = plan_launch(ctx, dim, shared, (hb->flags & ICP_B200_FLAG_ORDERED_SUMS) != 0, max_n, max_m, B, &plan);
     if (rc != ICP_B200_OK) return rc;
+    rc = plan_redo(ctx, hb, shared, max_n, max_m, &redo, &use_redo);
+    if (rc != ICP_B200_OK) return rc;
 
-    const uint64_t ncorr = hb->corr_mode == ICP_B200_CORR_ALL ? nsrc * hb->max_iter
-                         : hb->corr_mode == ICP_B200_CORR_LAST ? nsrc : 0;
+    const uint64_t ncorr_pts = shared_src ? nsrc * B : nsrc;   // SHARED_SOURCE: laid out as if the scan were repeated
+    const uint64_t ncorr = hb->max_iter == 0 ? 0
+                         : hb->corr_mode == ICP_B200_CORR_ALL ? ncorr_pts * hb->max_iter
+                         : hb->corr_mode == ICP_B200_CORR_LAST ? ncorr_pts : 0;
     ICP_CUDA(ctx, ctx->src.ensure(std::max<uint64_t>(nsrc, 1) * dim * 8));
     ICP_CUDA(ctx, ctx->dst.ensure(std::max<uint64_t>(ndst, 1) * dim * 8));
-    ICP_CUDA(ctx, ctx->src_off.ensure((B + 1) * 4));
+    ICP_CUDA(ctx, ctx->src_off.ensure((SB + 1) * 4));
     ICP_CUDA(ctx, ctx->dst_off.ensure((B + 1) * 4));
     ICP_CUDA(ctx, ctx->init_T.ensure((size_t)B * 48));
     ICP_CUDA(ctx, ctx->out_T.ensure((size_t)B * 48));
@@ -353,8 +420,11 @@ int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b2
     if (ncorr) ICP_CUDA(ctx, ctx->out_corr.ensure(ncorr * 4));
     if (hb->out_corr_hash) ICP_CUDA(ctx, ctx->out_hash.ensure((size_t)B * 8));
     if (hb->out_status) ICP_CUDA(ctx, ctx->out_status.ensure((size_t)B * 4));
-    ICP_CUDA(ctx, ctx->counters.ensure((kMaxChunks + 1) * 4));
+    if (hb->out_cost) ICP_CUDA(ctx, ctx->out_cost.ensure((size_t)B * 8));
+    ICP_CUDA(ctx, ctx->counters.ensure(kCtrWords * 4));
     for (int s = 0; s < 2; ++s) ICP_CUDA(ctx, ctx->workspace[s].ensure((size_t)plan.grid * plan.ws_stride + 256));
+    if (use_redo)
+        for (int s = 0; s < 2; ++s) ICP_CUDA(ctx, ctx->redo_workspace[s].ensure((size_t)redo.grid * redo.ws_stride + 256));
 
     icp_b200_batch db = *hb;
     db.src = ctx->src.as<double>(); db.dst = ctx->dst.as<double>();
@@ -364,6 +434,7 @@ int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b2
     db.out_corr = ncorr ? ctx->out_corr.as<int32_t>() : nullptr;
     db.out_corr_hash = hb->out_corr_hash ? ctx->out_hash.as<uint64_t>() : nullptr;
     db.out_status = hb->out_status ? ctx->out_status.as<int32_t>() : nullptr;
+    db.out_cost = hb->out_cost ? ctx->out_cost.as<double>() : nullptr;
 
     // chunking: enough chunks to overlap copies with compute, each at least one full wave
     int nchunks = (int)std::min<uint32_t>(kMaxChunks, std::max<uint32_t>(1, B / std::max<uint32_t>(1, (uint32_t)plan.grid * 2)));
@@ -372,23 +443,30 @@ int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b2
     const uint32_t per = (B + (uint32_t)nchunks - 1) / (uint32_t)nchunks;
 
     cudaStream_t s0 = ctx->stream[0], s1 = ctx->stream[1];
-    ICP_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, (kMaxChunks + 1) * 4, s0));
-    ICP_CUDA(ctx, cudaMemcpyAsync(ctx->src_off.p, so, (B + 1) * 4, cudaMemcpyHostToDevice, s0));
+    ICP_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, kCtrWords * 4, s0));
+    ICP_CUDA(ctx, cudaMemcpyAsync(ctx->src_off.p, so, (SB + 1) * 4, cudaMemcpyHostToDevice, s0));
+    if (shared_src && nsrc) {
+        ICP_CUDA(ctx, cudaMemcpyAsync(ctx->src.p, hb->src, nsrc * dim * 8, cudaMemcpyHostToDevice, s0));
+        ctx->info.h2d_bytes += nsrc * dim * 8;
+    }
     if (!shared) ICP_CUDA(ctx, cudaMemcpyAsync(ctx->dst_off.p, doff, (B + 1) * 4, cudaMemcpyHostToDevice, s0));
     ICP_CUDA(ctx, cudaMemcpyAsync(ctx->init_T.p, hb->init_T, (size_t)B * 48, cudaMemcpyHostToDevice, s0));
     ICP_CUDA(ctx, cudaEventRecord(ctx->ev_ready, s0));
     ICP_CUDA(ctx, cudaStreamWaitEvent(s1, ctx->ev_ready, 0));
-    ctx->info.h2d_bytes += (uint64_t)(B + 1) * 4 * (shared ? 1 : 2) + (uint64_t)B * 48;
+    ctx->info.h2d_bytes += (uint64_t)(SB + 1) * 4 + (shared ? 0 : (uint64_t)(B + 1) * 4) + (uint64_t)B * 48;
 
     int used = 0;
     for (int c = 0; c < nchunks; ++c) {
         const uint32_t b0 = (uint32_t)c * per, b1 = std::min<uint32_t>(B, b0 + per);
         if (b0 >= b1) break;
         cudaStream_t st = (c & 1) ? s1 : s0;
-        const uint64_t sp0 = so[b0], sp1 = so[b1];
-        if (sp1 > sp0)
-            ICP_CUDA(ctx, cudaMemcpyAsync(ctx->src.as<double>() + sp0 * dim, hb->src + sp0 * dim, (sp1 - sp0) * dim * 8, cudaMemcpyHostToDevice, st));
-        ctx->info.h2d_bytes += (sp1 - sp0) * dim * 8;
+        // SHARED_SOURCE: the one scan went up with the tables; sp0/sp1 then only place the correspondences
+        const uint64_t sp0 = shared_src ? nsrc * b0 : so[b0], sp1 = shared_src ? nsrc * b1 : so[b1];
+        if (!shared_src) {
+            if (sp1 > sp0)
+                ICP_CUDA(ctx, cudaMemcpyAsync(ctx->src.as<double>() + sp0 * dim, hb->src + sp0 * dim, (sp1 - sp0) * dim * 8, cudaMemcpyHostToDevice, st));
+            ctx->info.h2d_bytes += (sp1 - sp0) * dim * 8;
+        }
         if (!shared) {
             const uint64_t dp0 = doff[b0], dp1 = doff[b1];
             if (dp1 > dp0)
@@ -396,7 +474,7 @@ int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b2
             ctx->info.h2d_bytes += (dp1 - dp0) * dim * 8;
         }
         ICP_CUDA(ctx, cudaEventRecord(ctx->ev[c][0], st));
-        rc = launch_range(ctx, db, tgt, plan, b0, b1, c, c & 1, st);
+        rc = launch_range(ctx, db, tgt, plan, use_redo ? &redo : nullptr, b0, b1, c, c & 1, st);
         if (rc != ICP_B200_OK) return rc;
         ICP_CUDA(ctx, cudaEventRecord(ctx->ev[c][1], st));
         ICP_CUDA(ctx, cudaMemcpyAsync(hb->out_T + (size_t)b0 * 6, ctx->out_T.as<double>() + (size_t)b0 * 6, (size_t)(b1 - b0) * 48, cudaMemcpyDeviceToHost, st));
@@ -414,6 +492,10 @@ int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b2
             ICP_CUDA(ctx, cudaMemcpyAsync(hb->out_status + b0, ctx->out_status.as<int32_t>() + b0, (size_t)(b1 - b0) * 4, cudaMemcpyDeviceToHost, st));
             ctx->info.d2h_bytes += (uint64_t)(b1 - b0) * 4;
         }
+        if (hb->out_cost) {
+            ICP_CUDA(ctx, cudaMemcpyAsync(hb->out_cost + b0, ctx->out_cost.as<double>() + b0, (size_t)(b1 - b0) * 8, cudaMemcpyDeviceToHost, st));
+            ctx->info.d2h_bytes += (uint64_t)(b1 - b0) * 8;
+        }
         if (ncorr) {
             const uint64_t mul = hb->corr_mode == ICP_B200_CORR_ALL ? hb->max_iter : 1;
             if (sp1 > sp0)
@@ -423,9 +505,12 @@ int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b2
         used = c + 1;
     }
     int32_t err = 0;
+    uint32_t nredo[kMaxChunks];
     ICP_CUDA(ctx, cudaStreamSynchronize(s1));
-    ICP_CUDA(ctx, cudaMemcpyAsync(&err, ctx->counters.as<int32_t>() + kMaxChunks, 4, cudaMemcpyDeviceToHost, s0));
+    ICP_CUDA(ctx, cudaMemcpyAsync(&err, ctx->counters.as<int32_t>() + kCtrErr, 4, cudaMemcpyDeviceToHost, s0));
+    ICP_CUDA(ctx, cudaMemcpyAsync(nredo, ctx->counters.as<uint32_t>() + kCtrRedoCount, sizeof(nredo), cudaMemcpyDeviceToHost, s0));
     ICP_CUDA(ctx, cudaStreamSynchronize(s0));
+    for (int c = 0; c < used; ++c) ctx->info.redo_pairs += nredo[c];
     float total = 0.f;
     for (int c = 0; c < used; ++c) {
         float ms = 0.f;
@@ -500,6 +585,8 @@ int icp_b200_create(int device, icp_b200_context** out)
     ctx->stream_cells_per_point = std::max(1, std::min(256, env_int("ICP_B200_STREAM_CELLS_PER_POINT", 8)));
     ctx->force_stream = env_int("ICP_B200_FORCE_STREAM", 0);
     ctx->use_lean = env_int("ICP_B200_LEAN", 1);
+    ctx->guard = env_int("ICP_B200_GUARD", 1);
+    if (const char* gs = getenv("ICP_B200_GUARD_SCALE")) ctx->guard_scale = std::max(0.0, atof(gs));
     *out = ctx;
     return ICP_B200_OK;
 }
@@ -511,7 +598,8 @@ void icp_b200_destroy(icp_b200_context* ctx)
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&ctx->src, &ctx->dst, &ctx->src_off, &ctx->dst_off, &ctx->init_T, &ctx->out_T, &ctx->out_inner,
                       &ctx->out_corr, &ctx->out_hash, &ctx->out_status, &ctx->counters, &ctx->workspace[0],
-                      &ctx->workspace[1], &ctx->stats_in, &ctx->stats_off, &ctx->stats_out};
+                      &ctx->workspace[1], &ctx->stats_in, &ctx->stats_off, &ctx->stats_out, &ctx->out_cost,
+                      &ctx->redo_list, &ctx->redo_workspace[0], &ctx->redo_workspace[1]};
     for (DevBuf* b : bufs) b->release();
     if (ctx->events_ok) {
         for (int i = 0; i < kMaxChunks; ++i)
@@ -547,13 +635,8 @@ static int single_pair(icp_b200_context* ctx, uint32_t dim, const double* dst, u
     icp_b200_batch b{};
     b.dim = dim; b.batch = 1; b.max_iter = max_iter; b.corr_mode = ICP_B200_CORR_NONE;
     b.src = src; b.src_off = so; b.dst = dst; b.dst_off = dof; b.init_T = T0; b.out_T = out;
-    b.flags = ICP_B200_FLAG_ORDERED_SUMS;  // one pair: keep the reference's exact sums whenever the scan fits
-    int rc = estimate_host_impl(ctx, nullptr, &b);
-    if (rc == ICP_B200_ERR_TOO_LARGE) {     // large scans (e.g. the bundled 3-D frames): streaming kernel, warp-tree sums
-        b.flags = 0;
-        rc = estimate_host_impl(ctx, nullptr, &b);
-    }
-    return rc;
+    b.flags = ICP_B200_FLAG_ORDERED_SUMS;  // one pair: the reference's exact sums (any scan size)
+    return estimate_host_impl(ctx, nullptr, &b);
 }
 
 int icp_b200_icp2d_estimate(icp_b200_context* ctx, const double* dst_xy, uint32_t n_dst, const double* src_xy,

@@ -62,6 +62,22 @@ struct FusedCtl {
     uint64_t hash_part[kMaxWarps];
     uint32_t warp_tot[kMaxWarps];
     uint32_t pair;
+    uint32_t knife;       // tree mode: a decision of this pair fell inside a guard band (GuardBands)
+};
+
+// Knife-edge guard of the warp-tree mode.  The tree-reduced sums differ from the reference's
+// sequential fold by rounding (~1e-16 relative per sum, up to ~1e-13 on a decision quantity once the
+// perturbation has travelled through a few updates), and the inner loop's decisions are
+// discontinuous: det == 0 (linalg.rs:18), delta.dot(delta) < 1e-6 (lib.rs:71), error > prev_error
+// (lib.rs:76).  Whenever a decision quantity lies within a relative band of its threshold — bands
+// three or more orders of magnitude wider than that perturbation — the pair is reported in
+// FusedParams::redo_list and the host re-runs it with the reference-order sums (ORDERED), whose
+// decisions and transforms are the reference's by construction.  A pair that is never flagged took
+// every decision with a margin the summation order cannot bridge.  0 disables a band.
+struct GuardBands {
+    double det;     // |det| <= det * (|m00 n00| + |m10 c01| + |m20 n02|)
+    double delta;   // |d.d - 1e-6| <= delta * 1e-6
+    double err;     // |error - prev_error| <= err * max(error, prev_error)
 };
 
 ICP_HD uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
@@ -129,7 +145,32 @@ struct FusedParams {
     int cell_budget;
     int ncap, mcap;             // capacities the layout was built for
     uint32_t sm_count;          // SMs of the device (residency-slot estimate for warp-role rotation)
+    // pair_list != null: the launch handles pairs pair_list[0 .. *pair_count) instead of
+    // [pair_begin, pair_end) — the ordered re-run of the pairs a tree-mode launch flagged
+    const uint32_t* pair_list;
+    const uint32_t* pair_count;
+    // tree mode: pairs with a decision inside a guard band are appended here (null: no guard)
+    uint32_t* redo_list;
+    uint32_t* redo_count;
+    GuardBands guard;
+    double* out_cost;           // [B] nullable: huber_error (lib.rs:45-50) of the last inner solve
+    uint32_t shared_src;        // every pair aligns the scan src[0 .. src_off[1])
 };
+
+// Next pair of this launch (thread 0 only): a contiguous range, or the flagged-pair list.
+// Returns a value >= p.pair_end when the work is exhausted.
+ICP_DEV uint32_t fused_next_pair(const FusedParams& p)
+{
+    const uint32_t k = atomicAdd(p.work_counter, 1u);
+    if (p.pair_list) return k < *p.pair_count ? p.pair_list[k] : 0xffffffffu;
+    return p.pair_begin + k;
+}
+
+// End of a pair in tree mode (thread 0 only): report it for the ordered re-run if it was flagged.
+ICP_DEV void fused_report_knife(const FusedParams& p, FusedCtl* ctl, uint32_t pair)
+{
+    if (ctl->knife && p.redo_list) p.redo_list[atomicAdd(p.redo_count, 1u)] = pair;
+}
 
 // ---------------------------------------------------------------------------------------------
 // @region build_grid
@@ -251,10 +292,9 @@ constexpr int kChainStage = 4;   // points per pipeline stage
 // loaded, so the loop runs at the latency of the DADD chain alone.  Kept out of line so that it
 // gets its own register allocation instead of competing with the per-point state the calling
 // kernel keeps in registers.  nstages >= 2.
-ICP_DEV_NOINLINE double chain_run(ChainPtrs p, int nstages)
+ICP_DEV_NOINLINE double chain_run(ChainPtrs p, int nstages, double acc = 0.0)
 {
     constexpr int S = kChainStage;
-    double acc = 0.0;
     double2 lx[S], ly[S], lz[S];
     double t[2 * S];
 #pragma unroll
@@ -292,9 +332,8 @@ ICP_DEV_NOINLINE double chain_run(ChainPtrs p, int nstages)
 
 // sum of the Huber cost terms in source order (lib.rs:45-50); n2 = number of double2 entries
 // (a multiple of kChainUnroll)
-ICP_DEV_NOINLINE double cost_run(smem_ref rp, int n2)
+ICP_DEV_NOINLINE double cost_run(smem_ref rp, int n2, double e = 0.0)
 {
-    double e = 0.0;
     double2 v[kChainUnroll];
 #pragma unroll
     for (int u = 0; u < kChainUnroll; ++u) v[u] = smem_ld2(rp, u);
@@ -376,7 +415,8 @@ ICP_DEV void tree_accumulate_point(double acc[16], const Transform& Ti, double s
 // cofactor numerators, lane q < 9 forms the one quotient i_q = numerator_q / det and the warp
 // exchanges them — one division on the critical path instead of nine.  Same operations on the
 // same operands as solve_normal_equations, hence the same bits.
-ICP_DEV bool solve_normal_equations_warp(const double m[9], const double jtr[3], double delta[3])
+ICP_DEV bool solve_normal_equations_warp(const double m[9], const double jtr[3], double delta[3],
+                                         double* det_out = nullptr, double* det_scale = nullptr)
 {
     const double m00 = m[0], m01 = m[1], m02 = m[2];
     const double m10 = m[3], m11 = m[4], m12 = m[5];
@@ -385,6 +425,10 @@ ICP_DEV bool solve_normal_equations_warp(const double m[9], const double jtr[3],
     const double c01 = m22 * m01 - m21 * m02;
     const double n02 = m12 * m01 - m11 * m02;
     const double det = m00 * n00 - m10 * c01 + m20 * n02;
+    if (det_out) {
+        *det_out = det;
+        *det_scale = (fabs(m00 * n00) + fabs(m10 * c01)) + fabs(m20 * n02);
+    }
     if (det == 0.) return false;
     const double n01 = -c01;
     const double n10 = -(m22 * m10 - m20 * m12);
@@ -415,7 +459,8 @@ ICP_DEV bool solve_normal_equations_warp(const double m[9], const double jtr[3],
 // selection of the next evaluation provides several).
 // @region tree_reduce
 template <int NW>
-ICP_DEV void cta_tree_reduce_solve(FusedCtl* ctl, double acc[16], const Transform& Ti, double prev_error)
+ICP_DEV void cta_tree_reduce_solve(FusedCtl* ctl, double acc[16], const Transform& Ti, double prev_error,
+                                   const GuardBands& gb)
 {
     const int lane = lane_id(), warp = warp_id();
     warp_reduce16(acc);
@@ -436,10 +481,23 @@ ICP_DEV void cta_tree_reduce_solve(FusedCtl* ctl, double acc[16], const Transfor
         double delta[3];
         uint32_t decision = kBreakCap;   // kBreakCap here = "update accepted"
         Transform Tn = Ti;
-        if (!solve_normal_equations_warp(jtj, jtr, delta)) decision = kBreakNone;
-        else if ((delta[0] * delta[0] + delta[1] * delta[1]) + delta[2] * delta[2] < kDeltaNormThreshold) decision = kBreakDelta;
-        else if (error > prev_error) decision = kBreakError;
-        else Tn = transform_mul(transform_new(delta[0], delta[1], delta[2]), Ti);
+        double det, det_scale;
+        bool knife;
+        if (!solve_normal_equations_warp(jtj, jtr, delta, &det, &det_scale)) {
+            decision = kBreakNone;
+            knife = det_scale > 0. && gb.det > 0.;   // all-zero sums (sigma == 0 rows, lib.rs:245-247) are zero in any order
+        } else {
+            const double dd = (delta[0] * delta[0] + delta[1] * delta[1]) + delta[2] * delta[2];
+            knife = fabs(det) <= gb.det * det_scale || fabs(dd - kDeltaNormThreshold) <= gb.delta * kDeltaNormThreshold;
+            if (dd < kDeltaNormThreshold) {
+                decision = kBreakDelta;
+            } else {
+                knife = knife || fabs(error - prev_error) <= gb.err * fmax(error, prev_error);
+                if (error > prev_error) decision = kBreakError;
+                else Tn = transform_mul(transform_new(delta[0], delta[1], delta[2]), Ti);
+            }
+        }
+        if (lane == 0 && knife) ctl->knife = 1u;
         if (lane == 0) {
             ctl->bcast[0] = Tn.r00; ctl->bcast[1] = Tn.r01; ctl->bcast[2] = Tn.r10;
             ctl->bcast[3] = Tn.r11; ctl->bcast[4] = Tn.tx;  ctl->bcast[5] = Tn.ty;
@@ -448,6 +506,26 @@ ICP_DEV void cta_tree_reduce_solve(FusedCtl* ctl, double acc[16], const Transfor
         }
     }
     __syncthreads();
+}
+
+// Fixed-tree sum of one value per thread (xor butterfly across lanes, warps in warp order): the
+// tree-mode form of the final huber_error.  Every thread returns the total.  Two barriers; uses
+// ctl->red / ctl->bcast like cta_tree_reduce_solve.
+template <int NW>
+ICP_DEV double cta_tree_sum(FusedCtl* ctl, double v)
+{
+    const int lane = lane_id(), warp = warp_id();
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = v + shfl_xor_f64(v, m);
+    if (lane == 0) ctl->red[warp][0] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = ctl->red[0][0];
+        for (int w = 1; w < NW; ++w) tot = tot + ctl->red[w][0];
+        ctl->bcast[6] = tot;
+    }
+    __syncthreads();
+    return ctl->bcast[6];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -513,12 +591,13 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
     __syncthreads();
 
     for (;;) {
-        if (tid == 0) ctl->pair = p.pair_begin + atomicAdd(p.work_counter, 1u);
+        if (tid == 0) { ctl->pair = fused_next_pair(p); ctl->knife = 0u; }
         __syncthreads();
         const uint32_t pair = ctl->pair;
         if (pair >= p.pair_end) break;
-        const int n = (int)(p.src_off[pair + 1] - p.src_off[pair]);
-        const double* src = p.src + (size_t)p.src_off[pair] * DIM;
+        const uint32_t spair = p.shared_src ? 0u : pair;   // ICP_B200_FLAG_SHARED_SOURCE: one scan for every pair
+        const int n = (int)(p.src_off[spair + 1] - p.src_off[spair]);
+        const double* src = p.src + (size_t)p.src_off[spair] * DIM;
         int m;
         const double* dst = nullptr;
         if (SHARED_TARGET) {
@@ -551,6 +630,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                 if (p.out_status) p.out_status[pair] = status;
                 if (p.out_error) atomicMax(p.out_error, status);
                 if (p.out_hash) p.out_hash[pair] = 0ull;
+                if (p.out_cost) p.out_cost[pair] = 0.;
                 if (p.out_inner)
                     for (uint32_t it = 0; it < p.max_iter; ++it)
                         p.out_inner[(size_t)pair * p.max_iter + it] = 0u;
@@ -575,7 +655,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
         double est_med[2] = {0., 0.}, est_sigma[2] = {0., 0.};
         uint64_t H = 0;  // meaningful in thread 0
         const int npad = ((n + 2 * kChainUnroll - 1) / (2 * kChainUnroll)) * (2 * kChainUnroll);
-        const uint64_t corr_base = (uint64_t)p.src_off[pair] * (p.corr_mode == 2 ? p.max_iter : 1u);
+        const uint64_t corr_base = (p.shared_src ? (uint64_t)pair * (uint64_t)n : (uint64_t)p.src_off[pair]) *
+                                   (p.corr_mode == 2 ? p.max_iter : 1u);
 
         int ppos[PPT];   // sorted position of each point's match in the previous outer iteration (ordered mode)
 #pragma unroll
@@ -780,7 +861,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                             }
                         }
 // @region tree_reduce
-                        cta_tree_reduce_solve<NW>(ctl, acc, Ti, prev_error);
+                        cta_tree_reduce_solve<NW>(ctl, acc, Ti, prev_error, p.guard);
                         const uint32_t decision = (uint32_t)ctl->bcast[7];
                         if (decision != kBreakCap) { why = decision; break; }
                         prev_error = ctl->bcast[6];
@@ -804,6 +885,45 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                 }
             }
 // @region outer_tail
+            if (p.out_cost && it + 1 == p.max_iter) {
+                // huber_error (lib.rs:45-50) of the inner solve's final transform over this (the last)
+                // iteration's transformed source / matched target points
+                __syncthreads();   // every thread has read the last solve's sums / broadcast
+                if (ORDERED) {
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k) {
+                        const int i = tid + k * THREADS;
+                        if (i < npad) {
+                            double rh = 0.;
+                            if (i < n) {
+                                double tx_, ty_;
+                                transform_apply(Ti, sx[k], sy[k], &tx_, &ty_);
+                                const double rx = tx_ - dx[k], ry = ty_ - dy[k];
+                                rh = huber_rho(rx * rx + ry * ry);
+                            }
+                            rho[i] = rh;
+                        }
+                    }
+                    __syncthreads();
+                    if (warp == cost_warp) {
+                        const double e = npad > 0 ? cost_run(smem_ref_of(reinterpret_cast<const double2*>(rho)), npad / 2) : 0.;
+                        if (lane == 0) p.out_cost[pair] = e;
+                    }
+                } else {
+                    double e = 0.;
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k) {
+                        const int i = tid + k * THREADS;
+                        double tx_, ty_;
+                        transform_apply(Ti, sx[k], sy[k], &tx_, &ty_);
+                        const double rx = tx_ - dx[k], ry = ty_ - dy[k];
+                        const double rh = huber_rho(rx * rx + ry * ry);
+                        e = e + (i < n ? rh : 0.);
+                    }
+                    const double tot = cta_tree_sum<NW>(ctl, e);
+                    if (tid == 0) p.out_cost[pair] = tot;
+                }
+            }
             T = transform_mul(Ti, T);  // lib.rs:127
             if (tid == 0 && p.out_inner) p.out_inner[(size_t)pair * p.max_iter + it] = accepted | (why << 16);
             __syncthreads();  // rows are dead; next iteration restages the target
@@ -814,6 +934,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
             p.out_T[(size_t)pair * 6 + 4] = T.tx;  p.out_T[(size_t)pair * 6 + 5] = T.ty;
             if (p.out_status) p.out_status[pair] = kPairOk;
             if (p.out_hash) p.out_hash[pair] = H;
+            if (p.out_cost && p.max_iter == 0) p.out_cost[pair] = 0.;
+            if (!ORDERED) fused_report_knife(p, ctl, pair);
         }
         __syncthreads();  // ctl->pair is rewritten at the top of the loop
     }

@@ -446,12 +446,13 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
 
     for (;;) {
         ICP_LT_START
-        if (tid == 0) ctl->pair = p.pair_begin + atomicAdd(p.work_counter, 1u);
+        if (tid == 0) { ctl->pair = fused_next_pair(p); ctl->knife = 0u; }
         __syncthreads();
         const uint32_t pair = ctl->pair;
         if (pair >= p.pair_end) break;
-        const int n = (int)(p.src_off[pair + 1] - p.src_off[pair]);
-        const double* src = p.src + (size_t)p.src_off[pair] * DIM;
+        const uint32_t spair = p.shared_src ? 0u : pair;   // ICP_B200_FLAG_SHARED_SOURCE: one scan for every pair
+        const int n = (int)(p.src_off[spair + 1] - p.src_off[spair]);
+        const double* src = p.src + (size_t)p.src_off[spair] * DIM;
         int m;
         const double* dst = nullptr;
         if (SHARED_TARGET) {
@@ -484,6 +485,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                 if (p.out_status) p.out_status[pair] = status;
                 if (p.out_error) atomicMax(p.out_error, status);
                 if (p.out_hash) p.out_hash[pair] = 0ull;
+                if (p.out_cost) p.out_cost[pair] = 0.;
                 if (p.out_inner)
                     for (uint32_t it = 0; it < p.max_iter; ++it)
                         p.out_inner[(size_t)pair * p.max_iter + it] = 0u;
@@ -506,7 +508,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
         }
 
         uint64_t H = 0;  // meaningful in thread 0
-        const uint64_t corr_base = (uint64_t)p.src_off[pair] * (p.corr_mode == 2 ? p.max_iter : 1u);
+        const uint64_t corr_base = (p.shared_src ? (uint64_t)pair * (uint64_t)n : (uint64_t)p.src_off[pair]) *
+                                   (p.corr_mode == 2 ? p.max_iter : 1u);
 
         ICP_LT_MARK(0)
         for (uint32_t it = 0; it < p.max_iter; ++it) {
@@ -688,7 +691,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
 #ifdef ICP_LEAN_TIMING
                     ++lt_e;
 #endif
-                    cta_tree_reduce_solve<NW>(ctl, acc, Ti, prev_error);
+                    cta_tree_reduce_solve<NW>(ctl, acc, Ti, prev_error, p.guard);
                     ICP_LT_MARK(7)
                     const uint32_t decision = (uint32_t)ctl->bcast[7];
                     if (decision != kBreakCap) { why = decision; break; }
@@ -699,6 +702,23 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                 }
             }
 // @region lean_outer_tail
+            if (p.out_cost && it + 1 == p.max_iter) {
+                // huber_error (lib.rs:45-50) of the inner solve's final transform over this (the last)
+                // iteration's transformed source / matched target points
+                __syncthreads();   // every thread has read the last solve's broadcast
+                double e = 0.;
+#pragma unroll
+                for (int k = 0; k < PPT; ++k) {
+                    const int i = tid + k * THREADS;
+                    double tx_, ty_;
+                    transform_apply(Ti, sx[k], sy[k], &tx_, &ty_);
+                    const double rx = tx_ - dx[k], ry = ty_ - dy[k];
+                    const double rh = huber_rho(rx * rx + ry * ry);
+                    e = e + (i < n ? rh : 0.);
+                }
+                const double tot = cta_tree_sum<NW>(ctl, e);
+                if (tid == 0) p.out_cost[pair] = tot;
+            }
             T = transform_mul(Ti, T);  // lib.rs:127
             if (tid == 0 && p.out_inner) p.out_inner[(size_t)pair * p.max_iter + it] = accepted | (why << 16);
             __syncthreads();  // rows are rewritten by the next search; ctl->bcast by the next solve
@@ -709,6 +729,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
             p.out_T[(size_t)pair * 6 + 4] = T.tx;  p.out_T[(size_t)pair * 6 + 5] = T.ty;
             if (p.out_status) p.out_status[pair] = kPairOk;
             if (p.out_hash) p.out_hash[pair] = H;
+            if (p.out_cost && p.max_iter == 0) p.out_cost[pair] = 0.;
+            fused_report_knife(p, ctl, pair);
         }
         __syncthreads();  // ctl->pair is rewritten at the top of the loop
         ICP_LT_MARK(8)

@@ -10,15 +10,22 @@
 //   - per source point the transformed point and its matched target point (sx, sy | dx, dy).
 // Every Gauss-Newton evaluation streams that state: two exact selections (median, MAD; FAST map
 // with zoom, icp_cta.cuh) and one accumulation pass, reduced as the fixed warp tree of
-// cta_tree_reduce_solve.  Warp-tree sums only (the ordered chain would read 2n rows serially).
+// cta_tree_reduce_solve (default), or — StreamParams::ordered — in the reference's own order: the
+// row terms (lib.rs:242-255) go to the slab, tiles of kStreamTile points are staged in shared memory
+// (double buffered) and the chain warp of icp_fused.cuh adds them sequentially, carrying its twelve
+// accumulators from tile to tile.  That mode gives bit-identical transforms for scans of any size
+// (it is also the re-run path of large pairs the knife-edge guard flags).
 #pragma once
 #include "icp_fused.cuh"
 
 namespace icp {
 
+constexpr int kStreamTile = 256;   // points per shared-memory tile of the ordered chain
+
 struct StreamLayout {   // byte offsets inside one CTA's slab
     uint64_t s0, s1;                       // double2[n_cap] each
     uint64_t spos;                         // u32[n_cap]: sorted position of each point's previous match
+    uint64_t row_r, row_c, row_b, row_rho; // ordered mode: row terms, padded to whole tiles
     uint64_t gx, gy, gz, gidx, gslot;      // target copy sorted by cell
     uint64_t gcnt, gcstart;
     uint64_t total;
@@ -26,13 +33,19 @@ struct StreamLayout {   // byte offsets inside one CTA's slab
 
 ICP_HD uint64_t align256(uint64_t v) { return (v + 255ull) & ~255ull; }
 
-ICP_HD StreamLayout stream_layout(int dim, uint32_t n_cap, uint32_t m_cap, uint32_t c_cap, bool shared_target)
+ICP_HD StreamLayout stream_layout(int dim, uint32_t n_cap, uint32_t m_cap, uint32_t c_cap, bool shared_target,
+                                  bool ordered = false)
 {
     StreamLayout L;
     uint64_t o = 0;
     L.s0 = o; o = align256(o + 16ull * n_cap);
     L.s1 = o; o = align256(o + 16ull * n_cap);
     L.spos = o; o = align256(o + 4ull * n_cap);
+    const uint64_t n_pad = ordered ? ((uint64_t)n_cap + kStreamTile - 1) / kStreamTile * kStreamTile : 0ull;
+    L.row_r = o; o = align256(o + 16ull * n_pad);
+    L.row_c = o; o = align256(o + 16ull * n_pad);
+    L.row_b = o; o = align256(o + 16ull * n_pad);
+    L.row_rho = o; o = align256(o + 8ull * n_pad);
     if (shared_target) { m_cap = 0; c_cap = 0; }
     L.gx = o; o = align256(o + 8ull * m_cap);
     L.gy = o; o = align256(o + 8ull * m_cap);
@@ -49,7 +62,23 @@ struct StreamParams {
     FusedParams f;          // same batch description as the fused kernel (workspace/ws_stride = slabs)
     uint32_t n_cap, m_cap, c_cap;
     uint32_t cells_per_point;   // cell budget of a pair's own grid = cells_per_point * m, at most c_cap (0: 2)
+    uint32_t ordered;           // reference-order sums (ICP_B200_FLAG_ORDERED_SUMS) instead of the warp tree
 };
+
+// Shared-memory tile of the ordered chain: the row arrays of kStreamTile points at the 16-byte bank
+// phases chain_run's 128-bit loads expect (icp_fused.cuh fused_layout: r +0, b +16, c alone).
+struct StreamTileLayout { uint32_t r, b, c, rho, bytes; };
+ICP_HD StreamTileLayout stream_tile_layout()
+{
+    StreamTileLayout t;
+    uint32_t o = 0;
+    t.r = o; o = align128(o + 16u * kStreamTile);
+    t.b = o + 16u; o = align128(t.b + 16u * kStreamTile);
+    t.c = o; o = align128(o + 16u * kStreamTile);
+    t.rho = o; o = align128(o + 8u * kStreamTile);
+    t.bytes = o;
+    return t;
+}
 
 // residual keys recomputed from the streamed state (lib.rs:34-36)
 struct KeysStreamed {
@@ -68,7 +97,57 @@ struct KeysStreamed {
     }
 };
 
-constexpr uint32_t kStreamShared = (uint32_t)(((sizeof(SelShared) + 15u) & ~15u) + sizeof(FusedCtl));
+constexpr uint32_t kStreamSharedBase = (uint32_t)((((sizeof(SelShared) + 15u) & ~15u) + sizeof(FusedCtl) + 127u) & ~127u);
+// + ordered mode: two tiles and the constant table of the chain (K0 at phase +32, K1 at +48)
+ICP_HD uint32_t stream_smem_bytes(bool ordered)
+{
+    if (!ordered) return kStreamSharedBase;
+    return kStreamSharedBase + 2u * stream_tile_layout().bytes + align128(32u + 16u + 2u * 16u * (uint32_t)kChainUnroll);
+}
+constexpr uint32_t kStreamShared = kStreamSharedBase;
+
+// Reference-order sums of one Gauss-Newton evaluation (lib.rs:242-255, 45-50) over the row arrays in
+// the slab: tile t+1 is copied into shared memory while the chain warp (and the cost warp) consume
+// tile t.  On return ctl->sums[0..11] = jtj, jtr and ctl->sums[12] = cost, visible to every thread.
+// cost_only: only sums[12] (the final huber_error).  npad: a multiple of kStreamTile.
+template <int THREADS>
+ICP_DEV void stream_ordered_sums(unsigned char* tiles, const double2* ktab, const double2* R2, const double2* C2,
+                                 const double2* B2, const double* RHO, int npad, bool cost_only, FusedCtl* ctl)
+{
+    constexpr int NW = THREADS / 32;
+    const StreamTileLayout TL = stream_tile_layout();
+    const int tid = (int)threadIdx.x, lane = lane_id(), warp = warp_id();
+    const int ntiles = npad / kStreamTile;
+    auto copy_tile = [&](int t) {
+        unsigned char* buf = tiles + (size_t)(t & 1) * TL.bytes;
+        const size_t p0 = (size_t)t * kStreamTile;
+        for (int q = tid; q < kStreamTile; q += THREADS) {
+            if (!cost_only) {
+                reinterpret_cast<double2*>(buf + TL.r)[q] = R2[p0 + q];
+                reinterpret_cast<double2*>(buf + TL.b)[q] = B2[p0 + q];
+                reinterpret_cast<double2*>(buf + TL.c)[q] = C2[p0 + q];
+            }
+            reinterpret_cast<double*>(buf + TL.rho)[q] = RHO[p0 + q];
+        }
+    };
+    double acc = 0.0, cost = 0.0;
+    if (ntiles > 0) copy_tile(0);
+    __syncthreads();
+    for (int t = 0; t < ntiles; ++t) {
+        if (t + 1 < ntiles) copy_tile(t + 1);
+        const unsigned char* buf = tiles + (size_t)(t & 1) * TL.bytes;
+        if (warp == 0 && !cost_only)
+            acc = chain_run(chain_role(lane, reinterpret_cast<const double2*>(buf + TL.r), reinterpret_cast<const double2*>(buf + TL.c),
+                                       reinterpret_cast<const double2*>(buf + TL.b), ktab),
+                            kStreamTile / kChainStage, acc);
+        if (warp == (NW > 1 ? 1 : 0))
+            cost = cost_run(smem_ref_of(reinterpret_cast<const double2*>(buf + TL.rho)), kStreamTile / 2, cost);
+        __syncthreads();
+    }
+    if (warp == 0 && lane < 12 && !cost_only) ctl->sums[lane] = acc;
+    if (warp == (NW > 1 ? 1 : 0) && lane == 0) ctl->sums[12] = cost;
+    __syncthreads();
+}
 
 // CTA-wide exclusive scan of cnt[0..ncells) into cstart[0..ncells], one contiguous chunk per warp
 template <int THREADS>
@@ -104,23 +183,31 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, 1) icp_stream_kernel(StreamParams sp)
     SelShared* sel = reinterpret_cast<SelShared*>(smem);
     FusedCtl* ctl = reinterpret_cast<FusedCtl*>(smem + ((sizeof(SelShared) + 15u) & ~15u));
     const int tid = (int)threadIdx.x, lane = lane_id(), warp = warp_id();
-    const StreamLayout L = stream_layout(DIM, sp.n_cap, sp.m_cap, sp.c_cap, SHARED_TARGET);
+    const bool ordered = sp.ordered != 0;
+    const StreamLayout L = stream_layout(DIM, sp.n_cap, sp.m_cap, sp.c_cap, SHARED_TARGET, ordered);
     unsigned char* slab = p.workspace + (size_t)blockIdx.x * p.ws_stride;
     double2* S0 = reinterpret_cast<double2*>(slab + L.s0);
     double2* S1 = reinterpret_cast<double2*>(slab + L.s1);
     uint32_t* spos = reinterpret_cast<uint32_t*>(slab + L.spos);
+    double2* R2 = reinterpret_cast<double2*>(slab + L.row_r);
+    double2* C2 = reinterpret_cast<double2*>(slab + L.row_c);
+    double2* B2 = reinterpret_cast<double2*>(slab + L.row_b);
+    double* RHO = reinterpret_cast<double*>(slab + L.row_rho);
+    unsigned char* tiles = smem + kStreamSharedBase;
+    double2* ktab = reinterpret_cast<double2*>(tiles + 2u * stream_tile_layout().bytes + 32u);
 
     for (int q = tid; q < 2 * kSelHistPad; q += THREADS) (&sel->hist[0][0])[q] = 0u;
     int hist_par = 0;
     __syncthreads();
 
     for (;;) {
-        if (tid == 0) ctl->pair = p.pair_begin + atomicAdd(p.work_counter, 1u);
+        if (tid == 0) { ctl->pair = fused_next_pair(p); ctl->knife = 0u; }
         __syncthreads();
         const uint32_t pair = ctl->pair;
         if (pair >= p.pair_end) break;
-        const int n = (int)(p.src_off[pair + 1] - p.src_off[pair]);
-        const double* src = p.src + (size_t)p.src_off[pair] * DIM;
+        const uint32_t spair = p.shared_src ? 0u : pair;   // ICP_B200_FLAG_SHARED_SOURCE: one scan for every pair
+        const int n = (int)(p.src_off[spair + 1] - p.src_off[spair]);
+        const double* src = p.src + (size_t)p.src_off[spair] * DIM;
         int m;
         const double* dst = nullptr;
         if (SHARED_TARGET) {
@@ -152,6 +239,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, 1) icp_stream_kernel(StreamParams sp)
                 if (p.out_status) p.out_status[pair] = status;
                 if (p.out_error) atomicMax(p.out_error, status);
                 if (p.out_hash) p.out_hash[pair] = 0ull;
+                if (p.out_cost) p.out_cost[pair] = 0.;
                 if (p.out_inner)
                     for (uint32_t it = 0; it < p.max_iter; ++it) p.out_inner[(size_t)pair * p.max_iter + it] = 0u;
             }
@@ -231,7 +319,9 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, 1) icp_stream_kernel(StreamParams sp)
 
         double est_med[2] = {0., 0.}, est_sigma[2] = {0., 0.};
         uint64_t H = 0;  // meaningful in thread 0
-        const uint64_t corr_base = (uint64_t)p.src_off[pair] * (p.corr_mode == 2 ? p.max_iter : 1u);
+        const int npad = ((n + kStreamTile - 1) / kStreamTile) * kStreamTile;   // ordered mode: whole tiles
+        const uint64_t corr_base = (p.shared_src ? (uint64_t)pair * (uint64_t)n : (uint64_t)p.src_off[pair]) *
+                                   (p.corr_mode == 2 ? p.max_iter : 1u);
 
         for (uint32_t it = 0; it < p.max_iter; ++it) {
             // ---- transform (lib.rs:113-116 / transform_xy lib.rs:52-57) + correspondence search
@@ -278,6 +368,52 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, 1) icp_stream_kernel(StreamParams sp)
                     double sigma[2];
                     hist_par = cta_calc_stddevs<THREADS, 0>(sel, ks, n, est_med, est_sigma, hist_par, sigma);
                     const double g0 = 1. / sigma[0], g1 = 1. / sigma[1];
+                    if (ordered) {
+                        // row weights (lib.rs:245-250), Jacobian third column (lib.rs:176-184), Huber cost
+                        // terms (lib.rs:47-48) -> slab; zero rows pad the last tile (they add +0.0)
+                        for (int i = tid; i < npad; i += THREADS) {
+                            double2 rr, cc, bb;
+                            double rh = 0.;
+                            rr.x = 0.; rr.y = 0.; cc.x = 0.; cc.y = 0.; bb.x = 0.; bb.y = 0.;
+                            if (i < n) {
+                                const double2 s = S0[i];
+                                rr = ks.get(0, i);
+                                if (sigma[0] != 0.) cc.x = huber_drho_of_residual(rr.x) * g0;
+                                if (sigma[1] != 0.) cc.y = huber_drho_of_residual(rr.y) * g1;
+                                const double a0 = -s.y, a1 = s.x;
+                                bb.x = Ti.r00 * a0 + Ti.r01 * a1;
+                                bb.y = Ti.r10 * a0 + Ti.r11 * a1;
+                                rh = huber_rho(rr.x * rr.x + rr.y * rr.y);
+                            }
+                            R2[i] = rr; C2[i] = cc; B2[i] = bb; RHO[i] = rh;
+                        }
+                        if (tid < 2 * kChainUnroll) {
+                            double2 kv;
+                            if (tid < kChainUnroll) { kv.x = Ti.r00; kv.y = Ti.r10; }
+                            else { kv.x = Ti.r01; kv.y = Ti.r11; }
+                            ktab[tid < kChainUnroll ? tid : tid - kChainUnroll + kChainK1] = kv;
+                        }
+                        __syncthreads();
+                        stream_ordered_sums<THREADS>(tiles, ktab, R2, C2, B2, RHO, npad, false, ctl);
+                        double jtj[9], jtr[3], delta[3];
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) jtj[q] = ctl->sums[q];
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) jtr[q] = ctl->sums[9 + q];
+                        const double error = ctl->sums[12];
+                        __syncthreads();   // sums are rewritten by the next evaluation
+                        // solve + break tests + update: every thread, identically (lib.rs:67-81)
+                        if (!solve_normal_equations(jtj, jtr, delta)) { why = kBreakNone; break; }
+                        if ((delta[0] * delta[0] + delta[1] * delta[1]) + delta[2] * delta[2] < kDeltaNormThreshold) {
+                            why = kBreakDelta;
+                            break;
+                        }
+                        if (error > prev_error) { why = kBreakError; break; }
+                        prev_error = error;
+                        Ti = transform_mul(transform_new(delta[0], delta[1], delta[2]), Ti);
+                        ++accepted;
+                        continue;
+                    }
                     double acc[16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q) acc[q] = 0.;
@@ -285,13 +421,41 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, 1) icp_stream_kernel(StreamParams sp)
                         const double2 s = S0[i];
                         tree_accumulate_point(acc, Ti, s.x, s.y, ks.get(0, i), sigma, g0, g1);
                     }
-                    cta_tree_reduce_solve<NW>(ctl, acc, Ti, prev_error);
+                    cta_tree_reduce_solve<NW>(ctl, acc, Ti, prev_error, p.guard);
                     const uint32_t decision = (uint32_t)ctl->bcast[7];
                     if (decision != kBreakCap) { why = decision; break; }
                     prev_error = ctl->bcast[6];
                     Ti.r00 = ctl->bcast[0]; Ti.r01 = ctl->bcast[1]; Ti.r10 = ctl->bcast[2];
                     Ti.r11 = ctl->bcast[3]; Ti.tx = ctl->bcast[4];  Ti.ty = ctl->bcast[5];
                     ++accepted;
+                }
+            }
+            if (p.out_cost && it + 1 == p.max_iter) {
+                // huber_error (lib.rs:45-50) of the inner solve's final transform over this (the last)
+                // iteration's transformed source / matched target points
+                __syncthreads();
+                KeysStreamed kf;
+                kf.s0 = S0; kf.s1 = S1; kf.Ti = Ti;
+                if (ordered) {
+                    for (int i = tid; i < npad; i += THREADS) {
+                        double rh = 0.;
+                        if (i < n) {
+                            const double2 rr = kf.get(0, i);
+                            rh = huber_rho(rr.x * rr.x + rr.y * rr.y);
+                        }
+                        RHO[i] = rh;
+                    }
+                    __syncthreads();
+                    stream_ordered_sums<THREADS>(tiles, ktab, R2, C2, B2, RHO, npad, true, ctl);
+                    if (tid == 0) p.out_cost[pair] = npad > 0 ? ctl->sums[12] : 0.;
+                } else {
+                    double e = 0.;
+                    for (int i = tid; i < n; i += THREADS) {
+                        const double2 rr = kf.get(0, i);
+                        e = e + huber_rho(rr.x * rr.x + rr.y * rr.y);
+                    }
+                    const double tot = cta_tree_sum<NW>(ctl, e);
+                    if (tid == 0) p.out_cost[pair] = tot;
                 }
             }
             T = transform_mul(Ti, T);  // lib.rs:127
@@ -304,6 +468,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, 1) icp_stream_kernel(StreamParams sp)
             p.out_T[(size_t)pair * 6 + 4] = T.tx;  p.out_T[(size_t)pair * 6 + 5] = T.ty;
             if (p.out_status) p.out_status[pair] = kPairOk;
             if (p.out_hash) p.out_hash[pair] = H;
+            if (p.out_cost && p.max_iter == 0) p.out_cost[pair] = 0.;
+            if (!ordered) fused_report_knife(p, ctl, pair);
         }
         __syncthreads();
     }

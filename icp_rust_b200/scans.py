@@ -13,7 +13,6 @@ import os
 
 import numpy as np
 
-HUBER_K = 1.345  # src/lib.rs:28 via huber.rs
 
 
 def load_scan2d_txt(path):
@@ -86,41 +85,27 @@ def scan_chain(scans, max_iter=20, ctx=None, first=0, count=None):
     return transforms, np.array(path).reshape(-1, 2)
 
 
-def huber_error(T6, src_xy, matched_xy, k=HUBER_K):
-    """lib.rs:45-50: sum of rho(|T s - d|^2) with rho of huber.rs:6-15, for arrays of points."""
-    T6 = np.asarray(T6, dtype=np.float64).reshape(6)
-    s = np.asarray(src_xy, dtype=np.float64).reshape(-1, 2)
-    d = np.asarray(matched_xy, dtype=np.float64).reshape(-1, 2)
-    rx = (T6[0] * s[:, 0] + T6[1] * s[:, 1]) + T6[4] - d[:, 0]
-    ry = (T6[2] * s[:, 0] + T6[3] * s[:, 1]) + T6[5] - d[:, 1]
-    e = rx * rx + ry * ry
-    k2 = k * k
-    return float(np.where(e <= k2, e, 2.0 * k * np.sqrt(e) - k2).sum())
-
-
 def estimate_best_of(src, dst, initial_transforms, max_iter=20, ctx=None):
     """Multi-hypothesis front end: align `src` to `dst` from every initial transform
-    in ONE batched call, score each result with the reference's own cost — `huber_error` (lib.rs:45-50)
-    of the final transform over its nearest-neighbour correspondences — and return the best.
-    2-D.  Returns dict(best=index, T=(H,6) results, cost=(H,) scores, transform=Transform of the best)."""
+    in ONE batched call — one device target (Icp2d::new once), ONE copy of the scan
+    (ICP_B200_FLAG_SHARED_SOURCE), H initial transforms — and score each result with the cost the
+    loop itself minimises: `huber_error` (lib.rs:45-50) of the last inner solve over the last
+    iteration's correspondences, which the kernel returns in out_cost.  The best is an argmin over
+    that array.  2-D or 3-D.
+    Returns dict(best=index, T=(H,6) results, cost=(H,) scores, transform=Transform of the best)."""
     from . import Target, Transform, default_context
     ctx = ctx or default_context()
-    src = np.ascontiguousarray(src, dtype=np.float64).reshape(-1, 2)
-    dst = np.ascontiguousarray(dst, dtype=np.float64).reshape(-1, 2)
+    src = np.ascontiguousarray(src, dtype=np.float64)
+    dst = np.ascontiguousarray(dst, dtype=np.float64)
     T0 = np.ascontiguousarray([t.to_array() if isinstance(t, Transform) else np.asarray(t, dtype=np.float64).reshape(6)
                                for t in initial_transforms]).reshape(-1, 6)
-    H, n = T0.shape[0], src.shape[0]
-    tgt = Target(dst, ctx)   # one search structure for all hypotheses (Icp2d::new once)
+    tgt = Target(dst, ctx)
     try:
-        off = (np.arange(H + 1, dtype=np.uint64) * n).astype(np.uint32)
-        res = tgt.estimate_batch(np.tile(src, (H, 1)), off, T0, max_iter, want_inner=False, want_hash=False)
-        T = res["T"]
-        moved = np.empty((H, n, 2))
-        moved[:, :, 0] = T[:, None, 0] * src[None, :, 0] + T[:, None, 1] * src[None, :, 1] + T[:, None, 4]
-        moved[:, :, 1] = T[:, None, 2] * src[None, :, 0] + T[:, None, 3] * src[None, :, 1] + T[:, None, 5]
-        idx = tgt.search(moved.reshape(-1, 2)).reshape(H, n)
+        res = tgt.estimate_batch(src, np.array([0, src.shape[0]], dtype=np.uint32), T0, max_iter, want_inner=False,
+                                 want_hash=False, want_cost=True, shared_source=True)
     finally:
         tgt.close()
-    cost = np.array([huber_error(T[h], src, dst[idx[h]]) for h in range(H)])
+    cost = res["cost"]
     best = int(np.argmin(cost))
-    return {"best": best, "T": T, "cost": cost, "transform": Transform.from_array(T[best]), "status": res["status"]}
+    return {"best": best, "T": res["T"], "cost": cost, "transform": Transform.from_array(res["T"][best]),
+            "status": res["status"]}

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ICP_B200_ABI_VERSION 2
+#define ICP_B200_ABI_VERSION 3
 
 typedef enum {
     ICP_B200_OK = 0,
@@ -61,14 +61,28 @@ typedef enum {
 
 /* icp_b200_batch.flags
  * Default (0): the normal-equation sums J^T W J, J^T W r and the Huber cost are reduced with warp
- * shuffles in a fixed order.  Correspondences and inner iteration counts equal the reference's
- * unless a break test (src/lib.rs:71,76) lands within summation rounding (~1e-13 relative) of its
- * threshold; transforms agree to ~1e-14, far inside the 1e-9 contract.  Results are deterministic
- * (independent of scheduling) but depend on the kernel instance chosen for the scan size.
+ * shuffles in a fixed order; they differ from the reference's sequential fold by summation rounding
+ * (~1e-16 relative), so transforms agree to ~1e-13, far inside the 1e-9 contract.  The inner loop's
+ * decisions (det == 0 src/linalg.rs:18, delta.dot(delta) < 1e-6 src/lib.rs:71, error > prev_error
+ * src/lib.rs:76) are discontinuous, so they are GUARDED: a pair with a decision quantity within a
+ * relative band of its threshold (1e-10 for det and the error test, 1e-6 for the delta test — bands
+ * at least a thousand times wider than the perturbation a different summation order can cause) is
+ * re-run by the library, inside the same call, with ORDERED_SUMS.  Iteration counts and
+ * correspondences therefore equal the ordered mode's: a pair either took every decision with a
+ * margin the summation order cannot bridge, or was recomputed in the reference's order.
+ * icp_b200_call_info.redo_pairs counts the re-runs (about 1 pair in 1000 on BASELINE config 2).
+ * Results are deterministic (independent of scheduling) but, for unflagged pairs, depend in their
+ * last bits on the kernel instance chosen for the scan size.
  * ORDERED_SUMS: every sum is accumulated in the reference's own order (src/lib.rs:242-255,45-50):
- * transforms are bit-identical to the reference arithmetic by construction, at roughly half the
- * throughput. */
+ * transforms are bit-identical to the reference arithmetic by construction, at roughly a third of
+ * the throughput.  Any scan size (large scans stream their row terms through shared-memory tiles).
+ * NO_GUARD: default mode without the guard and the re-run (measurement / diagnosis only).
+ * SHARED_SOURCE: every pair aligns the SAME source scan src[0 .. src_off[1]) (src_off then holds
+ * two entries) — the multi-hypothesis form: one scan, `batch` initial transforms, no copies.
+ * out_corr (if any) is laid out as if the scan were repeated: pair b starts at b * n. */
 #define ICP_B200_FLAG_ORDERED_SUMS 1u
+#define ICP_B200_FLAG_SHARED_SOURCE 2u
+#define ICP_B200_FLAG_NO_GUARD 4u
 
 typedef struct icp_b200_context icp_b200_context;
 typedef struct icp_b200_target icp_b200_target;
@@ -95,6 +109,10 @@ typedef struct {
                                 iteration's correspondences (definition in DESIGN.md) */
     int32_t *out_status;     /* nullable [B]: ICP_B200_PAIR_* */
     uint32_t flags;          /* ICP_B200_FLAG_* */
+    double *out_cost;        /* nullable [B]: huber_error (src/lib.rs:45-50) of the last inner solve's
+                                transform over the last outer iteration's transformed source points and
+                                their matched target points — the cost the loop itself minimises; 0 for
+                                rejected pairs and max_iter == 0 */
 } icp_b200_batch;
 
 /* counters of the most recent compute call on a context */
@@ -104,6 +122,7 @@ typedef struct {
     uint64_t h2d_bytes;        /* bytes the call copied host -> device */
     uint64_t d2h_bytes;        /* bytes the call copied device -> host */
     uint32_t grid_ctas, block_threads, smem_bytes; /* launch shape of the ICP kernel */
+    uint32_t redo_pairs;       /* pairs the knife-edge guard re-ran with ordered sums (synchronous calls) */
 } icp_b200_call_info;
 
 int icp_b200_abi_version(void);

@@ -33,6 +33,30 @@ extern "C" int simt_set_schedule(int mode)
     return 0;
 }
 
+// Options of the next simt_icp_fused / simt_icp_stream calls (the host library's per-call state):
+// guard_scale > 0: tree-mode runs use the knife-edge guard with the library's bands times that
+// scale and re-run flagged pairs with ordered sums, exactly as icp_b200.cu's launch_range does;
+// out_cost: where the final huber_error goes; stream_ordered: reference-order sums in the
+// streaming kernel; shared_src: ICP_B200_FLAG_SHARED_SOURCE.
+static double g_guard_scale = 0.0, g_band_delta_scale = 1.0;
+static double* g_out_cost = nullptr;
+static int g_stream_ordered = 0, g_shared_src = 0;
+static uint32_t g_last_redo = 0;
+extern "C" void simt_set_options(double guard_scale, double* out_cost, int stream_ordered, int shared_src,
+                                 double delta_band_scale)
+{
+    g_guard_scale = guard_scale; g_out_cost = out_cost; g_stream_ordered = stream_ordered; g_shared_src = shared_src;
+    g_band_delta_scale = delta_band_scale;   // extra factor on the delta band only (tests isolate the error band with it)
+}
+extern "C" uint32_t simt_last_redo_count() { return g_last_redo; }
+static void apply_guard(FusedParams& p, std::vector<uint32_t>& list, uint32_t* count, uint32_t B)
+{
+    list.assign(B + 1, 0u);
+    *count = 0;
+    p.redo_list = list.data(); p.redo_count = count;
+    p.guard.det = 1e-10 * g_guard_scale; p.guard.delta = 1e-6 * g_guard_scale * g_band_delta_scale; p.guard.err = 1e-10 * g_guard_scale;
+}
+
 // Same argument meaning as icp_b200_batch.  variant: 0 -> 128 threads x 3 points, 1 -> 128 x 9,
 // 2 -> 64 x 2 (tiny), 3 -> 32 x 4 (single warp).
 extern "C" int simt_icp_fused(int dim, int variant, unsigned grid, const double* src, const uint32_t* src_off,
@@ -51,20 +75,38 @@ extern "C" int simt_icp_fused(int dim, int variant, unsigned grid, const double*
     p.out_status = out_status; p.out_error = &err; p.work_counter = &counter;
     p.pair_begin = 0; p.pair_end = B; p.max_iter = max_iter; p.corr_mode = corr_mode;
     p.cell_budget = cell_budget; p.mcap = mcap; p.sm_count = 1;
+    p.out_cost = g_out_cost; p.shared_src = (uint32_t)g_shared_src;
     const FusedLayout L = fused_layout(dim, 128 * 9, mcap, cell_budget, false, true);
     std::vector<unsigned char> ws((size_t)grid * (L.nn_bytes + 64));
     p.workspace = ws.data();
     p.ws_stride = L.nn_bytes + 64 - ((L.nn_bytes + 64) % 16);
-    if (dim == 2) {
-        if (variant == 0) { p.ncap = 384; run_fused<128, 3, 2>(p, grid, ordered); }
-        else if (variant == 1) { p.ncap = 1152; run_fused<128, 9, 2>(p, grid, ordered); }
-        else if (variant == 2) { p.ncap = 128; run_fused<64, 2, 2>(p, grid, ordered); }
-        else { p.ncap = 128; run_fused<32, 4, 2>(p, grid, ordered); }
-    } else {
-        if (variant == 0) { p.ncap = 384; run_fused<128, 3, 3>(p, grid, ordered); }
-        else if (variant == 1) { p.ncap = 1152; run_fused<128, 9, 3>(p, grid, ordered); }
-        else if (variant == 2) { p.ncap = 128; run_fused<64, 2, 3>(p, grid, ordered); }
-        else { p.ncap = 128; run_fused<32, 4, 3>(p, grid, ordered); }
+    std::vector<uint32_t> redo_list;
+    uint32_t redo_count = 0, counter2 = 0;
+    const bool guard = g_guard_scale > 0.0 && ordered != 1;
+    if (guard) apply_guard(p, redo_list, &redo_count, B);
+    auto run = [&](const FusedParams& q, int mode) {
+        FusedParams r = q;
+        if (dim == 2) {
+            if (variant == 0) { r.ncap = 384; run_fused<128, 3, 2>(r, grid, mode); }
+            else if (variant == 1) { r.ncap = 1152; run_fused<128, 9, 2>(r, grid, mode); }
+            else if (variant == 2) { r.ncap = 128; run_fused<64, 2, 2>(r, grid, mode); }
+            else { r.ncap = 128; run_fused<32, 4, 2>(r, grid, mode); }
+        } else {
+            if (variant == 0) { r.ncap = 384; run_fused<128, 3, 3>(r, grid, mode); }
+            else if (variant == 1) { r.ncap = 1152; run_fused<128, 9, 3>(r, grid, mode); }
+            else if (variant == 2) { r.ncap = 128; run_fused<64, 2, 3>(r, grid, mode); }
+            else { r.ncap = 128; run_fused<32, 4, 3>(r, grid, mode); }
+        }
+    };
+    run(p, ordered);
+    g_last_redo = 0;
+    if (guard) {   // the ordered re-run of the flagged pairs (icp_b200.cu launch_range)
+        FusedParams r = p;
+        r.pair_list = redo_list.data(); r.pair_count = &redo_count;
+        r.redo_list = nullptr; r.redo_count = nullptr; r.guard = GuardBands{0., 0., 0.};
+        r.work_counter = &counter2;
+        run(r, 1);
+        g_last_redo = redo_count;
     }
     return err;
 }
@@ -73,7 +115,7 @@ extern "C" int simt_icp_fused(int dim, int variant, unsigned grid, const double*
 template <int THREADS, int DIM>
 static void run_stream(StreamParams sp, unsigned grid)
 {
-    simt::launch(grid, THREADS, kStreamShared, [&] { icp_stream_kernel<THREADS, DIM, false>(sp); });
+    simt::launch(grid, THREADS, stream_smem_bytes(sp.ordered != 0), [&] { icp_stream_kernel<THREADS, DIM, false>(sp); });
 }
 
 extern "C" int simt_icp_stream(int dim, int threads, unsigned grid, const double* src, const uint32_t* src_off,
@@ -97,18 +139,37 @@ extern "C" int simt_icp_stream(int dim, int threads, unsigned grid, const double
     p.out_status = out_status; p.out_error = &err; p.work_counter = &counter;
     p.pair_begin = 0; p.pair_end = B; p.max_iter = max_iter; p.corr_mode = corr_mode; p.sm_count = 1;
     sp.n_cap = ncap; sp.m_cap = mcap; sp.c_cap = std::max(64u, 2u * mcap);
-    const StreamLayout L = stream_layout(dim, sp.n_cap, sp.m_cap, sp.c_cap, false);
+    p.out_cost = g_out_cost; p.shared_src = (uint32_t)g_shared_src;
+    const StreamLayout L = stream_layout(dim, sp.n_cap, sp.m_cap, sp.c_cap, false, true);
     std::vector<unsigned char> ws((size_t)grid * L.total + 256, 0xCD);
     p.workspace = ws.data();
     p.ws_stride = L.total;
-    if (dim == 2) {
-        if (threads == 32) run_stream<32, 2>(sp, grid);
-        else if (threads == 64) run_stream<64, 2>(sp, grid);
-        else run_stream<128, 2>(sp, grid);
-    } else {
-        if (threads == 32) run_stream<32, 3>(sp, grid);
-        else if (threads == 64) run_stream<64, 3>(sp, grid);
-        else run_stream<128, 3>(sp, grid);
+    std::vector<uint32_t> redo_list;
+    uint32_t redo_count = 0, counter2 = 0;
+    const bool guard = g_guard_scale > 0.0 && !g_stream_ordered;
+    if (guard) apply_guard(p, redo_list, &redo_count, B);
+    auto run = [&](StreamParams q) {
+        if (dim == 2) {
+            if (threads == 32) run_stream<32, 2>(q, grid);
+            else if (threads == 64) run_stream<64, 2>(q, grid);
+            else run_stream<128, 2>(q, grid);
+        } else {
+            if (threads == 32) run_stream<32, 3>(q, grid);
+            else if (threads == 64) run_stream<64, 3>(q, grid);
+            else run_stream<128, 3>(q, grid);
+        }
+    };
+    sp.ordered = (uint32_t)g_stream_ordered;
+    run(sp);
+    g_last_redo = 0;
+    if (guard) {
+        StreamParams r = sp;
+        r.ordered = 1u;
+        r.f.pair_list = redo_list.data(); r.f.pair_count = &redo_count;
+        r.f.redo_list = nullptr; r.f.redo_count = nullptr; r.f.guard = GuardBands{0., 0., 0.};
+        r.f.work_counter = &counter2;
+        run(r);
+        g_last_redo = redo_count;
     }
     return err;
 }

@@ -25,6 +25,30 @@ def set_schedule(mode):
     lib().simt_set_schedule(C.c_int(mode))
 
 
+_cost_buf = None
+
+
+def set_options(guard_scale=0.0, want_cost=0, stream_ordered=False, shared_src=False, delta_band_scale=1.0):
+    """Per-call state of the host library for the next icp_fused / icp_stream calls: knife-edge guard
+    (bands x guard_scale, flagged pairs re-run with ordered sums), a final-cost output of `want_cost`
+    pairs (read it back with last_cost()), reference-order sums in the streaming kernel,
+    ICP_B200_FLAG_SHARED_SOURCE."""
+    global _cost_buf
+    _cost_buf = np.full(want_cost, np.nan) if want_cost else None
+    lib().simt_set_options(C.c_double(guard_scale), _cost_buf.ctypes.data_as(_dp) if want_cost else None,
+                           C.c_int(1 if stream_ordered else 0), C.c_int(1 if shared_src else 0),
+                           C.c_double(delta_band_scale))
+
+
+def last_cost():
+    return _cost_buf
+
+
+def last_redo_count():
+    lib().simt_last_redo_count.restype = C.c_uint32
+    return int(lib().simt_last_redo_count())
+
+
 def calc_stddevs(sets, mode=0, threads=128):
     """sets: list of (n,2) arrays -> (sigma (B,2), median (B,2)); sigma < 0 means None"""
     off = np.zeros(len(sets) + 1, dtype=np.uint32)

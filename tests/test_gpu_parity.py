@@ -209,11 +209,11 @@ def test_status_codes_instead_of_panics(ctx, icp):
         assert np.array_equal(g["T"][b], T0[b], equal_nan=True)
     with pytest.raises(icp.IcpError):
         _run(ctx, icp, srcs, dsts, T0, 2)
-    # above 3072 source points only the streaming kernel (warp-tree sums) holds a scan
+    # above 3072 source points the streaming kernel holds a scan, in both reduction modes
     big = rng.normal(0, 100, (3073, 2))
-    with pytest.raises(icp.IcpError) as e:
-        _run(ctx, icp, [big], [big + 0.25], [I6], 1, ordered=True)
-    assert e.value.status == icp.ERR_TOO_LARGE
+    g = _run(ctx, icp, [big], [big + 0.25], [I6], 1, ordered=True)
+    assert ctx.call_info()["block_threads"] == 512
+    _check_vs_oracle(g, [big], [big + 0.25], [I6], 1, ordered=True)
     g = _run(ctx, icp, [big], [big + 0.25], [I6], 1)
     assert ctx.call_info()["block_threads"] == 512
     _check_vs_oracle(g, [big], [big + 0.25], [I6], 1, ordered=False)
@@ -386,7 +386,9 @@ def test_scan_chain_driver_3d(ctx, icp, scans3d):
 
 
 def test_multi_hypothesis_front_end(ctx, icp, scans2d):
-    """many initial transforms for one pair in one batch, scored with lib.rs:45-50."""
+    """many initial transforms for one pair in one batch (one copy of the scan,
+    ICP_B200_FLAG_SHARED_SOURCE), each scored on the device with the loop's own cost (lib.rs:45-50,
+    icp_b200_batch.out_cost); the oracle's final_cost is the same quantity."""
     from icp_rust_b200 import scans as S
     src, dst = scans2d[10], scans2d[12]
     inits = [I6, oracle.transform_new([30., -20., 0.02]), oracle.transform_new([-60., 45., -0.05]),
@@ -396,11 +398,78 @@ def test_multi_hypothesis_front_end(ctx, icp, scans2d):
     for h, T0 in enumerate(inits):
         o = oracle.icp_estimate(src, dst, T0, 20, nn_mode=oracle.NN_KDTREE)
         assert np.abs(r["T"][h] - o["T"]).max() <= 1e-9
-        moved = np.array([oracle.transform_apply(o["T"], p) for p in src])
-        m = dst[oracle.nn_search(dst, moved, oracle.NN_BRUTE)]
-        costs.append(oracle.huber_error(o["T"], src, m))
-    assert np.allclose(r["cost"], costs, rtol=1e-6)
+        costs.append(o["cost"])
+    assert np.allclose(r["cost"], costs, rtol=1e-9, atol=0)
     assert r["best"] == int(np.argmin(costs))
+    # bit-exact in ordered mode, shared source == repeated source, every kernel family
+    off = np.array([0, len(src)], np.uint32)
+    T0 = np.array(inits)
+    t = icp.Target(dst, ctx)
+    a = t.estimate_batch(src, off, T0, 20, ordered=True, want_cost=True, shared_source=True, corr_mode=icp.CORR_LAST)
+    b = t.estimate_batch(np.tile(src, (4, 1)), (np.arange(5) * len(src)).astype(np.uint32), T0, 20, ordered=True,
+                         want_cost=True, corr_mode=icp.CORR_LAST)
+    t.close()
+    for k in ("T", "inner", "corr_hash", "cost", "corr"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["cost"], costs)
+    c = ctx.estimate_batch(src, off, np.tile(dst, (4, 1)), (np.arange(5) * len(dst)).astype(np.uint32), T0, 20,
+                           ordered=True, want_cost=True, shared_source=True)
+    assert np.array_equal(c["T"], a["T"]) and np.array_equal(c["cost"], a["cost"])
+
+
+def test_final_cost_every_kernel(ctx, icp, frames3d_20):
+    """out_cost against the oracle's final huber_error: lean / fused / streaming kernels, both modes."""
+    B = 12
+    src, dst, off, _ = icp.synth_scan_pairs(B, beams=1080, first_pair=31337)
+    T0 = np.tile(I6, (B, 1))
+    o = oracle.icp_estimate_batch(2, src, off, dst, off, T0, 20, want_cost=True)
+    g = ctx.estimate_batch(src, off, dst, off, T0, 20, want_cost=True)
+    assert np.allclose(g["cost"], o["cost"], rtol=1e-11, atol=0)
+    g = ctx.estimate_batch(src, off, dst, off, T0, 20, want_cost=True, ordered=True)
+    assert np.array_equal(g["cost"], o["cost"]) and np.array_equal(g["T"], o["T"])
+    from icp_rust_b200.workloads import config4_pairs
+    src, dst, off, T0 = config4_pairs(3, frames=frames3d_20)
+    o = oracle.icp_estimate_batch(3, src, off, dst, off, T0, 5, want_cost=True)
+    g = ctx.estimate_batch(src, off, dst, off, T0, 5, dim=3, want_cost=True)
+    assert np.allclose(g["cost"], o["cost"], rtol=1e-11, atol=0)
+    g = ctx.estimate_batch(src, off, dst, off, T0, 5, dim=3, want_cost=True, ordered=True)   # tiled ordered chain
+    assert np.array_equal(g["cost"], o["cost"]) and np.array_equal(g["T"], o["T"])
+    assert np.array_equal(g["inner"], o["inner"]) and np.array_equal(g["corr_hash"], o["corr_hash"])
+
+
+def test_knife_edge_guard_reruns_flagged_pairs(icp):
+    """The default mode with its guard bands forced wide (ICP_B200_GUARD_SCALE): every pair is
+    flagged and re-run with ordered sums inside the same call, so the results are BIT-identical to
+    the oracle; with the real bands a few pairs in a thousand are re-run and every inner iteration
+    count / correspondence checksum of 2048 pairs equals the oracle's; with the guard off the same
+    call leaves the tree results."""
+    B = 2048
+    src, dst, off, _ = icp.synth_scan_pairs(B, beams=1080, first_pair=500000)
+    T0 = np.tile(I6, (B, 1))
+    o = oracle.icp_estimate_batch(2, src, off, dst, off, T0, 20, nn_mode=oracle.NN_KDTREE, want_margins=True)
+    os.environ["ICP_B200_GUARD_SCALE"] = "1e9"
+    try:
+        c = icp.Context(0)
+    finally:
+        os.environ.pop("ICP_B200_GUARD_SCALE")
+    n = 256
+    g = c.estimate_batch(src[:n * 1080], off[:n + 1], dst[:n * 1080], off[:n + 1], T0[:n], 20)
+    assert g["redo_pairs"] == n
+    assert np.array_equal(g["T"], o["T"][:n]) and np.array_equal(g["inner"], o["inner"][:n])
+    assert np.array_equal(g["corr_hash"], o["corr_hash"][:n])
+    c.close()
+    c = icp.Context(0)
+    g = c.estimate_batch(src, off, dst, off, T0, 20)
+    assert np.array_equal(g["inner"], o["inner"]) and np.array_equal(g["corr_hash"], o["corr_hash"])
+    assert np.abs(g["T"] - o["T"]).max() <= TOL
+    # every pair whose tightest error test lies inside the band was re-run (and is bit-identical)
+    inside = np.flatnonzero(o["margins"][:, 1] < 0.5e-10)
+    assert g["redo_pairs"] >= len(inside)
+    assert all(np.array_equal(g["T"][b], o["T"][b]) for b in inside)
+    assert g["redo_pairs"] <= B // 20, "the guard should re-run a few pairs per thousand, not a large share"
+    g2 = c.estimate_batch(src, off, dst, off, T0, 20, guard=False)
+    assert g2["redo_pairs"] == 0
+    c.close()
 
 
 def test_config3_queries_full_map(ctx, icp):

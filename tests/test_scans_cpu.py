@@ -1,5 +1,5 @@
 """Host-side pieces of the scan-chain driver and the multi-hypothesis front end (no GPU):
-loaders as the reference's examples parse their recordings, Transform::inverse, huber_error."""
+loaders as the reference's examples parse their recordings, Transform::inverse."""
 import os
 
 import numpy as np
@@ -30,15 +30,10 @@ def test_fixture_matches_recording_shape():
     assert len(S.remove_invalid_values([[0.1, 0.1, 0.1], [0.2, 0., 0.], [1., 0., 0.]])) == 1
 
 
-def test_inverse_and_huber_error_follow_the_reference():
-    rng = np.random.default_rng(3)
+def test_inverse_follows_the_reference():
     T = oracle.transform_new([120.0, -35.0, 0.3])
     Ti = Transform.from_array(T).inverse()                       # transform.rs:26-32
     assert np.allclose(Ti.to_array(), oracle.transform_inverse(T), rtol=0, atol=1e-12)
-    src = rng.normal(0, 500, (200, 2))
-    dst = src @ T[:4].reshape(2, 2).T + T[4:] + rng.normal(0, 2.0, (200, 2))
-    dst[::7] += 40.0                                             # outliers: the linear branch of rho
-    assert abs(S.huber_error(T, src, dst) - oracle.huber_error(T, src, dst)) <= 1e-9 * oracle.huber_error(T, src, dst)
 
 
 def test_examples_exist_and_parse():

@@ -306,3 +306,133 @@ def test_target_search_random_geometries():
         exp = oracle.nn_search(d, q, oracle.NN_BRUTE)
         cpp = float(10.0 ** rng.uniform(0, 2))
         assert np.array_equal(E.target_search(d, q, budget=max(64, int(m * cpp)), fast=True), exp), f"trial {trial}"
+
+
+# ------------------------------------------------------------------------------------------------
+# Knife-edge guard (GuardBands, icp_fused.cuh) + ordered re-run, final cost, ordered streaming sums
+def _noisy_pairs(B, n, seed, dim=2):
+    rng = np.random.default_rng(seed)
+    srcs, dsts = [], []
+    for _ in range(B):
+        a = rng.uniform(-300, 300, (n, dim))
+        if dim == 3:
+            a[:, 2] *= 0.1
+        T = oracle.transform_new([rng.uniform(-4, 4), rng.uniform(-4, 4), rng.uniform(-0.01, 0.01)])
+        d = a.copy()
+        d[:, :2] = a[:, :2] @ T[:4].reshape(2, 2).T + T[4:]
+        d += rng.normal(0, 0.7, d.shape)
+        srcs.append(a)
+        dsts.append(d[rng.permutation(n)])
+    return srcs, dsts
+
+
+@pytest.mark.parametrize("mode", [False, "lean"])
+def test_knife_edge_guard_forced_band(mode):
+    """Guard bands blown up by 1e9 (every decision is 'inside the band'): every pair that takes a
+    decision is flagged and re-run with ordered sums, so the whole batch becomes BIT-identical to the
+    oracle although the first pass used tree reductions.  With the real bands nothing on this
+    batch is flagged and the tree results stand."""
+    srcs, dsts = _noisy_pairs(5, 150, 21)
+    T0 = [I6] * 5
+    refs = _oracle_ref(srcs, dsts, T0, 4)
+    try:
+        E.set_options(guard_scale=1e9)
+        g = E.icp_fused(srcs, dsts, T0, 4, variant=0, grid=2, ordered=mode)
+        assert E.last_redo_count() == 5
+        _compare(g, refs, srcs, 4, ordered=True)
+        E.set_options(guard_scale=1.0)
+        g = E.icp_fused(srcs, dsts, T0, 4, variant=0, grid=2, ordered=mode)
+        assert E.last_redo_count() == 0
+        _compare(g, refs, srcs, 4, ordered=False)
+    finally:
+        E.set_options()
+
+
+def test_knife_edge_guard_partial_band():
+    """A band between the pairs' own margins: only the pairs whose tightest decision lies inside it
+    are re-run (bit-identical); the others keep their tree result (within 1e-9)."""
+    srcs, dsts = _noisy_pairs(8, 120, 33)
+    T0 = [I6] * 8
+    refs = _oracle_ref(srcs, dsts, T0, 5)
+    so = np.zeros(9, np.uint32); so[1:] = np.cumsum([len(s) for s in srcs])
+    o = oracle.icp_estimate_batch(2, np.concatenate(srcs), so, np.concatenate(dsts), so, np.array(T0), 5,
+                                  nn_mode=oracle.NN_BRUTE, want_margins=True)
+    err_m = np.sort(o["margins"][:, 1])
+    band = float(np.sqrt(err_m[3] * err_m[4]))          # half of the pairs have an error test inside it
+    try:
+        E.set_options(guard_scale=band / 1e-10, delta_band_scale=1e-10 / band)   # delta band stays 1e-6
+        g = E.icp_fused(srcs, dsts, T0, 5, variant=0, grid=3, ordered="lean")
+        flagged = E.last_redo_count()
+    finally:
+        E.set_options()
+    assert 4 <= flagged < 8     # the det band (scaled alike) may add pairs, never remove any
+    _compare(g, refs, srcs, 5, ordered=False)
+    exact = sum(np.array_equal(g["T"][b], refs[b]["T"]) for b in range(8))
+    assert exact >= flagged
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_streaming_kernel_ordered_sums(dim):
+    """Reference-order sums in the large-scan kernel (tiles of 256 points through shared memory, the
+    chain's accumulators carried across tiles): bit-identical to the oracle, 1 to 3 tiles + ragged."""
+    srcs, dsts = _noisy_pairs(3, 300, 5, dim=dim)
+    srcs[1], dsts[1] = srcs[1][:256], dsts[1][:256]      # exactly one tile
+    srcs[2], dsts[2] = np.concatenate([srcs[2], srcs[0] + 3.0]), np.concatenate([dsts[2], dsts[0] + 3.0])  # 600 -> 3 tiles
+    T0 = [I6] * 3
+    refs = _oracle_ref(srcs, dsts, T0, 3)
+    try:
+        E.set_options(stream_ordered=True, want_cost=3)
+        for threads in (32, 64):
+            g = E.icp_stream(srcs, dsts, T0, 3, threads=threads, grid=2)
+            _compare(g, refs, srcs, 3, ordered=True)
+            assert np.array_equal(E.last_cost(), [r["cost"] for r in refs])
+        # and as the re-run path of the guard
+        E.set_options(guard_scale=1e9)
+        g = E.icp_stream(srcs, dsts, T0, 3, threads=64, grid=1)
+        assert E.last_redo_count() == 3
+        _compare(g, refs, srcs, 3, ordered=True)
+    finally:
+        E.set_options()
+
+
+@pytest.mark.parametrize("mode", [True, False, "lean"])
+def test_final_cost_output(mode):
+    """out_cost = huber_error (lib.rs:45-50) of the last inner solve: bit-identical with ordered sums,
+    ~1e-13 relative with the tree; 0 for max_iter == 0; degenerate pairs (n < 2)."""
+    srcs, dsts = _noisy_pairs(4, 90, 8)
+    srcs.append(srcs[0][:1]); dsts.append(dsts[0])
+    T0 = [I6] * 5
+    refs = _oracle_ref(srcs, dsts, T0, 3)
+    try:
+        E.set_options(want_cost=5)
+        E.icp_fused(srcs, dsts, T0, 3, variant=0, grid=2, ordered=mode)
+        cost = E.last_cost().copy()
+        E.set_options(want_cost=5)
+        E.icp_fused(srcs, dsts, T0, 0, variant=0, grid=2, ordered=mode)
+        assert np.array_equal(E.last_cost(), np.zeros(5))
+    finally:
+        E.set_options()
+    exp = np.array([r["cost"] for r in refs])
+    if mode is True:
+        assert np.array_equal(cost, exp)
+    else:
+        assert np.allclose(cost, exp, rtol=1e-12, atol=0)
+
+
+def test_shared_source_batch():
+    """ICP_B200_FLAG_SHARED_SOURCE: one scan, several initial transforms — same results as the scan
+    repeated per pair."""
+    srcs, dsts = _noisy_pairs(1, 140, 12)
+    inits = [I6, oracle.transform_new([2., -1., 0.004]), oracle.transform_new([-3., 2., -0.006])]
+    refs = _oracle_ref(srcs * 3, dsts * 3, inits, 4)
+    g_rep = E.icp_fused(srcs * 3, dsts * 3, inits, 4, variant=0, grid=2, ordered=True)
+    _compare(g_rep, refs, srcs * 3, 4, ordered=True)
+    try:
+        E.set_options(shared_src=True)
+        g = E.icp_fused(srcs * 3, dsts * 3, inits, 4, variant=0, grid=2, ordered=True)   # src_off[0:2] is the one scan
+        for k in ("T", "inner", "corr", "corr_hash"):
+            assert np.array_equal(g[k], g_rep[k]), k
+        g = E.icp_fused(srcs * 3, dsts * 3, inits, 4, variant=0, grid=2, ordered="lean")
+        _compare(g, refs, srcs * 3, 4, ordered=False)
+    finally:
+        E.set_options()

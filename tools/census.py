@@ -1,0 +1,67 @@
+"""Mismatch census of the default (warp-tree + knife-edge guard) mode against the oracle.
+
+usage: census.py [pairs=131072] [chunk=16384] [--no-guard]
+BASELINE config 2/5 stream (synth_scan_pairs, pairs [first, first+pairs)), 20 outer iterations.
+Per chunk: the device result through the C ABI (host buffers) and the oracle on every host core
+(exact kd-tree); counts pairs whose inner-iteration table or correspondence checksum differ, the
+largest transform difference, how many pairs the guard re-ran, and the tightest decision margin
+(oracle's) among the pairs that were NOT re-run.  Prints one JSON line."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+import icp_rust_b200 as icp
+import oracle
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    N = int(args[0]) if len(args) > 0 else 131072
+    chunk = int(args[1]) if len(args) > 1 else 16384
+    guard = "--no-guard" not in sys.argv
+    first = 2_000_000          # away from the pairs bench.py and the tests use
+    ctx = icp.Context(0)
+    cores = len(os.sched_getaffinity(0))
+    out = {"workload": f"config 2/5 stream, pairs [{first}, {first + N}), 1080 points, 20 outer iterations",
+           "pairs": N, "guard": guard, "inner_mismatch": 0, "corr_hash_mismatch": 0, "redo_pairs": 0,
+           "max_abs_transform_difference": 0.0, "host_cores": cores}
+    tight = [np.inf, np.inf]
+    mism = []
+    t_gpu = t_cpu = 0.0
+    for c0 in range(0, N, chunk):
+        n = min(chunk, N - c0)
+        src, dst, off, _ = icp.synth_scan_pairs(n, beams=1080, first_pair=first + c0)
+        T0 = np.tile(np.array([1., 0., 0., 1., 0., 0.]), (n, 1))
+        t = time.perf_counter()
+        g = ctx.estimate_batch(src, off, dst, off, T0, 20, guard=guard)
+        t_gpu += time.perf_counter() - t
+        t = time.perf_counter()
+        o = oracle.icp_estimate_batch(2, src, off, dst, off, T0, 20, nn_mode=oracle.NN_KDTREE, nthreads=cores,
+                                      want_margins=True)
+        t_cpu += time.perf_counter() - t
+        bad_i = np.flatnonzero((g["inner"] != o["inner"]).any(axis=1))
+        bad_h = np.flatnonzero(g["corr_hash"] != o["corr_hash"])
+        out["inner_mismatch"] += int(len(bad_i))
+        out["corr_hash_mismatch"] += int(len(bad_h))
+        out["redo_pairs"] += int(g["redo_pairs"])
+        out["max_abs_transform_difference"] = max(out["max_abs_transform_difference"], float(np.abs(g["T"] - o["T"]).max()))
+        exact = (g["T"] == o["T"]).all(axis=1)          # re-run pairs are bit-identical; so are lucky ones
+        for k in range(2):
+            m = o["margins"][~exact, k]
+            if len(m):
+                tight[k] = min(tight[k], float(m.min()))
+        for b in sorted(set(bad_i) | set(bad_h))[:8]:
+            mism.append({"pair": int(first + c0 + b), "margins": o["margins"][b].tolist()})
+    out["tightest_margin_of_pairs_not_bit_identical"] = {"delta_test": tight[0], "error_test": tight[1]}
+    out["mismatching_pairs"] = mism
+    out["gpu_host_call_s"] = round(t_gpu, 2)
+    out["oracle_s"] = round(t_cpu, 2)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
