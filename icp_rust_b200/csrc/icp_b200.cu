@@ -53,12 +53,10 @@ const Instance* const kInstances[] = {&kFusedInstance0, &kFusedInstance1, &kFuse
                                       &kFusedInstance12, &kFusedInstance13};
 constexpr int kNumInstances = (int)(sizeof(kInstances) / sizeof(kInstances[0]));
 constexpr int kMaxChunks = 64;
-// device counter words of a context: per-chunk work counters | error word | per-chunk work counters
-// of the ordered re-run | per-chunk counts of flagged pairs
-constexpr int kCtrWork = 0, kCtrErr = kMaxChunks, kCtrRedoWork = kMaxChunks + 1, kCtrRedoCount = 2 * kMaxChunks + 1;
-constexpr int kCtrWords = 3 * kMaxChunks + 1;
-// bands of the knife-edge guard (GuardBands, icp_fused.cuh; include/icp_b200.h "flags")
-constexpr double kGuardDet = 1e-10, kGuardDelta = 1e-6, kGuardErr = 1e-10;
+// device counter words of a context: per-chunk work counters | error word | work counter of the
+// ordered re-run | count of flagged pairs
+constexpr int kCtrWork = 0, kCtrErr = kMaxChunks, kCtrRedoWork = kMaxChunks + 1, kCtrRedoCount = kMaxChunks + 2;
+constexpr int kCtrWords = kMaxChunks + 3;
 
 int env_int(const char* name, int dflt)
 {
@@ -75,11 +73,12 @@ struct icp_b200_context {
     cudaStream_t stream[2] = {nullptr, nullptr};
     cudaEvent_t ev[kMaxChunks][2];
     cudaEvent_t ev_ready = nullptr;
+    cudaEvent_t ev_redo[2] = {nullptr, nullptr};
     bool events_ok = false;
     DevBuf src, dst, src_off, dst_off, init_T, out_T, out_inner, out_corr, out_hash, out_status, out_cost;
     DevBuf counters;       // kCtrWords words (layout above)
     DevBuf workspace[2];
-    DevBuf redo_list, redo_workspace[2];   // flagged pairs of the launch in flight / slabs of their ordered re-run
+    DevBuf redo_list, redo_workspace;   // flagged pairs of the call in flight / slabs of their ordered re-run
     int guard = 1;          // ICP_B200_GUARD=0: no knife-edge guard (as ICP_B200_FLAG_NO_GUARD on every call)
     double guard_scale = 1.0;   // ICP_B200_GUARD_SCALE: multiplies the guard bands (tests force re-runs with it)
     DevBuf stats_in, stats_off, stats_out;
@@ -225,72 +224,89 @@ int validate_batch(icp_b200_context* ctx, const icp_b200_batch* b, bool shared_t
     return ICP_B200_OK;
 }
 
-// Device-pointer launch of pairs [begin, end) on `stream`.  `redo` (tree mode with the knife-edge
-// guard): the plan of the ordered kernel that re-runs, right behind the main kernel on the same
-// stream, the pairs the main kernel flagged (their indices and count stay on the device).
-int launch_range(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_target* tgt, const LaunchPlan& plan,
-                 const LaunchPlan* redo, uint32_t begin, uint32_t end, int chunk_slot, int ws_slot, cudaStream_t stream)
+void fill_params(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_target* tgt, FusedParams* out)
 {
-    FusedParams p{};
+    FusedParams& p = *out;
     p.src = b.src; p.src_off = b.src_off; p.dst = b.dst; p.dst_off = b.dst_off; p.init_T = b.init_T;
     p.out_T = b.out_T; p.out_inner = b.out_inner; p.out_corr = b.out_corr; p.out_hash = b.out_corr_hash;
     p.out_status = b.out_status; p.out_cost = b.out_cost;
     p.shared_src = (b.flags & ICP_B200_FLAG_SHARED_SOURCE) ? 1u : 0u;
     p.out_error = ctx->counters.as<int32_t>() + kCtrErr;
-    p.work_counter = ctx->counters.as<uint32_t>() + kCtrWork + chunk_slot;
-    p.workspace = ctx->workspace[ws_slot].as<unsigned char>();
-    p.ws_stride = plan.ws_stride;
-    p.pair_begin = begin; p.pair_end = end; p.max_iter = b.max_iter; p.corr_mode = b.corr_mode;
-    p.cell_budget = ctx->cell_budget; p.mcap = plan.mcap;
-    p.ncap = plan.stream ? (int)plan.n_cap : plan.inst->threads * plan.inst->ppt;
+    p.max_iter = b.max_iter; p.corr_mode = b.corr_mode;
+    p.cell_budget = ctx->cell_budget;
     p.sm_count = (uint32_t)ctx->sm_count;
-    if (redo) {
-        p.redo_list = ctx->redo_list.as<uint32_t>() + begin;     // a chunk's flagged pairs fit its own pair range
-        p.redo_count = ctx->counters.as<uint32_t>() + kCtrRedoCount + chunk_slot;
-        p.guard.det = kGuardDet * ctx->guard_scale;
-        p.guard.delta = kGuardDelta * ctx->guard_scale;
-        p.guard.err = kGuardErr * ctx->guard_scale;
-    }
     if (tgt) {
         p.target.x = tgt->x.as<double>(); p.target.y = tgt->y.as<double>(); p.target.z = tgt->z.as<double>();
         p.target.idx = tgt->idx.as<uint32_t>(); p.target.cstart = tgt->cstart.as<uint32_t>();
         p.target.g = tgt->g; p.target.m = tgt->m;
         p.target.seed = tgt->seed_ptr; p.target.pf = tgt->seed_ptr ? tgt->pf.as<float2>() : nullptr;
     }
-    const uint32_t pairs = end - begin;
-    auto launch = [&](const LaunchPlan& pl, const FusedParams& fp, int grid) {
-        if (pl.stream) {
-            StreamParams sp{};
-            sp.f = fp; sp.n_cap = pl.n_cap; sp.m_cap = pl.m_cap; sp.c_cap = pl.c_cap;
-            sp.cells_per_point = (uint32_t)ctx->stream_cells_per_point;
-            sp.ordered = pl.stream_ordered ? 1u : 0u;
-            pl.skernel<<<grid, pl.threads, pl.smem, stream>>>(sp);
-        } else {
-            pl.kernel<<<grid, pl.threads, pl.smem, stream>>>(fp);
-        }
-    };
-    const int grid = (int)std::min<uint32_t>((uint32_t)plan.grid, pairs);
-    launch(plan, p, grid);
+}
+
+int launch_plan(icp_b200_context* ctx, const LaunchPlan& pl, const FusedParams& fp, int grid, cudaStream_t stream)
+{
+    if (pl.stream) {
+        StreamParams sp{};
+        sp.f = fp; sp.n_cap = pl.n_cap; sp.m_cap = pl.m_cap; sp.c_cap = pl.c_cap;
+        sp.cells_per_point = (uint32_t)ctx->stream_cells_per_point;
+        sp.ordered = pl.stream_ordered ? 1u : 0u;
+        pl.skernel<<<grid, pl.threads, pl.smem, stream>>>(sp);
+    } else {
+        pl.kernel<<<grid, pl.threads, pl.smem, stream>>>(fp);
+    }
     ICP_CUDA(ctx, cudaGetLastError());
     ctx->info.kernel_launches += 1;
+    return ICP_B200_OK;
+}
+
+// Device-pointer launch of pairs [begin, end) on `stream`.  `guarded` (tree mode with the knife-edge
+// guard): pairs with a decision inside a guard band are appended to the call's redo list on the
+// device (one list and one count per call, shared by its chunks).
+int launch_range(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_target* tgt, const LaunchPlan& plan,
+                 bool guarded, uint32_t begin, uint32_t end, int chunk_slot, int ws_slot, cudaStream_t stream)
+{
+    FusedParams p{};
+    fill_params(ctx, b, tgt, &p);
+    p.work_counter = ctx->counters.as<uint32_t>() + kCtrWork + chunk_slot;
+    p.workspace = ctx->workspace[ws_slot].as<unsigned char>();
+    p.ws_stride = plan.ws_stride;
+    p.pair_begin = begin; p.pair_end = end;
+    p.mcap = plan.mcap;
+    p.ncap = plan.stream ? (int)plan.n_cap : plan.inst->threads * plan.inst->ppt;
+    if (guarded) {
+        p.redo_list = ctx->redo_list.as<uint32_t>();
+        p.redo_count = ctx->counters.as<uint32_t>() + kCtrRedoCount;
+        p.guard.det = kGuardDet * ctx->guard_scale;
+        p.guard.delta = kGuardDelta * ctx->guard_scale;
+        p.guard.err = kGuardErr * ctx->guard_scale;
+    }
+    const int grid = (int)std::min<uint32_t>((uint32_t)plan.grid, end - begin);
+    int rc = launch_plan(ctx, plan, p, grid, stream);
+    if (rc != ICP_B200_OK) return rc;
     ctx->info.grid_ctas = (uint32_t)grid;
     ctx->info.block_threads = (uint32_t)plan.threads;
     ctx->info.smem_bytes = plan.smem;
-    if (redo) {
-        FusedParams r = p;
-        r.pair_list = p.redo_list; r.pair_count = p.redo_count;
-        r.redo_list = nullptr; r.redo_count = nullptr; r.guard = GuardBands{0., 0., 0.};
-        r.work_counter = ctx->counters.as<uint32_t>() + kCtrRedoWork + chunk_slot;
-        r.workspace = ctx->redo_workspace[ws_slot].as<unsigned char>();
-        r.ws_stride = redo->ws_stride;
-        r.pair_begin = 0; r.pair_end = b.batch;
-        r.mcap = redo->mcap;
-        r.ncap = redo->stream ? (int)redo->n_cap : redo->inst->threads * redo->inst->ppt;
-        launch(*redo, r, (int)std::min<uint32_t>((uint32_t)redo->grid, pairs));
-        ICP_CUDA(ctx, cudaGetLastError());
-        ctx->info.kernel_launches += 1;
-    }
     return ICP_B200_OK;
+}
+
+// The ordered re-run of the pairs the call's tree-mode launches flagged: one launch behind them on
+// `stream`, the flagged pairs spread over its CTAs (their indices and count never leave the device).
+// A lone 1080-point pair takes a few milliseconds in reference order (2n dependent additions per
+// evaluation), so the re-run is issued once per call, not once per chunk.
+int launch_redo(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_target* tgt, const LaunchPlan& redo,
+                cudaStream_t stream)
+{
+    FusedParams r{};
+    fill_params(ctx, b, tgt, &r);
+    r.pair_list = ctx->redo_list.as<uint32_t>();
+    r.pair_count = ctx->counters.as<uint32_t>() + kCtrRedoCount;
+    r.work_counter = ctx->counters.as<uint32_t>() + kCtrRedoWork;
+    r.workspace = ctx->redo_workspace.as<unsigned char>();
+    r.ws_stride = redo.ws_stride;
+    r.pair_begin = 0; r.pair_end = b.batch;
+    r.mcap = redo.mcap;
+    r.ncap = redo.stream ? (int)redo.n_cap : redo.inst->threads * redo.inst->ppt;
+    return launch_plan(ctx, redo, r, (int)std::min<uint32_t>((uint32_t)redo.grid, b.batch), stream);
 }
 
 // The ordered plan that re-runs flagged pairs, when this call wants the guard.
@@ -301,7 +317,9 @@ int plan_redo(icp_b200_context* ctx, const icp_b200_batch* b, bool shared, uint3
     if ((b->flags & (ICP_B200_FLAG_ORDERED_SUMS | ICP_B200_FLAG_NO_GUARD)) || !ctx->guard) return ICP_B200_OK;
     int rc = plan_launch(ctx, b->dim, shared, true, max_n, max_m, b->batch, redo);
     if (rc != ICP_B200_OK) return rc;
+    redo->grid = std::min(redo->grid, ctx->sm_count);   // a handful of pairs: one CTA per SM is plenty
     ICP_CUDA(ctx, ctx->redo_list.ensure((size_t)b->batch * 4));
+    ICP_CUDA(ctx, ctx->redo_workspace.ensure((size_t)redo->grid * redo->ws_stride + 256));
     *use = true;
     return ICP_B200_OK;
 }
@@ -312,6 +330,7 @@ int ensure_events(icp_b200_context* ctx)
     for (int i = 0; i < kMaxChunks; ++i)
         for (int j = 0; j < 2; ++j) ICP_CUDA(ctx, cudaEventCreate(&ctx->ev[i][j]));
     ICP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
+    for (int j = 0; j < 2; ++j) ICP_CUDA(ctx, cudaEventCreate(&ctx->ev_redo[j]));
     ctx->events_ok = true;
     return ICP_B200_OK;
 }
@@ -352,11 +371,14 @@ int estimate_device_impl(icp_b200_context* ctx, const icp_b200_target* tgt, cons
     if (rc != ICP_B200_OK) return rc;
     ICP_CUDA(ctx, ctx->counters.ensure(kCtrWords * 4));
     ICP_CUDA(ctx, ctx->workspace[0].ensure((size_t)plan.grid * plan.ws_stride + 256));
-    if (use_redo) ICP_CUDA(ctx, ctx->redo_workspace[0].ensure((size_t)redo.grid * redo.ws_stride + 256));
     ICP_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, kCtrWords * 4, stream));
     ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], stream));
-    rc = launch_range(ctx, *b, tgt, plan, use_redo ? &redo : nullptr, 0, b->batch, 0, 0, stream);
+    rc = launch_range(ctx, *b, tgt, plan, use_redo, 0, b->batch, 0, 0, stream);
     if (rc != ICP_B200_OK) return rc;
+    if (use_redo) {
+        rc = launch_redo(ctx, *b, tgt, redo, stream);
+        if (rc != ICP_B200_OK) return rc;
+    }
     ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][1], stream));
     if (synchronize) {
         int32_t err = 0;
@@ -423,8 +445,6 @@ int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b2
     if (hb->out_cost) ICP_CUDA(ctx, ctx->out_cost.ensure((size_t)B * 8));
     ICP_CUDA(ctx, ctx->counters.ensure(kCtrWords * 4));
     for (int s = 0; s < 2; ++s) ICP_CUDA(ctx, ctx->workspace[s].ensure((size_t)plan.grid * plan.ws_stride + 256));
-    if (use_redo)
-        for (int s = 0; s < 2; ++s) ICP_CUDA(ctx, ctx->redo_workspace[s].ensure((size_t)redo.grid * redo.ws_stride + 256));
 
     icp_b200_batch db = *hb;
     db.src = ctx->src.as<double>(); db.dst = ctx->dst.as<double>();
@@ -474,7 +494,7 @@ int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b2
             ctx->info.h2d_bytes += (dp1 - dp0) * dim * 8;
         }
         ICP_CUDA(ctx, cudaEventRecord(ctx->ev[c][0], st));
-        rc = launch_range(ctx, db, tgt, plan, use_redo ? &redo : nullptr, b0, b1, c, c & 1, st);
+        rc = launch_range(ctx, db, tgt, plan, use_redo, b0, b1, c, c & 1, st);
         if (rc != ICP_B200_OK) return rc;
         ICP_CUDA(ctx, cudaEventRecord(ctx->ev[c][1], st));
         ICP_CUDA(ctx, cudaMemcpyAsync(hb->out_T + (size_t)b0 * 6, ctx->out_T.as<double>() + (size_t)b0 * 6, (size_t)(b1 - b0) * 48, cudaMemcpyDeviceToHost, st));
@@ -505,16 +525,56 @@ int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b2
         used = c + 1;
     }
     int32_t err = 0;
-    uint32_t nredo[kMaxChunks];
+    uint32_t nredo = 0;
     ICP_CUDA(ctx, cudaStreamSynchronize(s1));
+    if (use_redo) {
+        // every chunk's kernel has been issued (s1's have finished): one ordered re-run of the pairs
+        // they flagged, behind s0's last chunk, then the results of exactly those pairs once more
+        ICP_CUDA(ctx, cudaEventRecord(ctx->ev_redo[0], s0));
+        rc = launch_redo(ctx, db, tgt, redo, s0);
+        if (rc != ICP_B200_OK) return rc;
+        ICP_CUDA(ctx, cudaEventRecord(ctx->ev_redo[1], s0));
+        ICP_CUDA(ctx, cudaMemcpyAsync(&nredo, ctx->counters.as<uint32_t>() + kCtrRedoCount, 4, cudaMemcpyDeviceToHost, s0));
+    }
     ICP_CUDA(ctx, cudaMemcpyAsync(&err, ctx->counters.as<int32_t>() + kCtrErr, 4, cudaMemcpyDeviceToHost, s0));
-    ICP_CUDA(ctx, cudaMemcpyAsync(nredo, ctx->counters.as<uint32_t>() + kCtrRedoCount, sizeof(nredo), cudaMemcpyDeviceToHost, s0));
     ICP_CUDA(ctx, cudaStreamSynchronize(s0));
-    for (int c = 0; c < used; ++c) ctx->info.redo_pairs += nredo[c];
+    ctx->info.redo_pairs = nredo;
+    if (nredo > 0) {
+        std::vector<uint32_t> list(nredo);
+        ICP_CUDA(ctx, cudaMemcpyAsync(list.data(), ctx->redo_list.p, (size_t)nredo * 4, cudaMemcpyDeviceToHost, s0));
+        ICP_CUDA(ctx, cudaStreamSynchronize(s0));
+        const bool all = nredo > 64;     // many (forced bands in tests): whole arrays again
+        const size_t npairs = all ? 1 : nredo;
+        for (size_t k = 0; k < npairs; ++k) {
+            const uint32_t b0 = all ? 0u : list[k], cnt = all ? B : 1u;
+            ICP_CUDA(ctx, cudaMemcpyAsync(hb->out_T + (size_t)b0 * 6, ctx->out_T.as<double>() + (size_t)b0 * 6, (size_t)cnt * 48, cudaMemcpyDeviceToHost, s0));
+            if (hb->out_inner && hb->max_iter)
+                ICP_CUDA(ctx, cudaMemcpyAsync(hb->out_inner + (size_t)b0 * hb->max_iter, ctx->out_inner.as<uint32_t>() + (size_t)b0 * hb->max_iter,
+                                              (size_t)cnt * hb->max_iter * 4, cudaMemcpyDeviceToHost, s0));
+            if (hb->out_corr_hash)
+                ICP_CUDA(ctx, cudaMemcpyAsync(hb->out_corr_hash + b0, ctx->out_hash.as<uint64_t>() + b0, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s0));
+            if (hb->out_cost)
+                ICP_CUDA(ctx, cudaMemcpyAsync(hb->out_cost + b0, ctx->out_cost.as<double>() + b0, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s0));
+            if (ncorr) {
+                const uint64_t mul = hb->corr_mode == ICP_B200_CORR_ALL ? hb->max_iter : 1;
+                const uint64_t sp0 = shared_src ? nsrc * b0 : so[b0], sp1 = shared_src ? nsrc * (b0 + cnt) : so[b0 + cnt];
+                if (sp1 > sp0)
+                    ICP_CUDA(ctx, cudaMemcpyAsync(hb->out_corr + sp0 * mul, ctx->out_corr.as<int32_t>() + sp0 * mul, (sp1 - sp0) * mul * 4, cudaMemcpyDeviceToHost, s0));
+                ctx->info.d2h_bytes += (sp1 - sp0) * mul * 4;
+            }
+            ctx->info.d2h_bytes += (uint64_t)cnt * (48 + (hb->out_inner ? hb->max_iter * 4 : 0) + (hb->out_corr_hash ? 8 : 0) + (hb->out_cost ? 8 : 0));
+        }
+        ICP_CUDA(ctx, cudaStreamSynchronize(s0));
+    }
     float total = 0.f;
     for (int c = 0; c < used; ++c) {
         float ms = 0.f;
         ICP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[c][0], ctx->ev[c][1]));
+        total += ms;
+    }
+    if (use_redo) {
+        float ms = 0.f;
+        ICP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_redo[0], ctx->ev_redo[1]));
         total += ms;
     }
     ctx->info.kernel_ms = total;
@@ -599,12 +659,13 @@ void icp_b200_destroy(icp_b200_context* ctx)
     DevBuf* bufs[] = {&ctx->src, &ctx->dst, &ctx->src_off, &ctx->dst_off, &ctx->init_T, &ctx->out_T, &ctx->out_inner,
                       &ctx->out_corr, &ctx->out_hash, &ctx->out_status, &ctx->counters, &ctx->workspace[0],
                       &ctx->workspace[1], &ctx->stats_in, &ctx->stats_off, &ctx->stats_out, &ctx->out_cost,
-                      &ctx->redo_list, &ctx->redo_workspace[0], &ctx->redo_workspace[1]};
+                      &ctx->redo_list, &ctx->redo_workspace};
     for (DevBuf* b : bufs) b->release();
     if (ctx->events_ok) {
         for (int i = 0; i < kMaxChunks; ++i)
             for (int j = 0; j < 2; ++j) cudaEventDestroy(ctx->ev[i][j]);
         cudaEventDestroy(ctx->ev_ready);
+        for (int j = 0; j < 2; ++j) cudaEventDestroy(ctx->ev_redo[j]);
     }
     for (int s = 0; s < 2; ++s)
         if (ctx->stream[s]) cudaStreamDestroy(ctx->stream[s]);

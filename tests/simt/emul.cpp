@@ -54,7 +54,7 @@ static void apply_guard(FusedParams& p, std::vector<uint32_t>& list, uint32_t* c
     list.assign(B + 1, 0u);
     *count = 0;
     p.redo_list = list.data(); p.redo_count = count;
-    p.guard.det = 1e-10 * g_guard_scale; p.guard.delta = 1e-6 * g_guard_scale * g_band_delta_scale; p.guard.err = 1e-10 * g_guard_scale;
+    p.guard.det = kGuardDet * g_guard_scale; p.guard.delta = kGuardDelta * g_guard_scale * g_band_delta_scale; p.guard.err = kGuardErr * g_guard_scale;
 }
 
 // Same argument meaning as icp_b200_batch.  variant: 0 -> 128 threads x 3 points, 1 -> 128 x 9,

@@ -360,7 +360,7 @@ def test_knife_edge_guard_partial_band():
     err_m = np.sort(o["margins"][:, 1])
     band = float(np.sqrt(err_m[3] * err_m[4]))          # half of the pairs have an error test inside it
     try:
-        E.set_options(guard_scale=band / 1e-10, delta_band_scale=1e-10 / band)   # delta band stays 1e-6
+        E.set_options(guard_scale=band / 1e-11, delta_band_scale=1e-11 / band)   # the delta band keeps its own width
         g = E.icp_fused(srcs, dsts, T0, 5, variant=0, grid=3, ordered="lean")
         flagged = E.last_redo_count()
     finally:

@@ -37,12 +37,17 @@ def main():
         src, dst, off, _ = icp.synth_scan_pairs(n, beams=1080, first_pair=first + c0)
         T0 = np.tile(np.array([1., 0., 0., 1., 0., 0.]), (n, 1))
         t = time.perf_counter()
-        g = ctx.estimate_batch(src, off, dst, off, T0, 20, guard=guard)
+        g = ctx.estimate_batch(src, off, dst, off, T0, 20, guard=guard, want_cost=True)
         t_gpu += time.perf_counter() - t
         t = time.perf_counter()
         o = oracle.icp_estimate_batch(2, src, off, dst, off, T0, 20, nn_mode=oracle.NN_KDTREE, nthreads=cores,
-                                      want_margins=True)
+                                      want_margins=True, want_cost=True)
         t_cpu += time.perf_counter() - t
+        # how far the tree-mode state drifts from the reference-order state: relative difference of the
+        # final huber_error (the quantity the error test compares) — what the guard bands must exceed
+        rel = np.abs(g["cost"] - o["cost"]) / np.maximum(o["cost"], 1e-300)
+        out["max_rel_final_cost_difference"] = max(out.get("max_rel_final_cost_difference", 0.0), float(rel.max()))
+        out["p99_rel_final_cost_difference"] = max(out.get("p99_rel_final_cost_difference", 0.0), float(np.quantile(rel, 0.99)))
         bad_i = np.flatnonzero((g["inner"] != o["inner"]).any(axis=1))
         bad_h = np.flatnonzero(g["corr_hash"] != o["corr_hash"])
         out["inner_mismatch"] += int(len(bad_i))
