@@ -23,6 +23,13 @@ collective on the data path).  One "step" = one pass of the ICP 
   cpu_baseline : the oracle (C restatement of the reference, exact kd-tree) on the host cores,
                  bounded sample of the same workload.  kind "port": the reference is a Rust crate
                  and cannot be built in this image.
+  config4_3d   : BASELINE config 4 — 1024 pairs (frame i, frame i+1 mod 20) of the bundled 3-D
+                 recording x 16,384 points, 20 iterations — pairs/s, NN queries/s, 28 B/query roofline,
+                 oracle parity sample.
+  config5_1m   : (--gpus N > 1 only) BASELINE config 5 — 1,000,000 config-2 pairs in contiguous slices
+                 over the N GPUs, chunks of 16,384 pairs, device-timed, max over ranks, result checksum.
+  census       : inner-iteration tables and correspondence checksums of the cpu_baseline sample against
+                 the oracle (0 mismatches expected: decisions are guarded, include/icp_b200.h "flags").
 --impl reference times that same oracle as the reference arm (rank 0 only).
 Two distinct input batches alternate between steps; each batch is 141.6 MB of points (> the
 126 MB L2), so no step finds its inputs in cache.
@@ -51,6 +58,14 @@ BYTES_PER_PAIR = 16 * BEAMS + 16 * BEAMS + 96
 NN_BYTES_PER_QUERY = 20
 
 
+def bench_config(world, B):
+    """`config` of the JSON line: the workload only, identical in the product arm and the reference arm."""
+    return {"workload": WORKLOAD if B == PAIRS_PER_GPU else f"{B} synthetic 2D scan pairs x {BEAMS} points per GPU, {MAX_ITER} outer iterations",
+            "pairs_per_gpu": B, "points_per_scan": BEAMS, "outer_iterations": MAX_ITER,
+            "parallelism": f"{world} x independent pair slices, no data-path collective",
+            "l2": "two distinct 141.6 MB input batches alternate between steps (inputs larger than the 126 MB L2)"}
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -68,7 +83,8 @@ def measured_peaks():
 
 def profiled_traffic(kernel, units=None):
     """dram bytes per launch from the committed ncu --set full capture (profiles/traffic.json),
-    scaled to `units` (pairs / queries per launch) when the capture was of a different size."""
+    scaled to `units` (pairs / queries per launch) when the capture was of a different size.
+    A STATIC figure from a profile, not a property of this run: bench.py says so in `traffic_source`."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         with open(p) as f:
@@ -80,6 +96,9 @@ def profiled_traffic(kernel, units=None):
                 return int(round(b * units / cap))
             return b
     return None
+
+
+TRAFFIC_SOURCE = "profiles/traffic.json (static: one ncu --set full capture, scaled to this launch's units)"
 
 
 # ----------------------------------------------------------------------------------------------
@@ -141,13 +160,17 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
     """Reference arm: the CPU implementation of the path (oracle port of icp_rust, exact kd-tree,
-    one pair per thread on every host core) on a bounded sample of the same workload per step."""
+    one pair per thread on every host core) on a bounded sample of the same workload per step:
+    64 pairs per core and step (1024 on 16 cores), so that a step's tail is short against its body
+    and the timed region covers >= 4096 pairs."""
     if rank != 0:
         return
     import icp_rust_b200 as icp
     import oracle
     cores = host_cores()
-    sample = max(16, 16 * cores)
+    sample = min(PAIRS_PER_GPU, max(256, 64 * cores))
+    while sample * args.steps < PAIRS_PER_GPU and sample < PAIRS_PER_GPU:
+        sample *= 2
     total = sample * (args.steps + args.warmup)
     src, dst, _, _ = icp.synth_scan_pairs(total, beams=BEAMS, seed=SEED)
     off = (np.arange(sample + 1, dtype=np.uint64) * BEAMS).astype(np.uint32)
@@ -165,12 +188,13 @@ def run_reference(args, rank, world):
         step(args.warmup + k)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
-    desc = f"{sample} pairs per step ({sample * args.steps} timed) of the same synthetic stream, {cores} threads, exact kd-tree"
+    desc = (f"{sample} pairs per step ({sample * args.steps} timed) of the same synthetic stream, {cores} threads, "
+            "exact kd-tree; oracle port of icp_rust (Rust toolchain absent)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU reference arm: oracle port of icp_rust (Rust toolchain absent), bounded sample per step"},
+        "config": bench_config(args.gpus, PAIRS_PER_GPU),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -313,8 +337,18 @@ def run_gpu(args, rank, local_rank, world):
     # ---- correspondence kernel alone (config 3 shape: 100k-point map, queries near the surface)
     nn = None
     c3 = None
+    c4 = None
     cpu = None
-    if rank == 0:
+    clocks = sampler.summary([(w0, w1), (w2, w3)])
+    sampler.stop_flag = True
+    # ---- BASELINE config 5 (strong scaling) when several GPUs run: every rank takes part
+    c5 = None
+    if world > 1 and not args.no_config5:
+        try:
+            c5 = bench_config5(icp, ctx, torch, dist, dev, stream, rank, world)
+        except Exception as e:  # pragma: no cover
+            c5 = {"error": repr(e)}
+    if rank == 0 and not args.headline_only:
         try:
             nn = bench_nn_search(icp, ctx, torch, dev, stream)
         except Exception as e:  # pragma: no cover
@@ -323,8 +357,10 @@ def run_gpu(args, rank, local_rank, world):
             c3 = bench_config3(icp, ctx)
         except Exception as e:  # pragma: no cover
             c3 = {"error": repr(e)}
-    clocks = sampler.summary([(w0, w1), (w2, w3)])
-    sampler.stop_flag = True
+        try:
+            c4 = bench_config4(icp, ctx)
+        except Exception as e:  # pragma: no cover
+            c4 = {"error": repr(e)}
 
     # ---- results only are gathered (48 B per pair), after the timed regions
     if world > 1:
@@ -333,8 +369,9 @@ def run_gpu(args, rank, local_rank, world):
         assert allT.shape == (world * B, 6) and np.isfinite(allT).all()
 
     if rank == 0:
+        census = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline(icp, host[0], B)
+            cpu, census = cpu_baseline(icp, ctx, host[0], B)
             cpu["single_pair_latency"] = single_pair_latency(icp, ctx)
         peak, peak_src = measured_peaks()
         achieved = BYTES_PER_PAIR * B / (launch_ms * 1e-3) / 1e9
@@ -345,11 +382,10 @@ def run_gpu(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD if B == PAIRS_PER_GPU else f"{B} synthetic 2D scan pairs x {BEAMS} points per GPU, {MAX_ITER} outer iterations",
-                       "pairs_per_gpu": B, "points_per_scan": BEAMS, "outer_iterations": MAX_ITER,
-                       "parallelism": f"{world} x independent pair slices, no data-path collective",
-                       "l2": "two distinct 141.6 MB input batches alternate between steps (inputs larger than the 126 MB L2)",
-                       "kernel": {"grid": info["grid_ctas"], "block": info["block_threads"], "smem": info["smem_bytes"]}},
+            "config": bench_config(world, B),
+            "kernel_shape": {"grid": info["grid_ctas"], "block": info["block_threads"], "smem": info["smem_bytes"],
+                             "launches_per_step": info["kernel_launches"],
+                             "note": "one icp_lean_kernel launch + one (normally empty) ordered re-run launch of the knife-edge guard"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hinfo["h2d_bytes"]),
                     "d2h_bytes_per_step": int(hinfo["d2h_bytes"]), "ms_per_step": e2e_s / K * 1e3,
                     "bit_identical_to_device_path": same},
@@ -358,6 +394,7 @@ def run_gpu(args, rank, local_rank, world):
                          "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if args.ordered else profiled_traffic("icp_lean_kernel", B),
+                         "traffic_source": TRAFFIC_SOURCE,
                          "peak_source": peak_src, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": BYTES_PER_PAIR * B,
                          "fp64": fp64,
                          "note": "latency/FP64-chain bound by design (34.7 KB per pair, ~180 Gauss-Newton evaluations per pair); "
@@ -366,6 +403,11 @@ def run_gpu(args, rank, local_rank, world):
             "ordered_sums_mode": other,
             "nn_search": nn,
             "config3_shared_map": c3,
+            "config4_3d": c4,
+            "config5_1m": c5,
+            "guard": {"redo_pairs_last_host_step": int(hinfo["redo_pairs"]),
+                      "note": "pairs of one 4096-pair step the knife-edge guard re-ran with ordered sums (include/icp_b200.h flags)"},
+            "census": census,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "accuracy": {"median_abs_translation_error_mm": float(np.median(np.abs(oT[:, 4:] - tT[:, 4:]).max(axis=1))),
@@ -431,9 +473,9 @@ def bench_nn_search(icp, ctx, torch, dev, stream, map_points=100_000, nscan=1553
                                  "active (profiles/r01_ncu_full_summary.md); the 20 B/query stream is 2 % of HBM bandwidth"}}
 
 
-def bench_config3(icp, ctx, scans_n=16384):
-    """BASELINE config 3 in the ICP loop itself: scans against one shared 100k-point map
-    (icp_b200_target_estimate_batch, host buffers), a quarter of the 65536 scans to bound the run."""
+def bench_config3(icp, ctx, scans_n=65536):
+    """BASELINE config 3 in the ICP loop itself at full size: 65,536 scans against one shared
+    100k-point map (icp_b200_target_estimate_batch, host buffers)."""
     m = icp.synth_map(100_000, seed=7)
     scans, off, T0 = icp.synth_map_scans(scans_n, beams=BEAMS, seed=7)
     tgt = icp.Target(m, ctx)
@@ -447,7 +489,90 @@ def bench_config3(icp, ctx, scans_n=16384):
     tgt.close()
     return {"workload": f"config3: {scans_n} scans x {BEAMS} points vs one shared 100000-point map, {MAX_ITER} outer iterations",
             "value": scans_n / (best[1] * 1e-3), "unit": "pairs/s", "kernel_ms": best[1],
-            "host_call_pairs_per_s": scans_n / best[0], "status_ok": bool((g["status"] == 0).all())}
+            "host_call_pairs_per_s": scans_n / best[0], "status_ok": bool((g["status"] == 0).all()),
+            "redo_pairs": int(g["redo_pairs"])}
+
+
+def bench_config4(icp, ctx, pairs=1024, check=16):
+    """BASELINE config 4: 1024 pairs (frame i, frame i+1 mod 20) of the bundled 3-D recording x 16,384
+    points, seeded initial perturbation, 20 iterations (icp_rust_b200/workloads.py); host buffers
+    through icp_b200_estimate_batch.  NN queries/s counts the 20 x 16,384 searches of every pair;
+    its roofline is the correspondence stream of SURVEY.md 8(d): 28 B per 3-D query."""
+    import oracle
+    from icp_rust_b200.workloads import config4_pairs, CONFIG4_POINTS
+    src, dst, off, T0 = config4_pairs(pairs)
+    best = None
+    for _ in range(2):
+        t = time.perf_counter()
+        g = ctx.estimate_batch(src, off, dst, off, T0, MAX_ITER, dim=3)
+        wall = time.perf_counter() - t
+        info = ctx.call_info()
+        best = (wall, info["kernel_ms"]) if best is None or info["kernel_ms"] < best[1] else best
+    n = min(pairs, check)
+    o = oracle.icp_estimate_batch(3, src[:n * CONFIG4_POINTS], off[:n + 1], dst[:n * CONFIG4_POINTS], off[:n + 1], T0[:n],
+                                  MAX_ITER, nn_mode=oracle.NN_KDTREE)
+    peak, peak_src = measured_peaks()
+    queries = pairs * CONFIG4_POINTS * MAX_ITER
+    achieved = 28.0 * queries / (best[1] * 1e-3) / 1e9
+    return {"workload": f"config4: {pairs} pairs (frame i, frame i+1 mod 20) x {CONFIG4_POINTS} 3-D points, {MAX_ITER} outer iterations",
+            "value": pairs / (best[1] * 1e-3), "unit": "pairs/s", "kernel_ms": best[1], "host_call_pairs_per_s": pairs / best[0],
+            "nn_queries_per_s": queries / (best[1] * 1e-3), "kernel": f"icp_stream_kernel<{info['block_threads']} threads>",
+            "grid": info["grid_ctas"], "status_ok": bool((g["status"] == 0).all()), "redo_pairs": int(g["redo_pairs"]),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": None,
+                         "note": "28 B per 3-D query (SURVEY.md 8(d)) over the whole loop's device time: an upper-bound "
+                                 "accounting, the kernel also runs the IRLS solves"},
+            "oracle_parity_sample": {"pairs": n,
+                                     "inner_tables_equal": bool(np.array_equal(g["inner"][:n], o["inner"])),
+                                     "corr_hashes_equal": bool(np.array_equal(g["corr_hash"][:n], o["corr_hash"])),
+                                     "max_abs_transform_difference": float(np.abs(g["T"][:n] - o["T"]).max())}}
+
+
+def bench_config5(icp, ctx, torch, dist, dev, stream, rank, world, pairs=1_000_000, chunk=16384):
+    """BASELINE config 5: 1,000,000 config-2 pairs, contiguous slices of the pair index per GPU,
+    streamed through the device in chunks (generate on the host -> H2D -> timed launch), CUDA events
+    on the launching stream, max over ranks; results reduced to a checksum (sum of the transforms)."""
+    from icp_rust_b200.shard import pair_slice
+    b0, b1 = pair_slice(pairs, rank, world)
+    nthreads = max(1, host_cores() // world)
+    cap = min(chunk, b1 - b0)
+    d_src = torch.empty((cap * BEAMS, 2), dtype=torch.float64, device=dev)
+    d_dst = torch.empty((cap * BEAMS, 2), dtype=torch.float64, device=dev)
+    d_off = torch.from_numpy((np.arange(cap + 1, dtype=np.int64) * BEAMS).astype(np.int32)).to(dev)
+    d_T0 = torch.zeros((cap, 6), dtype=torch.float64, device=dev)
+    d_T0[:, 0] = 1.0
+    d_T0[:, 3] = 1.0
+    d_out = torch.empty((cap, 6), dtype=torch.float64, device=dev)
+    kernel_ms = 0.0
+    checksum = np.zeros(6)
+    dist.barrier()
+    wall0 = time.perf_counter()
+    for c0 in range(b0, b1, chunk):
+        n = min(chunk, b1 - c0)
+        src, dst, _, _ = icp.synth_scan_pairs(n, beams=BEAMS, seed=SEED, first_pair=c0, nthreads=nthreads)
+        d_src[:n * BEAMS].copy_(torch.from_numpy(src))
+        d_dst[:n * BEAMS].copy_(torch.from_numpy(dst))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.estimate_batch_device(dict(src=d_src.data_ptr(), src_off=d_off.data_ptr(), dst=d_dst.data_ptr(),
+                                       dst_off=d_off.data_ptr(), init_T=d_T0.data_ptr(), out_T=d_out.data_ptr()),
+                                  n, MAX_ITER, dim=2, max_src=BEAMS, max_dst=BEAMS, stream=stream.cuda_stream, synchronize=False)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        kernel_ms += e0.elapsed_time(e1)
+        checksum += d_out[:n].cpu().numpy().sum(axis=0)
+    wall = time.perf_counter() - wall0
+    t = torch.tensor([kernel_ms, wall], dtype=torch.float64, device=dev)
+    cs = torch.from_numpy(checksum).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(cs, op=dist.ReduceOp.SUM)
+    return {"workload": f"config5: {pairs} synthetic 2D scan pairs x {BEAMS} points, {MAX_ITER} outer iterations, contiguous "
+                        f"slices over {world} GPUs, chunks of {chunk} pairs",
+            "scaling": "strong", "value": pairs / (float(t[0]) * 1e-3), "unit": "pairs/s",
+            "device_seconds_max_over_ranks": float(t[0]) * 1e-3,
+            "wall_seconds_incl_host_generation_and_copies": float(t[1]),
+            "result_checksum": [float(v) for v in cs.cpu().numpy()]}
 
 
 FP64_FLOPS_PER_POINT_EVAL = 80      # SURVEY.md 8(d): residual 10 + 2 rows x (weight, c, 3 jtr, 6 jtj products and sums)
@@ -475,7 +600,8 @@ def fp64_roofline(icp, ctx, h, B, launch_ms, sample=256):
                               + MAX_ITER * FP64_FLOPS_PER_POINT_OUTER)
         tf = flops_pair * B / (launch_ms * 1e-3) / 1e12
         return {"achieved": tf, "peak": pk["fp64_dmul_dadd_tflops"], "unit": "TFLOP/s", "frac": tf / pk["fp64_dmul_dadd_tflops"],
-                "peak_source": "measured, separate DMUL+DADD (profiles/r01_fp64_peak.json; DFMA: %.1f)" % pk["fp64_dfma_tflops"],
+                "peak_source": "BUILDER-measured (tools/fp64/fp64_peak.cu on this pool's B200, not in MEASURED_PEAKS.json), "
+                               "separate DMUL+DADD: profiles/r01_fp64_peak.json; DFMA: %.1f" % pk["fp64_dfma_tflops"],
                 "gn_evaluations_per_pair": evals, "algorithmic_flops_per_pair": flops_pair,
                 "note": "algorithmic flops exclude the exact selections, sqrt/div expansions and index work"}
     except Exception as e:  # pragma: no cover
@@ -510,7 +636,9 @@ def single_pair_latency(icp, ctx, reps=20):
         return {"error": repr(e)}
 
 
-def cpu_baseline(icp, h, B):
+def cpu_baseline(icp, ctx, h, B):
+    """The oracle on every host core over the first pairs of the timed batch (~12 s), and on the same
+    pairs a census: the device's inner-iteration tables and correspondence checksums against it."""
     import oracle
     cores = host_cores()
     src, dst = h["src"].numpy(), h["dst"].numpy()
@@ -521,16 +649,20 @@ def cpu_baseline(icp, h, B):
         t = time.perf_counter()
         o = oracle.icp_estimate_batch(2, src[:n * BEAMS], off, dst[:n * BEAMS], off, T0[:n], MAX_ITER,
                                       nn_mode=oracle.NN_KDTREE, nthreads=cores)
-        return time.perf_counter() - t, o
+        return time.perf_counter() - t, o, off
 
     n0 = min(B, 2 * cores)
-    dt0, _ = run(n0)
+    dt0, _, _ = run(n0)
     n = int(min(B, max(n0, 12.0 / (dt0 / n0))))
-    dt, o = run(n)
+    dt, o, off = run(n)
     diff = float(np.abs(o["T"] - h["out"].numpy()[:n]).max())
+    g = ctx.estimate_batch(src[:n * BEAMS], off, dst[:n * BEAMS], off, T0[:n], MAX_ITER)
+    census = {"pairs": n, "inner_mismatch": int((g["inner"] != o["inner"]).any(axis=1).sum()),
+              "corr_hash_mismatch": int((g["corr_hash"] != o["corr_hash"]).sum()), "redo_pairs": int(g["redo_pairs"]),
+              "larger_run": "profiles/r02_census_*.json (tools/census.py, 131072 pairs)"}
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"first {n} pairs of the timed batch, {dt:.1f} s, one pair per thread, exact kd-tree",
-            "gpu_max_abs_transform_difference_on_sample": diff}
+            "gpu_max_abs_transform_difference_on_sample": diff}, census
 
 
 def main():
@@ -542,6 +674,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="scan pairs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ordered", action="store_true", help="ICP_B200_FLAG_ORDERED_SUMS: reference-order sums")
+    ap.add_argument("--headline-only", action="store_true", help="skip the nn_search / config3 / config4 side measurements")
+    ap.add_argument("--no-config5", action="store_true", help="skip the 1M-pair strong-scaling leg of multi-GPU runs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

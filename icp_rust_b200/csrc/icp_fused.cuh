@@ -63,6 +63,8 @@ struct FusedCtl {
     uint32_t warp_tot[kMaxWarps];
     uint32_t pair;
     uint32_t knife;       // tree mode: a decision of this pair fell inside a guard band (GuardBands)
+    double T6[6];         // lean schedule: the outer transform (kept out of the threads' registers)
+    uint64_t H;           // lean schedule: running correspondence checksum
 };
 
 // Knife-edge guard of the warp-tree mode.  The tree-reduced sums differ from the reference's
@@ -456,6 +458,41 @@ ICP_DEV bool solve_normal_equations_warp(const double m[9], const double jtr[3],
     return true;
 }
 
+// The decisions of one inner iteration (lib.rs:67-81) by one full warp whose lanes hold identical
+// sums: solve, the two break tests with their guard bands, the update; lane 0 publishes
+// {new inner transform, cost, decision} in ctl->bcast and raises ctl->knife.
+ICP_DEV void tree_decide(FusedCtl* ctl, const double jtj[9], const double jtr[3], double error, const Transform& Ti,
+                         double prev_error, const GuardBands& gb)
+{
+    const int lane = lane_id();
+    double delta[3];
+    uint32_t decision = kBreakCap;   // kBreakCap here = "update accepted"
+    Transform Tn = Ti;
+    double det, det_scale;
+    bool knife;
+    if (!solve_normal_equations_warp(jtj, jtr, delta, &det, &det_scale)) {
+        decision = kBreakNone;
+        knife = det_scale > 0. && gb.det > 0.;   // all-zero sums (sigma == 0 rows, lib.rs:245-247) are zero in any order
+    } else {
+        const double dd = (delta[0] * delta[0] + delta[1] * delta[1]) + delta[2] * delta[2];
+        knife = fabs(det) <= gb.det * det_scale || fabs(dd - kDeltaNormThreshold) <= gb.delta * kDeltaNormThreshold;
+        if (dd < kDeltaNormThreshold) {
+            decision = kBreakDelta;
+        } else {
+            knife = knife || fabs(error - prev_error) <= gb.err * fmax(error, prev_error);
+            if (error > prev_error) decision = kBreakError;
+            else Tn = transform_mul(transform_new(delta[0], delta[1], delta[2]), Ti);
+        }
+    }
+    if (lane == 0 && knife) ctl->knife = 1u;
+    if (lane == 0) {
+        ctl->bcast[0] = Tn.r00; ctl->bcast[1] = Tn.r01; ctl->bcast[2] = Tn.r10;
+        ctl->bcast[3] = Tn.r11; ctl->bcast[4] = Tn.tx;  ctl->bcast[5] = Tn.ty;
+        ctl->bcast[6] = error;
+        ctl->bcast[7] = (double)decision;
+    }
+}
+
 // Reduces the threads' partial sums in a fixed tree (split butterfly across lanes, warps in warp
 // order), then warp 0 solves and takes the break decisions of lib.rs:67-81 once and publishes
 // {new inner transform, cost, decision} in ctl->bcast.  Two barriers.  Callers must not write
@@ -482,32 +519,7 @@ ICP_DEV void cta_tree_reduce_solve(FusedCtl* ctl, double acc[16], const Transfor
         const double jtj[9] = {v[0], v[1], v[2], v[1], v[3], v[4], v[2], v[4], v[5]};
         const double jtr[3] = {v[6], v[7], v[8]};
         const double error = v[9];
-        double delta[3];
-        uint32_t decision = kBreakCap;   // kBreakCap here = "update accepted"
-        Transform Tn = Ti;
-        double det, det_scale;
-        bool knife;
-        if (!solve_normal_equations_warp(jtj, jtr, delta, &det, &det_scale)) {
-            decision = kBreakNone;
-            knife = det_scale > 0. && gb.det > 0.;   // all-zero sums (sigma == 0 rows, lib.rs:245-247) are zero in any order
-        } else {
-            const double dd = (delta[0] * delta[0] + delta[1] * delta[1]) + delta[2] * delta[2];
-            knife = fabs(det) <= gb.det * det_scale || fabs(dd - kDeltaNormThreshold) <= gb.delta * kDeltaNormThreshold;
-            if (dd < kDeltaNormThreshold) {
-                decision = kBreakDelta;
-            } else {
-                knife = knife || fabs(error - prev_error) <= gb.err * fmax(error, prev_error);
-                if (error > prev_error) decision = kBreakError;
-                else Tn = transform_mul(transform_new(delta[0], delta[1], delta[2]), Ti);
-            }
-        }
-        if (lane == 0 && knife) ctl->knife = 1u;
-        if (lane == 0) {
-            ctl->bcast[0] = Tn.r00; ctl->bcast[1] = Tn.r01; ctl->bcast[2] = Tn.r10;
-            ctl->bcast[3] = Tn.r11; ctl->bcast[4] = Tn.tx;  ctl->bcast[5] = Tn.ty;
-            ctl->bcast[6] = error;
-            ctl->bcast[7] = (double)decision;
-        }
+        tree_decide(ctl, jtj, jtr, error, Ti, prev_error, gb);
     }
     __syncthreads();
 }

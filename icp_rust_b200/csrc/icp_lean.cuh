@@ -9,20 +9,24 @@
 //   all threads   residuals r = Ti*s - d (lib.rs:230-234) -> shared rows; FAST bin of r per axis
 //                 (value-uniform bins around the previous evaluation's median, icp_cta.cuh) ->
 //                 packed two-axis histogram + the point's bin numbers in shared memory
-//   barrier
+//   named barrier the two service warps wait for the histogram; every other warp only ARRIVES and
+//                 goes on to its partial sums (below), which need neither sigma nor the medians
 //   warp a        axis a: prefix-scan the histogram, find the bin(s) holding the median ranks,
 //                 collect those points' keys by scanning the bin numbers, rank them -> exact median
 //                 ... and, from the SAME histogram, the exact MAD: |r - median| <= t is the window
 //                 [median - t, median + t] of r, so the rank's candidates sit in the two bins the
 //                 window's ends reach (lean_serve_mad; verified before it is trusted); sigma =
 //                 1.4826*MAD, 1/sigma and the next evaluation's bin maps are published by the warp
+//   all threads   (the service warps after serving) Huber weights and the FACTORISED sums of
+//                 lean_accumulate_point: five per axis + the cost, reduced by a fixed warp tree
 //   barrier
 //   (only when lean_serve_mad declines: all threads bin |r - median| into a second histogram,
 //    barrier, warp a serves it as in stage 0, barrier)
-//   all threads   Huber weights, Jacobian rows, 10 partial sums; fixed warp tree; warp 0 solves,
-//                 takes the break decisions and publishes the new inner transform (2 barriers)
+//   warp 0        adds the warps' partials, applies 1/sigma and R, solves, takes the (guarded) break
+//                 decisions and publishes the new inner transform
+//   barrier
 //
-// 4 barriers per evaluation (6 on the second-histogram path) and no per-thread selection state.  Whenever the short path cannot
+// 2 full barriers + 1 arrive per evaluation (4 on the second-histogram path) and no per-thread selection state.  Whenever the short path cannot
 // serve a selection (no estimate yet, rank outside the binned range, more than 32 keys in the
 // rank's bins) the CTA runs the general selection block_median2 over the shared rows instead, so
 // results never depend on which path ran: both return the exact order statistic.
@@ -65,6 +69,7 @@ struct LeanLayout {
     FusedLayout f;               // target arrays, build temporaries, residual rows (gn_r)
     uint32_t bins;               // u32[ncap]: this stage's bin of (axis 0 | axis 1 << 16) per point
     uint32_t pos;                // u32[ncap]: sorted position of the point's match in the previous outer iteration
+    uint32_t dmatch;             // double2[ncap]: the matched target point of this outer iteration (xy)
     uint32_t off_sel, off_ctl, total;
 };
 
@@ -74,7 +79,8 @@ ICP_HD LeanLayout lean_layout(int dim, int ncap, int mcap, int cell_budget, bool
     L.f = fused_layout(dim, ncap, mcap, cell_budget, shared_target, false);
     L.bins = align16(L.f.gn_r + 16u * (uint32_t)ncap);
     L.pos = align16(L.bins + 4u * (uint32_t)ncap);
-    uint32_t u = align128(L.pos + 4u * (uint32_t)ncap);
+    L.dmatch = align16(L.pos + 4u * (uint32_t)ncap);
+    uint32_t u = align128(L.dmatch + 16u * (uint32_t)ncap);
     if (u < L.f.u_bytes) u = L.f.u_bytes;
     L.off_sel = u;
     L.off_ctl = align16(L.off_sel + (uint32_t)sizeof(LeanSel));
@@ -405,6 +411,73 @@ ICP_DEV_NOINLINE void lean_general_selection(LeanSel* sel, const double2* r2v, i
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Factorised normal-equation sums.  Row j of a point has J = [Rj0, Rj1, b_j] (lib.rs:176-184) with
+// Rj0, Rj1 the same for every point, and its weight is c = w_j * g_j with w_j = drho(r_j^2) of the
+// UNSCALED residual (lib.rs:250) and g_j = 1 / sigma_j the same for every point (lib.rs:248).  So
+//   J^T W J = sum_j g_j [ Rj0^2 A_j   Rj0 Rj1 A_j   Rj0 B_j ]      J^T W r = sum_j g_j [ Rj0 D_j ]
+//                       [     .        Rj1^2 A_j    Rj1 B_j ]                          [ Rj1 D_j ]
+//                       [     .            .          C_j   ]                          [   E_j   ]
+// with A = sum w, B = sum w b, C = sum w b^2, D = sum w r, E = sum w b r per axis: five sums per axis
+// that need neither sigma nor g.  The threads form them while the service warps are still selecting
+// the medians, and warp 0 applies g and R once.  Same quantities as lib.rs:242-255 up to summation
+// rounding (tree mode: decisions are guarded, transforms agree to ~1e-13).
+// acc: 0-4 axis 0 (A B C D E), 5-9 axis 1, 10 Huber cost (lib.rs:47-48), 11-15 unused (zero).
+// @region lean_accumulate
+ICP_DEV void lean_accumulate_point(double acc[16], const Transform& Ti, double sx, double sy, double2 rr, bool valid)
+{
+    const double a0 = -sy, a1 = sx;   // jacobian(), lib.rs:176-184
+    const double b0 = Ti.r00 * a0 + Ti.r01 * a1, b1 = Ti.r10 * a0 + Ti.r11 * a1;
+    const double w0r = huber_drho_of_residual(rr.x), w1r = huber_drho_of_residual(rr.y);
+    const double w0 = valid ? w0r : 0., w1 = valid ? w1r : 0.;
+    const double wb0 = w0 * b0, wb1 = w1 * b1;
+    acc[0] = acc[0] + w0; acc[1] = acc[1] + wb0; acc[2] = acc[2] + wb0 * b0;
+    acc[3] = acc[3] + w0 * rr.x; acc[4] = acc[4] + wb0 * rr.x;
+    acc[5] = acc[5] + w1; acc[6] = acc[6] + wb1; acc[7] = acc[7] + wb1 * b1;
+    acc[8] = acc[8] + w1 * rr.y; acc[9] = acc[9] + wb1 * rr.y;
+    const double rho = huber_rho(rr.x * rr.x + rr.y * rr.y);
+    acc[10] = acc[10] + (valid ? rho : 0.);
+}
+
+// Warp 0: adds the warps' partial sums in warp order, applies g and R (see above; an axis with
+// sigma == 0 is skipped as lib.rs:245-247 skips its rows), then solves and decides (tree_decide).
+// Ends with a barrier: every thread then reads ctl->bcast.
+// @region lean_combine
+template <int NW>
+ICP_DEV void lean_combine_solve(FusedCtl* ctl, const LeanSel* sel, const Transform& Ti, double prev_error,
+                                const GuardBands& gb)
+{
+    const int lane = lane_id(), warp = warp_id();
+    if (warp == 0) {
+        double tot = 0.;
+        if (lane < 16) {
+            tot = ctl->red[0][lane];
+            for (int w = 1; w < NW; ++w) tot = tot + ctl->red[w][lane];
+        }
+        double v[11];
+#pragma unroll
+        for (int q = 0; q < 11; ++q) v[q] = shfl_f64(tot, q);
+        double m00 = 0., m01 = 0., m02 = 0., m11 = 0., m12 = 0., m22 = 0., t0 = 0., t1 = 0., t2 = 0.;
+        if (sel->sigma[0] != 0.) {
+            const double g = sel->g[0], p = Ti.r00, q = Ti.r01;
+            const double gA = g * v[0], gB = g * v[1], gD = g * v[3];
+            m00 = (gA * p) * p; m01 = (gA * p) * q; m02 = gB * p; m11 = (gA * q) * q; m12 = gB * q; m22 = g * v[2];
+            t0 = gD * p; t1 = gD * q; t2 = g * v[4];
+        }
+        if (sel->sigma[1] != 0.) {
+            const double g = sel->g[1], p = Ti.r10, q = Ti.r11;
+            const double gA = g * v[5], gB = g * v[6], gD = g * v[8];
+            m00 = m00 + (gA * p) * p; m01 = m01 + (gA * p) * q; m02 = m02 + gB * p;
+            m11 = m11 + (gA * q) * q; m12 = m12 + gB * q; m22 = m22 + g * v[7];
+            t0 = t0 + gD * p; t1 = t1 + gD * q; t2 = t2 + g * v[9];
+        }
+        const double jtj[9] = {m00, m01, m02, m01, m11, m12, m02, m12, m22};
+        const double jtr[3] = {t0, t1, t2};
+        tree_decide(ctl, jtj, jtr, v[10], Ti, prev_error, gb);
+    }
+    __syncthreads();
+}
+
 // Phase timing of CTA 0 (debug builds only, -DICP_LEAN_TIMING): thread 0 accumulates clock64()
 // differences between the barriers of an evaluation and prints the per-pair averages.
 #ifdef ICP_LEAN_TIMING
@@ -434,6 +507,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
     double2* r2v = reinterpret_cast<double2*>(U + L.gn_r);
     uint32_t* binv = reinterpret_cast<uint32_t*>(U + LL.bins);
     uint32_t* prev_pos = reinterpret_cast<uint32_t*>(U + LL.pos);
+    double2* d2v = reinterpret_cast<double2*>(U + LL.dmatch);
     uint32_t* h0 = sel->lh[0] + kLeanHistBase;
     uint32_t* h1 = sel->lh[1] + kLeanHistBase;
 
@@ -461,10 +535,10 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
             m = (int)(p.dst_off[pair + 1] - p.dst_off[pair]);
             dst = p.dst + (size_t)p.dst_off[pair] * DIM;
         }
-        Transform T;
-        T.r00 = p.init_T[(size_t)pair * 6 + 0]; T.r01 = p.init_T[(size_t)pair * 6 + 1];
-        T.r10 = p.init_T[(size_t)pair * 6 + 2]; T.r11 = p.init_T[(size_t)pair * 6 + 3];
-        T.tx = p.init_T[(size_t)pair * 6 + 4];  T.ty = p.init_T[(size_t)pair * 6 + 5];
+        // the outer transform and the checksum live in shared memory (ctl->T6, ctl->H): they are
+        // touched once per outer iteration and would otherwise cost every thread 14 registers
+        if (tid < 6) ctl->T6[tid] = p.init_T[(size_t)pair * 6 + tid];
+        if (tid == 0) ctl->H = 0ull;
 
         int status = kPairOk;
         if (m == 0 && n > 0 && p.max_iter > 0) status = kPairEmptyTarget;
@@ -507,7 +581,6 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
             sel->est_sigma[tid] = 0.;
         }
 
-        uint64_t H = 0;  // meaningful in thread 0
         const uint64_t corr_base = (p.shared_src ? (uint64_t)pair * (uint64_t)n : (uint64_t)p.src_off[pair]) *
                                    (p.corr_mode == 2 ? p.max_iter : 1u);
 
@@ -516,17 +589,24 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
 // @region lean_search
             // ---- transform (lib.rs:113-116) + correspondence search (lib.rs:118-124): one inlined
             // copy of the search; queries and matched points go through the thread's own row slots
-            double sx[PPT], sy[PPT], dx[PPT], dy[PPT];
+            double sx[PPT], sy[PPT];
             uint64_t hpart = 0;
+            {
+                Transform T;   // visible: written before the barrier that ended the previous iteration / the input check
+                T.r00 = ctl->T6[0]; T.r01 = ctl->T6[1]; T.r10 = ctl->T6[2]; T.r11 = ctl->T6[3]; T.tx = ctl->T6[4]; T.ty = ctl->T6[5];
 #pragma unroll
-            for (int k = 0; k < PPT; ++k) {
-                const int i = tid + k * THREADS;
-                sx[k] = 0.; sy[k] = 0.; dx[k] = 0.; dy[k] = 0.;
-                if (i < n) {
-                    transform_apply(T, src[(size_t)i * DIM + 0], src[(size_t)i * DIM + 1], &sx[k], &sy[k]);
-                    double2 q;
-                    q.x = sx[k]; q.y = sy[k];
-                    r2v[i] = q;
+                for (int k = 0; k < PPT; ++k) {
+                    const int i = tid + k * THREADS;
+                    sx[k] = 0.; sy[k] = 0.;
+                    double2 zero;
+                    zero.x = 0.; zero.y = 0.;
+                    if (i >= n) d2v[i] = zero;   // slots beyond the scan: finite residuals, weight 0
+                    if (i < n) {
+                        transform_apply(T, src[(size_t)i * DIM + 0], src[(size_t)i * DIM + 1], &sx[k], &sy[k]);
+                        double2 q;
+                        q.x = sx[k]; q.y = sy[k];
+                        r2v[i] = q;
+                    }
                 }
             }
 #pragma unroll 1
@@ -555,19 +635,11 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                     idx = r.idx;
                     prev_pos[i] = (uint32_t)r.pos;
                 }
-                r2v[i] = d;
+                d2v[i] = d;
                 hpart += mix64(((uint64_t)(uint32_t)i << 32) | (uint64_t)(uint32_t)idx);
                 if (p.out_corr) {
                     if (p.corr_mode == 2) p.out_corr[corr_base + (uint64_t)it * (uint64_t)n + (uint64_t)i] = idx;
                     else if (p.corr_mode == 1 && it + 1 == p.max_iter) p.out_corr[corr_base + (uint64_t)i] = idx;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < PPT; ++k) {
-                const int i = tid + k * THREADS;
-                if (i < n) {
-                    const double2 d = r2v[i];
-                    dx[k] = d.x; dy[k] = d.y;
                 }
             }
             hpart = warp_sum_u64(hpart);
@@ -576,7 +648,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
             if (tid == 0) {
                 uint64_t h = 0;
                 for (int w = 0; w < NW; ++w) h += ctl->hash_part[w];
-                H = H * 0x100000001B3ull + h;
+                ctl->H = ctl->H * 0x100000001B3ull + h;
             }
             ICP_LT_MARK(1)
 
@@ -597,42 +669,60 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                         const int i = tid + k * THREADS;
                         double tx_, ty_;
                         transform_apply(Ti, sx[k], sy[k], &tx_, &ty_);
-                        rr[k].x = tx_ - dx[k];
-                        rr[k].y = ty_ - dy[k];
+                        const double2 d = d2v[i];
+                        rr[k].x = tx_ - d.x;
+                        rr[k].y = ty_ - d.y;
                         if (i < n) r2v[i] = rr[k];
                     }
-                    bool served = false;
-                    if (sel->valid[0] & sel->valid[1]) {
-                        {
-                            const float lo0 = sel->lo0[0], lo1 = sel->lo0[1], s0 = sel->sc0[0], s1 = sel->sc0[1];
+                    // fast: both bin maps usable (uniform: written before the previous evaluation's last barrier)
+                    const bool fast = (sel->valid[0] & sel->valid[1]) != 0;
+                    if (fast) {
+                        const float lo0 = sel->lo0[0], lo1 = sel->lo0[1], s0 = sel->sc0[0], s1 = sel->sc0[1];
 #pragma unroll
-                            for (int k = 0; k < PPT; ++k) {
-                                const int i = tid + k * THREADS;
-                                if (i < n) {
-                                    const uint32_t b0 = lean_bin(rr[k].x, lo0, s0);
-                                    const uint32_t b1 = lean_bin(rr[k].y, lo1, s1);
-                                    lean_insert(h0, sel->bucket[0], b0, 1u, 0, i);
-                                    lean_insert(h0, sel->bucket[1], b1, 0x10000u, 16, i);
-                                    binv[i] = b0 | (b1 << 16);
-                                }
+                        for (int k = 0; k < PPT; ++k) {
+                            const int i = tid + k * THREADS;
+                            if (i < n) {
+                                const uint32_t b0 = lean_bin(rr[k].x, lo0, s0);
+                                const uint32_t b1 = lean_bin(rr[k].y, lo1, s1);
+                                lean_insert(h0, sel->bucket[0], b0, 1u, 0, i);
+                                lean_insert(h0, sel->bucket[1], b1, 0x10000u, 16, i);
+                                binv[i] = b0 | (b1 << 16);
                             }
                         }
-                        __syncthreads();
-                        ICP_LT_MARK(2)
-                        if (warp < 2) {
-                            double v = 0., dev = 0.;
-                            const float mlo = sel->lo0[warp], msc = sel->sc0[warp];
-                            const bool ok = lean_serve(h0, sel->bucket[warp], binv, r2v, sel->s.list[warp], n, warp, 0, 0., &v,
-                                                       sel->s.hist[warp]);
-                            const bool ok1 = ok && lean_serve_mad(sel->bucket[warp], r2v, sel->s.list[warp], sel->s.hist[warp], n,
-                                                                  warp, v, mlo, msc, &dev);
-                            if (lane == 0) {
-                                sel->med[warp] = v; sel->ok[warp] = ok ? 1 : 0; sel->ok1[warp] = ok1 ? 1 : 0;
-                                if (ok1) lean_publish(sel, warp, v, kPpf34 * dev);   // stats.rs:39-47
-                            }
+                        // the service warps wait for the whole histogram; everybody else goes on
+                        if (warp < 2) icp_bar_sync(1, THREADS);
+                        else icp_bar_arrive(1, THREADS);
+                    }
+                    ICP_LT_MARK(2)
+                    if (fast && warp < 2) {
+                        double v = 0., dev = 0.;
+                        const float mlo = sel->lo0[warp], msc = sel->sc0[warp];
+                        const bool ok = lean_serve(h0, sel->bucket[warp], binv, r2v, sel->s.list[warp], n, warp, 0, 0., &v,
+                                                   sel->s.hist[warp]);
+                        const bool ok1 = ok && lean_serve_mad(sel->bucket[warp], r2v, sel->s.list[warp], sel->s.hist[warp], n,
+                                                              warp, v, mlo, msc, &dev);
+                        if (lane == 0) {
+                            sel->med[warp] = v; sel->ok[warp] = ok ? 1 : 0; sel->ok1[warp] = ok1 ? 1 : 0;
+                            if (ok1) lean_publish(sel, warp, v, kPpf34 * dev);   // stats.rs:39-47
                         }
-                        __syncthreads();
-                        ICP_LT_MARK(3)
+                    }
+// @region lean_accumulate
+                    // Huber weights (lib.rs:250), Jacobian (lib.rs:176-184), Huber cost (lib.rs:47-48):
+                    // factorised partial sums, in the shadow of the service warps
+                    double acc[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) acc[q] = 0.;
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k) {
+                        const int i = tid + k * THREADS;
+                        lean_accumulate_point(acc, Ti, sx[k], sy[k], rr[k], i < n);
+                    }
+                    warp_reduce16(acc);
+                    if ((lane & 1) == 0) ctl->red[warp][warp_reduce16_owner(lane)] = acc[0];
+                    __syncthreads();
+                    ICP_LT_MARK(3)
+                    bool served = false;
+                    if (fast) {
                         if (sel->ok[0] & sel->ok[1] & sel->ok1[0] & sel->ok1[1]) {
                             served = true;
                             lean_zero_lh<THREADS>(sel->lh[0]);
@@ -673,25 +763,12 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                     } else if (!(sel->ok1[0] & sel->ok1[1])) {
                         lean_zero_lh<THREADS>(sel->lh[1]);
                     }
-// @region lean_accumulate
-                    // row weights (lib.rs:245-250), Jacobian (lib.rs:176-184), Huber cost (lib.rs:47-48)
-                    double sigma[2];
-                    sigma[0] = sel->sigma[0]; sigma[1] = sel->sigma[1];
-                    const double g0 = sel->g[0], g1 = sel->g[1];
-                    double acc[16];   // 0-5 upper triangle of jtj, 6-8 jtr, 9 cost, 10-15 unused (zero)
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) acc[q] = 0.;
-#pragma unroll
-                    for (int k = 0; k < PPT; ++k) {
-                        const int i = tid + k * THREADS;
-                        tree_accumulate_point(acc, Ti, sx[k], sy[k], rr[k], sigma, g0, g1, i < n);
-                    }
 // @region lean_reduce
                     ICP_LT_MARK(6)
 #ifdef ICP_LEAN_TIMING
                     ++lt_e;
 #endif
-                    cta_tree_reduce_solve<NW>(ctl, acc, Ti, prev_error, p.guard);
+                    lean_combine_solve<NW>(ctl, sel, Ti, prev_error, p.guard);
                     ICP_LT_MARK(7)
                     const uint32_t decision = (uint32_t)ctl->bcast[7];
                     if (decision != kBreakCap) { why = decision; break; }
@@ -712,23 +789,28 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                     const int i = tid + k * THREADS;
                     double tx_, ty_;
                     transform_apply(Ti, sx[k], sy[k], &tx_, &ty_);
-                    const double rx = tx_ - dx[k], ry = ty_ - dy[k];
+                    const double2 d = d2v[i];
+                    const double rx = tx_ - d.x, ry = ty_ - d.y;
                     const double rh = huber_rho(rx * rx + ry * ry);
                     e = e + (i < n ? rh : 0.);
                 }
                 const double tot = cta_tree_sum<NW>(ctl, e);
                 if (tid == 0) p.out_cost[pair] = tot;
             }
-            T = transform_mul(Ti, T);  // lib.rs:127
-            if (tid == 0 && p.out_inner) p.out_inner[(size_t)pair * p.max_iter + it] = accepted | (why << 16);
-            __syncthreads();  // rows are rewritten by the next search; ctl->bcast by the next solve
+            if (tid == 0) {   // lib.rs:127
+                Transform T;
+                T.r00 = ctl->T6[0]; T.r01 = ctl->T6[1]; T.r10 = ctl->T6[2]; T.r11 = ctl->T6[3]; T.tx = ctl->T6[4]; T.ty = ctl->T6[5];
+                T = transform_mul(Ti, T);
+                ctl->T6[0] = T.r00; ctl->T6[1] = T.r01; ctl->T6[2] = T.r10; ctl->T6[3] = T.r11; ctl->T6[4] = T.tx; ctl->T6[5] = T.ty;
+                if (p.out_inner) p.out_inner[(size_t)pair * p.max_iter + it] = accepted | (why << 16);
+            }
+            __syncthreads();  // rows are rewritten by the next search; ctl->bcast by the next solve; T6 is read
         }
         if (tid == 0) {
-            p.out_T[(size_t)pair * 6 + 0] = T.r00; p.out_T[(size_t)pair * 6 + 1] = T.r01;
-            p.out_T[(size_t)pair * 6 + 2] = T.r10; p.out_T[(size_t)pair * 6 + 3] = T.r11;
-            p.out_T[(size_t)pair * 6 + 4] = T.tx;  p.out_T[(size_t)pair * 6 + 5] = T.ty;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) p.out_T[(size_t)pair * 6 + q] = ctl->T6[q];
             if (p.out_status) p.out_status[pair] = kPairOk;
-            if (p.out_hash) p.out_hash[pair] = H;
+            if (p.out_hash) p.out_hash[pair] = ctl->H;
             if (p.out_cost && p.max_iter == 0) p.out_cost[pair] = 0.;
             fused_report_knife(p, ctl, pair);
         }

@@ -27,8 +27,19 @@ static __device__ __forceinline__ smem_ref smem_adv2(smem_ref r, int n) { return
 static __device__ __forceinline__ double2 smem_ld2(smem_ref r, int idx)
 {
     double2 v;
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(r + 16u * (uint32_t)idx));
+    // volatile + "memory": the load must not be hoisted across the shared stores / barriers around it
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(r + 16u * (uint32_t)idx) : "memory");
     return v;
+}
+// Named barriers (PTX bar.sync / bar.arrive with an id and a thread count): `arrive` does not wait.
+// Writes a thread made before arriving are visible to the threads that leave the matching sync.
+static __device__ __forceinline__ void icp_bar_sync(int id, int count)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+static __device__ __forceinline__ void icp_bar_arrive(int id, int count)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 #endif
 

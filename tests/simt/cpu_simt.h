@@ -33,12 +33,15 @@ struct Warp {
     uint32_t gen = 0;
 };
 
+struct NamedBar { int arrived = 0; uint32_t gen = 0; };
+
 struct Cta {
     std::vector<unsigned char> smem;
     int nthreads = 0;
     int bar_arrived = 0;
     uint32_t bar_gen = 0;
     int bar_or[2] = {0, 0};
+    NamedBar named[16];
     std::vector<Warp> warps;
 };
 
@@ -188,6 +191,20 @@ static inline int __syncthreads_or(int pred)
     return c.bar_or[g & 1];
 }
 static inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_exchange(0); }
+
+// named barriers: bar.arrive (does not wait) / bar.sync with an id and a thread count
+static inline void icp_bar_arrive(int id, int count)
+{
+    simt::NamedBar& b = simt::st().cta->named[id];
+    if (++b.arrived == count) { b.arrived = 0; b.gen++; }
+}
+static inline void icp_bar_sync(int id, int count)
+{
+    simt::NamedBar& b = simt::st().cta->named[id];
+    const uint32_t g = b.gen;
+    if (++b.arrived == count) { b.arrived = 0; b.gen = g + 1; }
+    else while (b.gen == g) simt::yield();
+}
 
 static inline uint32_t __shfl_sync(unsigned, uint32_t v, int src) { return simt::warp_exchange(v)[src & 31]; }
 static inline int __shfl_sync(unsigned m, int v, int src) { return (int)__shfl_sync(m, (uint32_t)v, src); }

@@ -103,10 +103,14 @@ def test_fused_real_scans(scans2d, schedule, ordered):
         T0 = [I6, I6]
         g = E.icp_fused(srcs, dsts, T0, max_iter=3, variant=1, grid=2, ordered=ordered)
         _compare(g, _oracle_ref(srcs, dsts, T0, 3), srcs, 3, ordered)
-        if ordered is not True:   # tree reductions are schedule-independent: same bits under every interleaving,
-            # and the same bits on either schedule of the warp-tree mode (icp_fused.cuh / icp_lean.cuh)
-            ref = E.icp_fused(srcs, dsts, T0, max_iter=3, variant=1, grid=1, ordered=False)
+        if ordered is not True:   # tree reductions are schedule-independent: same bits under every interleaving
+            # (the lean schedule sums factorised terms, icp_lean.cuh: its bits differ from icp_fused.cuh's
+            # tree mode, by rounding only)
+            E.set_schedule(0)
+            ref = E.icp_fused(srcs, dsts, T0, max_iter=3, variant=1, grid=1, ordered=ordered)
             assert np.array_equal(ref["T"], g["T"])
+            other = E.icp_fused(srcs, dsts, T0, max_iter=3, variant=1, grid=1, ordered=False)
+            assert np.abs(other["T"] - g["T"]).max() <= 1e-11
     finally:
         E.set_schedule(0)
 
@@ -155,7 +159,7 @@ def test_lean_crowded_and_odd_sizes():
     g = E.icp_fused(srcs, dsts, T0, max_iter=3, variant=1, grid=2, ordered="lean")
     _compare(g, _oracle_ref(srcs, dsts, T0, 3), srcs, 3, ordered=False)
     ref = E.icp_fused(srcs, dsts, T0, max_iter=3, variant=1, grid=1, ordered=False)
-    assert np.array_equal(ref["T"], g["T"]) and np.array_equal(ref["inner"], g["inner"])
+    assert np.abs(ref["T"] - g["T"]).max() <= 1e-11 and np.array_equal(ref["inner"], g["inner"])
 
 
 # ------------------------------------------------------------------ streaming (large-scan) kernel
