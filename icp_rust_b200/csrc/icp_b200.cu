@@ -160,7 +160,8 @@ int plan_launch(icp_b200_context* ctx, uint32_t dim, bool shared_target, bool or
                 uint32_t pairs, LaunchPlan* plan)
 {
     const Instance* inst = nullptr;
-    auto fits = [&](const Instance* c) { return c->ordered == ordered && (uint32_t)(c->threads * c->ppt) >= max_n; };
+    auto lean_of = [&](const Instance* c) { return !ordered && ctx->use_lean && c->lean[dim - 2][shared_target ? 1 : 0] != nullptr; };
+    auto fits = [&](const Instance* c) { return c->ordered == ordered && (uint32_t)c->capacity(lean_of(c)) >= max_n; };
     if (ctx->force_instance >= 0 && ctx->force_instance < kNumInstances && fits(kInstances[ctx->force_instance]))
         inst = kInstances[ctx->force_instance];
     for (int i = 0; !inst && i < kNumInstances; ++i)
@@ -168,10 +169,10 @@ int plan_launch(icp_b200_context* ctx, uint32_t dim, bool shared_target, bool or
     if (inst) {
         plan->inst = inst;
         plan->mcap = (int)((max_m + 7u) & ~7u);
-        plan->layout = fused_layout((int)dim, inst->threads * inst->ppt, plan->mcap, ctx->cell_budget, shared_target, ordered);
-        plan->lean = !ordered && ctx->use_lean && inst->lean[dim - 2][shared_target ? 1 : 0] != nullptr;
+        plan->lean = lean_of(inst);
+        plan->layout = fused_layout((int)dim, inst->capacity(plan->lean), plan->mcap, ctx->cell_budget, shared_target, ordered);
         if (plan->lean)
-            plan->layout.total = lean_layout((int)dim, inst->threads * inst->ppt, plan->mcap, ctx->cell_budget, shared_target).total;
+            plan->layout.total = lean_layout((int)dim, inst->capacity(true), plan->mcap, ctx->cell_budget, shared_target).total;
         if (!shared_target && max_m > 65528u) inst = nullptr;                   // u16 indices of the shared-memory grid
         else if ((int)plan->layout.total > ctx->max_smem_optin) inst = nullptr;  // does not fit one SM
     }
@@ -272,7 +273,7 @@ int launch_range(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_
     p.ws_stride = plan.ws_stride;
     p.pair_begin = begin; p.pair_end = end;
     p.mcap = plan.mcap;
-    p.ncap = plan.stream ? (int)plan.n_cap : plan.inst->threads * plan.inst->ppt;
+    p.ncap = plan.stream ? (int)plan.n_cap : plan.inst->capacity(plan.lean);
     if (guarded) {
         p.redo_list = ctx->redo_list.as<uint32_t>();
         p.redo_count = ctx->counters.as<uint32_t>() + kCtrRedoCount;
@@ -305,7 +306,7 @@ int launch_redo(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_t
     r.ws_stride = redo.ws_stride;
     r.pair_begin = 0; r.pair_end = b.batch;
     r.mcap = redo.mcap;
-    r.ncap = redo.stream ? (int)redo.n_cap : redo.inst->threads * redo.inst->ppt;
+    r.ncap = redo.stream ? (int)redo.n_cap : redo.inst->capacity(false);
     return launch_plan(ctx, redo, r, (int)std::min<uint32_t>((uint32_t)redo.grid, b.batch), stream);
 }
 
@@ -854,12 +855,20 @@ int icp_b200_target_search_device(icp_b200_target* t, const double* queries, uin
     const long long want = (long long)((nq + threads - 1) / threads);
     const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)ctx->sm_count * 8));
     ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], st));
-    if (t->dim == 2) nn_search_kernel<2><<<grid, threads, 0, st>>>(tv, queries, nq, out_index);
+    // 2-D targets with seeds: the warp-cooperative kernel (coherent queries: consecutive queries share
+    // their candidates; incoherent warps fall back to private walks inside it).  ICP_B200_NN_WARP=0: private walks only.
+    if (t->dim == 2 && tv.pf != nullptr && env_int("ICP_B200_NN_WARP", 1) != 0) {
+        const long long wantw = (long long)((nq + kNnWarpThreads - 1) / kNnWarpThreads);
+        const int gridw = (int)std::max<long long>(1, std::min<long long>(wantw, (long long)ctx->sm_count * 16));
+        nn_search_warp_kernel<<<gridw, kNnWarpThreads, kNnWarpShared, st>>>(tv, queries, nq, out_index);
+        ctx->info.grid_ctas = (uint32_t)gridw;
+    } else if (t->dim == 2) nn_search_kernel<2><<<grid, threads, 0, st>>>(tv, queries, nq, out_index);
     else nn_search_kernel<3><<<grid, threads, 0, st>>>(tv, queries, nq, out_index);
     ICP_CUDA(ctx, cudaGetLastError());
     ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][1], st));
     ctx->info.kernel_launches += 1;
-    ctx->info.grid_ctas = (uint32_t)grid; ctx->info.block_threads = threads; ctx->info.smem_bytes = 0;
+    if (!(t->dim == 2 && tv.pf != nullptr && env_int("ICP_B200_NN_WARP", 1) != 0)) ctx->info.grid_ctas = (uint32_t)grid;
+    ctx->info.block_threads = threads; ctx->info.smem_bytes = 0;
     if (synchronize) {
         ICP_CUDA(ctx, cudaStreamSynchronize(st));
         ICP_CUDA(ctx, cudaEventElapsedTime(&ctx->info.kernel_ms, ctx->ev[0][0], ctx->ev[0][1]));

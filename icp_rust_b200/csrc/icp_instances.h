@@ -11,8 +11,10 @@ typedef void (*FusedKernel)(FusedParams);
 struct Instance {
     int threads, ppt, minb;
     bool ordered;         // reference-order sums (bit-exact) vs warp-tree reductions
+    bool svc;             // lean kernels: warps 0 and 1 are dedicated service warps (capacity (threads - 64) * ppt)
     FusedKernel k[2][2];  // [dim-2][shared target]
     FusedKernel lean[2][2];   // icp_lean.cuh schedule of the warp-tree mode (null for ordered instances)
+    int capacity(bool lean_schedule) const { return (threads - (lean_schedule && svc ? 64 : 0)) * ppt; }
 };
 
 typedef void (*StreamKernel)(StreamParams);

@@ -492,12 +492,18 @@ ICP_DEV void lean_combine_solve(FusedCtl* ctl, const LeanSel* sel, const Transfo
 
 // ---------------------------------------------------------------------------------------------
 // @region lean_pair_setup
-template <int THREADS, int PPT, int DIM, bool SHARED_TARGET, int MINB>
+// SVC: warps 0 and 1 are DEDICATED service warps — they own no points, so the medians are being
+// served from the moment the histogram is complete while the THREADS - 64 worker threads form the
+// factorised sums; capacity (THREADS - 64) * PPT points.  !SVC: every warp owns points and warps
+// 0 and 1 add their own sums after serving (capacity THREADS * PPT).
+template <int THREADS, int PPT, int DIM, bool SHARED_TARGET, int MINB, bool SVC>
 ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
 {
     constexpr int NW = THREADS / 32;
-    constexpr int NCAP = THREADS * PPT;
-    static_assert(THREADS >= 64, "two service warps");
+    constexpr int WT0 = SVC ? 64 : 0;            // first worker thread
+    constexpr int WTHREADS = THREADS - WT0;      // threads that own points
+    constexpr int NCAP = WTHREADS * PPT;
+    static_assert(THREADS >= 64 && WTHREADS >= 32, "two service warps (+ at least one worker warp)");
     ICP_SHARED_DYN(smem);
     const LeanLayout LL = lean_layout(DIM, NCAP, p.mcap, p.cell_budget, SHARED_TARGET);
     const FusedLayout& L = LL.f;
@@ -512,6 +518,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
     uint32_t* h1 = sel->lh[1] + kLeanHistBase;
 
     const int tid = (int)threadIdx.x, lane = lane_id(), warp = warp_id();
+    const bool worker = !SVC || warp >= 2;
+    const int wtid = tid - WT0;                  // point i = wtid + k * WTHREADS belongs to worker wtid
 
     lean_zero_lh<THREADS>(sel->lh[0]);
     lean_zero_lh<THREADS>(sel->lh[1]);
@@ -594,19 +602,12 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
             {
                 Transform T;   // visible: written before the barrier that ended the previous iteration / the input check
                 T.r00 = ctl->T6[0]; T.r01 = ctl->T6[1]; T.r10 = ctl->T6[2]; T.r11 = ctl->T6[3]; T.tx = ctl->T6[4]; T.ty = ctl->T6[5];
-#pragma unroll
-                for (int k = 0; k < PPT; ++k) {
-                    const int i = tid + k * THREADS;
-                    sx[k] = 0.; sy[k] = 0.;
-                    double2 zero;
-                    zero.x = 0.; zero.y = 0.;
-                    if (i >= n) d2v[i] = zero;   // slots beyond the scan: finite residuals, weight 0
-                    if (i < n) {
-                        transform_apply(T, src[(size_t)i * DIM + 0], src[(size_t)i * DIM + 1], &sx[k], &sy[k]);
-                        double2 q;
-                        q.x = sx[k]; q.y = sy[k];
-                        r2v[i] = q;
-                    }
+                for (int i = tid; i < NCAP; i += THREADS) {
+                    double2 q;
+                    q.x = 0.; q.y = 0.;
+                    if (i < n) transform_apply(T, src[(size_t)i * DIM + 0], src[(size_t)i * DIM + 1], &q.x, &q.y);
+                    else d2v[i] = q;   // slots beyond the scan: zero points, finite residuals, weight 0
+                    r2v[i] = q;
                 }
             }
 #pragma unroll 1
@@ -650,6 +651,13 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                 for (int w = 0; w < NW; ++w) h += ctl->hash_part[w];
                 ctl->H = ctl->H * 0x100000001B3ull + h;
             }
+            // the transformed source points of the thread's own slots (the search walked the scan with
+            // every thread; the rows below belong to the workers)
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                const double2 q = worker ? r2v[wtid + k * WTHREADS] : d2v[0];
+                sx[k] = q.x; sy[k] = q.y;
+            }   // (a worker reads and later overwrites only its own slots of r2v: no barrier needed here)
             ICP_LT_MARK(1)
 
 // @region lean_irls
@@ -663,32 +671,32 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                 for (int inner = 0; inner < kInnerMaxIter; ++inner) {
 // @region lean_stage0
                     // residuals (lib.rs:230-234): registers + shared rows (read by the service warps)
-                    double2 rr[PPT];
-#pragma unroll
-                    for (int k = 0; k < PPT; ++k) {
-                        const int i = tid + k * THREADS;
-                        double tx_, ty_;
-                        transform_apply(Ti, sx[k], sy[k], &tx_, &ty_);
-                        const double2 d = d2v[i];
-                        rr[k].x = tx_ - d.x;
-                        rr[k].y = ty_ - d.y;
-                        if (i < n) r2v[i] = rr[k];
-                    }
                     // fast: both bin maps usable (uniform: written before the previous evaluation's last barrier)
                     const bool fast = (sel->valid[0] & sel->valid[1]) != 0;
-                    if (fast) {
+                    if (worker) {
                         const float lo0 = sel->lo0[0], lo1 = sel->lo0[1], s0 = sel->sc0[0], s1 = sel->sc0[1];
 #pragma unroll
                         for (int k = 0; k < PPT; ++k) {
-                            const int i = tid + k * THREADS;
+                            const int i = wtid + k * WTHREADS;
+                            double tx_, ty_;
+                            transform_apply(Ti, sx[k], sy[k], &tx_, &ty_);
+                            const double2 d = d2v[i];
+                            double2 rr;
+                            rr.x = tx_ - d.x;
+                            rr.y = ty_ - d.y;
                             if (i < n) {
-                                const uint32_t b0 = lean_bin(rr[k].x, lo0, s0);
-                                const uint32_t b1 = lean_bin(rr[k].y, lo1, s1);
-                                lean_insert(h0, sel->bucket[0], b0, 1u, 0, i);
-                                lean_insert(h0, sel->bucket[1], b1, 0x10000u, 16, i);
-                                binv[i] = b0 | (b1 << 16);
+                                r2v[i] = rr;   // the accumulation below reads it back: the rows need no registers
+                                if (fast) {
+                                    const uint32_t b0 = lean_bin(rr.x, lo0, s0);
+                                    const uint32_t b1 = lean_bin(rr.y, lo1, s1);
+                                    lean_insert(h0, sel->bucket[0], b0, 1u, 0, i);
+                                    lean_insert(h0, sel->bucket[1], b1, 0x10000u, 16, i);
+                                    binv[i] = b0 | (b1 << 16);
+                                }
                             }
                         }
+                    }
+                    if (fast) {
                         // the service warps wait for the whole histogram; everybody else goes on
                         if (warp < 2) icp_bar_sync(1, THREADS);
                         else icp_bar_arrive(1, THREADS);
@@ -712,10 +720,12 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                     double acc[16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q) acc[q] = 0.;
+                    if (worker) {
 #pragma unroll
-                    for (int k = 0; k < PPT; ++k) {
-                        const int i = tid + k * THREADS;
-                        lean_accumulate_point(acc, Ti, sx[k], sy[k], rr[k], i < n);
+                        for (int k = 0; k < PPT; ++k) {
+                            const int i = wtid + k * WTHREADS;
+                            lean_accumulate_point(acc, Ti, sx[k], sy[k], r2v[i], i < n);   // slots >= n hold zeros
+                        }
                     }
                     warp_reduce16(acc);
                     if ((lane & 1) == 0) ctl->red[warp][warp_reduce16_owner(lane)] = acc[0];
@@ -733,10 +743,11 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                             lean_zero_lh<THREADS>(sel->lh[0]);
 #pragma unroll
                             for (int k = 0; k < PPT; ++k) {
-                                const int i = tid + k * THREADS;
-                                if (i < n) {
-                                    const uint32_t b0 = lean_bin(fabs(rr[k].x - m0), l0, s0);
-                                    const uint32_t b1 = lean_bin(fabs(rr[k].y - m1), l1, s1);
+                                const int i = wtid + k * WTHREADS;
+                                if (worker && i < n) {
+                                    const double2 rr = r2v[i];
+                                    const uint32_t b0 = lean_bin(fabs(rr.x - m0), l0, s0);
+                                    const uint32_t b1 = lean_bin(fabs(rr.y - m1), l1, s1);
                                     lean_insert(h1, sel->bucket[0], b0, 1u, 0, i);
                                     lean_insert(h1, sel->bucket[1], b1, 0x10000u, 16, i);
                                     binv[i] = b0 | (b1 << 16);
@@ -784,15 +795,17 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                 // iteration's transformed source / matched target points
                 __syncthreads();   // every thread has read the last solve's broadcast
                 double e = 0.;
+                if (worker) {
 #pragma unroll
-                for (int k = 0; k < PPT; ++k) {
-                    const int i = tid + k * THREADS;
-                    double tx_, ty_;
-                    transform_apply(Ti, sx[k], sy[k], &tx_, &ty_);
-                    const double2 d = d2v[i];
-                    const double rx = tx_ - d.x, ry = ty_ - d.y;
-                    const double rh = huber_rho(rx * rx + ry * ry);
-                    e = e + (i < n ? rh : 0.);
+                    for (int k = 0; k < PPT; ++k) {
+                        const int i = wtid + k * WTHREADS;
+                        double tx_, ty_;
+                        transform_apply(Ti, sx[k], sy[k], &tx_, &ty_);
+                        const double2 d = d2v[i];
+                        const double rx = tx_ - d.x, ry = ty_ - d.y;
+                        const double rh = huber_rho(rx * rx + ry * ry);
+                        e = e + (i < n ? rh : 0.);
+                    }
                 }
                 const double tot = cta_tree_sum<NW>(ctl, e);
                 if (tid == 0) p.out_cost[pair] = tot;

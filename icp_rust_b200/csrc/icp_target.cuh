@@ -173,3 +173,31 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, 2) nn_search_kernel(TargetView tv, const 
 }
 
 }  // namespace icp
+
+namespace icp {
+
+// Warp-cooperative search kernel (2-D targets with seeds and binary32 copies): warp w takes queries
+// [32 w', 32 w' + 32) of the array — consecutive queries, i.e. consecutive beams when the queries are
+// scans.  target_nn_search2_warp (icp_target_nn.cuh).  256 threads, 512 B of shared memory per warp.
+constexpr int kNnWarpThreads = 256;
+ICP_GLOBAL void ICP_LAUNCH_BOUNDS(kNnWarpThreads, 4) nn_search_warp_kernel(TargetView tv, const double* queries,
+                                                                           unsigned long long nq, int32_t* out_idx)
+{
+    ICP_SHARED_DYN(nn_smem);
+    NnWarpScratch* ws = reinterpret_cast<NnWarpScratch*>(nn_smem) + warp_id();
+    const int lane = lane_id();
+    const unsigned long long groups = (nq + 31ull) / 32ull;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * (kNnWarpThreads / 32);
+    for (unsigned long long g = (unsigned long long)blockIdx.x * (kNnWarpThreads / 32) + (unsigned long long)warp_id(); g < groups;
+         g += nwarps) {
+        unsigned long long q = g * 32ull + (unsigned long long)lane;
+        const bool real = q < nq;
+        if (!real) q = nq - 1ull;       // padding lanes repeat the last query
+        const double qx = queries[q * 2ull], qy = queries[q * 2ull + 1ull];
+        const int pos = target_nn_search2_warp(tv, qx, qy, ws);
+        if (real) out_idx[q] = (int32_t)tv.idx[pos];
+    }
+}
+constexpr uint32_t kNnWarpShared = (uint32_t)(sizeof(NnWarpScratch) * (kNnWarpThreads / 32));
+
+}  // namespace icp

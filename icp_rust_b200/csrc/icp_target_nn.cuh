@@ -286,6 +286,107 @@ ICP_DEV NnResult<2, uint32_t, uint32_t> target_nn_search2(const TargetView& tv, 
     return nn_exact_pass(tv, Q, qx, qy, thr);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative form of the same search, for COHERENT queries: the 32 lanes of a warp hold 32
+// queries that lie close together (consecutive beams of a scan hit the same walls a few
+// millimetres apart — the queries ICP issues).  The discs of the 32 queries overlap almost
+// entirely, so instead of 32 private walks (each lane fetching its own 8-byte candidates and 4-byte
+// cell-table entries: the L1/TEX unit saturates at ~40 sectors per query and the lanes idle on the
+// heavy tail of the candidate count) the warp walks the UNION of the discs once:
+//   rows      every lane forms its own chord of the row (nn_row_span, same bounds as above); two
+//             warp reductions give the union chord; its two cell-table entries are one broadcast
+//             load for the whole warp;
+//   candidates of the union chord are fetched 32 at a time with ONE coalesced 256-byte load,
+//             staged in shared memory (double buffered, one __syncwarp per chunk) and read back as
+//             broadcasts: every lane forms its binary32 d2 to every staged candidate with all 32
+//             lanes active, in the same arithmetic as the private walk (offsets from the centre of
+//             the candidate's 32x32-cell block).
+// A lane therefore sees a SUPERSET of its own candidates.  Nothing in the filter's proof needs the
+// candidates to lie inside the lane's disc — only the error bound of one binary32 coordinate
+// difference, which grows with the largest difference formed: `a` is taken for the whole frame
+// (W cells) instead of the lane's own radius.  The frame is limited to kNnWarpExtent cells; a warp
+// whose queries are spread wider (incoherent queries), or that holds a query outside the filter's
+// range, falls back to the private search for all its lanes.  Ties, near-ties and duplicates go to
+// the lane's own exact pass as before.  Results are bit-identical to target_nn_search2.
+constexpr int kNnWarpExtent = 96;
+
+struct NnWarpScratch {
+    float2 c[2][32];   // one chunk of candidates, double buffered
+};
+
+ICP_DEV int nn_warp_min(int v) { return __reduce_min_sync(ICP_FULL_MASK, v); }
+ICP_DEV int nn_warp_max(int v) { return __reduce_max_sync(ICP_FULL_MASK, v); }
+
+// Must be called by all 32 lanes of a converged warp (padding lanes repeat a real query).
+// Returns the sorted position of the exact nearest target point of (qx, qy).
+ICP_DEV int target_nn_search2_warp(const TargetView& tv, double qx, double qy, NnWarpScratch* ws)
+{
+    const NnQuery Q = nn_query_setup(tv, qx, qy);
+    const int lane = lane_id();
+    const int gx = tv.g.gx;
+    int xlo = 0, xhi = 0;
+    if (!Q.slow) {
+        const float Uc = sqrtf(Q.Uc2) * 1.000001f;
+        xlo = nn_floor_clamp(Q.txf - Uc - Q.sx, gx - 1);
+        xhi = nn_floor_clamp(Q.txf + Uc + Q.sx, gx - 1);
+    }
+    const bool any_slow = __any_sync(ICP_FULL_MASK, Q.slow);
+    const int Y0 = nn_warp_min(Q.ya), Y1 = nn_warp_max(Q.yb), X0 = nn_warp_min(xlo), X1 = nn_warp_max(xhi);
+    const int W = ((X1 - X0) > (Y1 - Y0) ? (X1 - X0) : (Y1 - Y0)) + 1;
+    if (any_slow || W > kNnWarpExtent) return target_nn_search2(tv, qx, qy).pos;   // incoherent warp: private walks
+    ICP_NN_COUNT(q, 1);
+    // the stored point (|.| <= 17), the query's block offset (|.| <= W + 17) and their difference
+    // (|.| <= W + 35) are each rounded to 24 bits: see NnQuery::a
+    const float a = ((float)W + 40.0f) * 2.4e-7f;
+    NnFilterState f;
+    f.m1 = 3.0e38f; f.m2 = 3.0e38f; f.pos = (int)Q.seed;
+    int buf = 0;
+    for (int yy = Y0; yy <= Y1; ++yy) {
+        int xa = 0x7fffffff, xb = -1;
+        if (yy >= Q.ya && yy <= Q.yb) {
+            int ca, cb;
+            if (nn_row_span(Q, yy, gx, &ca, &cb)) { xa = ca; xb = cb; }   // bound (columns), per lane
+        }
+        const int Xa = nn_warp_min(xa), Xb = nn_warp_max(xb);
+        if (Xa > Xb) continue;
+        ICP_NN_COUNT(rows, 1);
+        const int row = yy * gx;
+        const float qry = nn_block_offset(Q.ty, yy);
+        for (int xs = Xa; xs <= Xb;) {
+            const int xe_blk = xs | (kNnBlockCells - 1);
+            const int xe = xe_blk < Xb ? xe_blk : Xb;
+            const int p0 = (int)tv.cstart[row + xs], p1 = (int)tv.cstart[row + xe + 1];   // the same address in every lane
+            if (p1 > p0) {
+                ICP_NN_COUNT(spans, 1);
+                ICP_NN_COUNT(cand, p1 - p0);
+                const float qrx = nn_block_offset(Q.tx, xs);
+                for (int base = p0; base < p1; base += 32) {
+                    const int cnt = (p1 - base) < 32 ? (p1 - base) : 32;
+                    float2 v;
+                    v.x = 0.0f; v.y = 0.0f;
+                    if (lane < cnt) v = tv.pf[base + lane];     // one coalesced load per chunk
+                    ws->c[buf][lane] = v;
+                    __syncwarp();
+#pragma unroll 4
+                    for (int j = 0; j < cnt; ++j) {
+                        const float2 c = ws->c[buf][j];         // broadcast
+                        const float ex = qrx - c.x, ey = qry - c.y;
+                        const float d32 = nn_fma(ex, ex, ey * ey);
+                        f.m2 = fminf(f.m2, fmaxf(d32, f.m1));
+                        f.pos = (d32 < f.m1) ? base + j : f.pos;
+                        f.m1 = fminf(f.m1, d32);
+                    }
+                    buf ^= 1;
+                }
+            }
+            xs = xe + 1;
+        }
+    }
+    const float thr = nn_filter_band(f.m1, a);
+    if (f.m2 > thr && f.m1 < 3.0e38f) return f.pos;
+    return nn_exact_pass(tv, Q, qx, qy, thr).pos;
+}
+
 constexpr uint32_t kNnMaxPoints = 1u << 31;   // positions and original indices travel as int
 
 // ---------------------------------------------------------------------------------------------

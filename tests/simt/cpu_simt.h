@@ -240,6 +240,27 @@ static inline uint32_t __reduce_max_sync(unsigned, uint32_t v)
     for (int i = 0; i < 32; ++i) r = s[i] > r ? s[i] : r;
     return r;
 }
+static inline int __reduce_min_sync(unsigned, int v)
+{
+    const uint32_t* s = simt::warp_exchange((uint32_t)v);
+    int r = (int)s[0];
+    for (int i = 1; i < 32; ++i) r = (int)s[i] < r ? (int)s[i] : r;
+    return r;
+}
+static inline int __reduce_max_sync(unsigned, int v)
+{
+    const uint32_t* s = simt::warp_exchange((uint32_t)v);
+    int r = (int)s[0];
+    for (int i = 1; i < 32; ++i) r = (int)s[i] > r ? (int)s[i] : r;
+    return r;
+}
+static inline int __any_sync(unsigned, int pred)
+{
+    const uint32_t* s = simt::warp_exchange(pred ? 1u : 0u);
+    int r = 0;
+    for (int i = 0; i < 32; ++i) r |= (int)(s[i] & 1u);
+    return r;
+}
 // NOTE: partial warps (block size not a multiple of 32) are not supported by the collectives.
 
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }

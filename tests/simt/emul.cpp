@@ -15,10 +15,17 @@ using namespace icp;
 template <int THREADS, int PPT, int DIM>
 static void run_fused(FusedParams p, unsigned grid, int ordered)
 {
-    if (ordered == 2) {
+    if (ordered == 2 || ordered == 3) {   // lean schedule; 3: dedicated service warps (capacity (THREADS-64)*PPT)
+        if constexpr (THREADS >= 128) {
+            if (ordered == 3) {
+                const LeanLayout LL = lean_layout(DIM, (THREADS - 64) * PPT, p.mcap, p.cell_budget, false);
+                simt::launch(grid, THREADS, LL.total, [&] { icp_lean_kernel<THREADS, PPT, DIM, false, 1, true>(p); });
+                return;
+            }
+        }
         if constexpr (THREADS >= 64) {
             const LeanLayout LL = lean_layout(DIM, THREADS * PPT, p.mcap, p.cell_budget, false);
-            simt::launch(grid, THREADS, LL.total, [&] { icp_lean_kernel<THREADS, PPT, DIM, false, 1>(p); });
+            simt::launch(grid, THREADS, LL.total, [&] { icp_lean_kernel<THREADS, PPT, DIM, false, 1, false>(p); });
         }
         return;
     }
@@ -58,7 +65,7 @@ static void apply_guard(FusedParams& p, std::vector<uint32_t>& list, uint32_t* c
 }
 
 // Same argument meaning as icp_b200_batch.  variant: 0 -> 128 threads x 3 points, 1 -> 128 x 9,
-// 2 -> 64 x 2 (tiny), 3 -> 32 x 4 (single warp).
+// 2 -> 64 x 2 (tiny), 3 -> 32 x 4 (single warp), 4 -> 256 x 6.
 extern "C" int simt_icp_fused(int dim, int variant, unsigned grid, const double* src, const uint32_t* src_off,
                               const double* dst, const uint32_t* dst_off, const double* init_T, uint32_t B,
                               uint32_t max_iter, int corr_mode, int cell_budget, int ordered, double* out_T, uint32_t* out_inner,
@@ -76,7 +83,7 @@ extern "C" int simt_icp_fused(int dim, int variant, unsigned grid, const double*
     p.pair_begin = 0; p.pair_end = B; p.max_iter = max_iter; p.corr_mode = corr_mode;
     p.cell_budget = cell_budget; p.mcap = mcap; p.sm_count = 1;
     p.out_cost = g_out_cost; p.shared_src = (uint32_t)g_shared_src;
-    const FusedLayout L = fused_layout(dim, 128 * 9, mcap, cell_budget, false, true);
+    const FusedLayout L = fused_layout(dim, 256 * 6, mcap, cell_budget, false, true);
     std::vector<unsigned char> ws((size_t)grid * (L.nn_bytes + 64));
     p.workspace = ws.data();
     p.ws_stride = L.nn_bytes + 64 - ((L.nn_bytes + 64) % 16);
@@ -90,11 +97,13 @@ extern "C" int simt_icp_fused(int dim, int variant, unsigned grid, const double*
             if (variant == 0) { r.ncap = 384; run_fused<128, 3, 2>(r, grid, mode); }
             else if (variant == 1) { r.ncap = 1152; run_fused<128, 9, 2>(r, grid, mode); }
             else if (variant == 2) { r.ncap = 128; run_fused<64, 2, 2>(r, grid, mode); }
+            else if (variant == 4) { r.ncap = 1536; run_fused<256, 6, 2>(r, grid, mode); }
             else { r.ncap = 128; run_fused<32, 4, 2>(r, grid, mode); }
         } else {
             if (variant == 0) { r.ncap = 384; run_fused<128, 3, 3>(r, grid, mode); }
             else if (variant == 1) { r.ncap = 1152; run_fused<128, 9, 3>(r, grid, mode); }
             else if (variant == 2) { r.ncap = 128; run_fused<64, 2, 3>(r, grid, mode); }
+            else if (variant == 4) { r.ncap = 1536; run_fused<256, 6, 3>(r, grid, mode); }
             else { r.ncap = 128; run_fused<32, 4, 3>(r, grid, mode); }
         }
     };
@@ -191,7 +200,7 @@ extern "C" int simt_calc_stddevs(const double* residuals, const uint32_t* off, u
 
 // Shared-target structure (icp_target.cuh) built and searched on the emulator: the same kernels the
 // library launches in icp_b200_target_create / icp_b200_target_search.  fast != 0 selects the seeded
-// binary32-filtered search of icp_target_nn.cuh (2-D), else the ring search.
+// binary32-filtered search of icp_target_nn.cuh (2-D; fast == 2: its warp-cooperative kernel), else the ring search.
 extern "C" int simt_target_search(int dim, const double* pts, uint32_t m, long long budget, int fast,
                                   const double* queries, uint64_t nq, int32_t* out_idx)
 {
@@ -237,7 +246,8 @@ extern "C" int simt_target_search(int dim, const double* pts, uint32_t m, long l
         }
         tv.seed = bufs[cur]; tv.pf = pf.data();
     }
-    if (dim == 2) simt::launch(2, 256, 0, [&] { nn_search_kernel<2>(tv, queries, nq, out_idx); });
+    if (dim == 2 && fast == 2) simt::launch(2, kNnWarpThreads, kNnWarpShared, [&] { nn_search_warp_kernel(tv, queries, nq, out_idx); });
+    else if (dim == 2) simt::launch(2, 256, 0, [&] { nn_search_kernel<2>(tv, queries, nq, out_idx); });
     else simt::launch(2, 256, 0, [&] { nn_search_kernel<3>(tv, queries, nq, out_idx); });
     return 0;
 }

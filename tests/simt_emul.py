@@ -83,7 +83,7 @@ def icp_fused(srcs, dsts, init_T, max_iter=20, variant=0, grid=1, corr_mode=2, c
     err = lib().simt_icp_fused(
         C.c_int(dim), C.c_int(variant), C.c_uint(grid), src.ctypes.data_as(_dp), so.ctypes.data_as(_u32p),
         dst.ctypes.data_as(_dp), do.ctypes.data_as(_u32p), T0.ctypes.data_as(_dp), C.c_uint32(B),
-        C.c_uint32(max_iter), C.c_int(corr_mode), C.c_int(cell_budget), C.c_int(2 if ordered == 'lean' else (1 if ordered else 0)),
+        C.c_uint32(max_iter), C.c_int(corr_mode), C.c_int(cell_budget), C.c_int(3 if ordered == 'svc' else 2 if ordered == 'lean' else (1 if ordered else 0)),
         out_T.ctypes.data_as(_dp),
         inner.ctypes.data_as(_u32p), corr.ctypes.data_as(C.POINTER(C.c_int32)),
         hashes.ctypes.data_as(C.POINTER(C.c_uint64)), status.ctypes.data_as(C.POINTER(C.c_int32)))
@@ -125,7 +125,7 @@ def target_search(dst, queries, budget, fast=True):
     q = np.ascontiguousarray(queries, dtype=np.float64)
     out = np.full(q.shape[0], -1, dtype=np.int32)
     rc = lib().simt_target_search(C.c_int(d.shape[1]), d.ctypes.data_as(_dp), C.c_uint32(d.shape[0]),
-                                  C.c_longlong(int(budget)), C.c_int(1 if fast else 0), q.ctypes.data_as(_dp),
+                                  C.c_longlong(int(budget)), C.c_int(2 if fast == "warp" else 1 if fast else 0), q.ctypes.data_as(_dp),
                                   C.c_uint64(q.shape[0]), out.ctypes.data_as(C.POINTER(C.c_int32)))
     assert rc == 0
     return out

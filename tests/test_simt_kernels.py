@@ -222,8 +222,9 @@ def _map_queries(seed, count=6, beams=360):
     return np.concatenate(out)
 
 
+@pytest.mark.parametrize("fast", [True, "warp"])
 @pytest.mark.parametrize("cells_per_point", [2, 32, 200])
-def test_target_search_fast_path_is_exact(cells_per_point):
+def test_target_search_fast_path_is_exact(cells_per_point, fast):
     """Seeded, binary32-filtered disc search == brute force on a map sampled densely along walls:
     near-ties (neighbours on a wall), exact duplicates, queries on target points, far outside."""
     import icp_rust_b200 as icp
@@ -235,12 +236,16 @@ def test_target_search_fast_path_is_exact(cells_per_point):
                         rng.uniform(-5e3, 45e3, (300, 2)), rng.uniform(-1e7, 1e7, (16, 2)),
                         np.zeros((1, 2)), [[1e300, -1e300], [5e-324, 0.0]]])
     exp = oracle.nn_search(m, q, oracle.NN_BRUTE)
-    got = E.target_search(m, q, budget=len(m) * cells_per_point, fast=True)
+    got = E.target_search(m, q, budget=len(m) * cells_per_point, fast=fast)
     assert np.array_equal(got, exp)
     assert np.array_equal(E.target_search(m, q[:400], budget=len(m) * 2, fast=False), exp[:400])
+    if fast == "warp":      # a query count that is not a multiple of 32, and fewer than 32
+        for cut in (len(q) - 7, 5, 1):
+            assert np.array_equal(E.target_search(m, q[:cut], budget=len(m) * cells_per_point, fast="warp"), exp[:cut])
 
 
-def test_target_search_fast_path_odd_geometries():
+@pytest.mark.parametrize("fast", [True, "warp"])
+def test_target_search_fast_path_odd_geometries(fast):
     rng = np.random.default_rng(9)
     line = np.stack([np.linspace(-1.0, 1.0, 500), np.full(500, 3.25)], axis=1)       # flat in y
     lattice = np.stack(np.meshgrid(np.arange(40.), np.arange(40.)), -1).reshape(-1, 2)  # ties everywhere
@@ -254,7 +259,7 @@ def test_target_search_fast_path_odd_geometries():
             q = np.concatenate([q, lattice[:200] + 0.5, lattice[:100] + [0.5, 0.0]])   # 4-way and 2-way ties
         exp = oracle.nn_search(d, q, oracle.NN_BRUTE)
         for cpp in (4, 64):
-            assert np.array_equal(E.target_search(d, q, budget=max(64, len(d) * cpp), fast=True), exp)
+            assert np.array_equal(E.target_search(d, q, budget=max(64, len(d) * cpp), fast=fast), exp)
 
 
 @pytest.mark.parametrize("dim", [2, 3])
@@ -294,7 +299,8 @@ def test_seeded_disc_walk_is_exact_for_any_seed(dim):
         assert np.array_equal(got, exp), f"trial {trial} dim {dim} m {m} budget {budget}"
 
 
-def test_target_search_random_geometries():
+@pytest.mark.parametrize("fast", [True, "warp"])
+def test_target_search_random_geometries(fast):
     """Seeded disc + binary32 filter on shared 2-D targets across scales, offsets and cell sizes."""
     rng = np.random.default_rng(77)
     for trial in range(10):
@@ -309,7 +315,7 @@ def test_target_search_random_geometries():
                             d.mean(0) + rng.normal(0, 3 * scale, (80, 2))])
         exp = oracle.nn_search(d, q, oracle.NN_BRUTE)
         cpp = float(10.0 ** rng.uniform(0, 2))
-        assert np.array_equal(E.target_search(d, q, budget=max(64, int(m * cpp)), fast=True), exp), f"trial {trial}"
+        assert np.array_equal(E.target_search(d, q, budget=max(64, int(m * cpp)), fast=fast), exp), f"trial {trial}"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -438,5 +444,53 @@ def test_shared_source_batch():
             assert np.array_equal(g[k], g_rep[k]), k
         g = E.icp_fused(srcs * 3, dsts * 3, inits, 4, variant=0, grid=2, ordered="lean")
         _compare(g, refs, srcs * 3, 4, ordered=False)
+    finally:
+        E.set_options()
+
+
+def test_lean_dedicated_service_warps(scans2d):
+    """icp_lean.cuh with SVC: warps 0 and 1 own no points (they serve the medians while the workers
+    accumulate).  Same checks as the other schedules: real scans with index ties, the L shape,
+    degenerate pairs, crowded / odd sizes, the guard's re-run and the final cost; every schedule."""
+    srcs = [scans2d[1], scans2d[98]]
+    dsts = [scans2d[2], scans2d[99]]
+    T0 = [I6, I6]
+    refs = _oracle_ref(srcs, dsts, T0, 3)
+    outs = []
+    for schedule in (0, 1, 7):
+        E.set_schedule(schedule)
+        try:
+            g = E.icp_fused(srcs, dsts, T0, max_iter=3, variant=4, grid=2, ordered="svc")
+        finally:
+            E.set_schedule(0)
+        _compare(g, refs, srcs, 3, ordered=False)
+        outs.append(g["T"])
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    for dim in (2, 3):
+        src, dst, init, _ = _l_shape_case(dim)
+        g = E.icp_fused([src], [dst], [init], max_iter=20, variant=0, ordered="svc")
+        _compare(g, _oracle_ref([src], [dst], [init], 20), [src], 20, ordered=False)
+    rng = np.random.default_rng(3)
+    a = rng.normal(0, 100, (40, 2))
+    ds, dd = [a, a[:1], np.zeros((0, 2)), a, np.zeros((30, 2))], [a.copy(), a, a, a[:1], np.zeros((30, 2))]
+    g = E.icp_fused(ds, dd, [I6] * 5, max_iter=4, variant=0, grid=1, ordered="svc")
+    _compare(g, _oracle_ref(ds, dd, [I6] * 5, 4), ds, 4, ordered=False)
+    assert np.array_equal(g["T"][0], I6)
+    rng = np.random.default_rng(12)
+    cs, cd = [], []
+    for n, spread in ((1101, 0.5), (1100, 1e-7), (333, 30.0), (64, 3.0)):
+        d = rng.uniform(-1000, 1000, (n, 2))
+        s_ = d + rng.normal(0, spread, (n, 2)) + np.array([0.3, -0.2])
+        s_[: n // 3] = d[: n // 3] + np.array([0.25, 0.25])
+        cs.append(s_); cd.append(d)
+    g = E.icp_fused(cs, cd, [I6] * 4, max_iter=3, variant=4, grid=2, ordered="svc")
+    crefs = _oracle_ref(cs, cd, [I6] * 4, 3)
+    _compare(g, crefs, cs, 3, ordered=False)
+    try:
+        E.set_options(guard_scale=1e9, want_cost=4)
+        g = E.icp_fused(cs, cd, [I6] * 4, max_iter=3, variant=4, grid=2, ordered="svc")
+        assert E.last_redo_count() == 4
+        _compare(g, crefs, cs, 3, ordered=True)
+        assert np.array_equal(E.last_cost(), [r["cost"] for r in crefs])
     finally:
         E.set_options()
