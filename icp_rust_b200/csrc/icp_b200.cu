@@ -855,9 +855,9 @@ int icp_b200_target_search_device(icp_b200_target* t, const double* queries, uin
     const long long want = (long long)((nq + threads - 1) / threads);
     const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)ctx->sm_count * 8));
     ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], st));
-    // 2-D targets with seeds: the warp-cooperative kernel (coherent queries: consecutive queries share
-    // their candidates; incoherent warps fall back to private walks inside it).  ICP_B200_NN_WARP=0: private walks only.
-    if (t->dim == 2 && tv.pf != nullptr && env_int("ICP_B200_NN_WARP", 1) != 0) {
+    // ICP_B200_NN_WARP=1: the warp-cooperative union walk (measured slower on scan queries: 3.55 against 5.90 G
+    // queries/s — consecutive beams are ~60 mm apart at 10 m, their discs barely overlap; kept for A/B runs)
+    if (t->dim == 2 && tv.pf != nullptr && env_int("ICP_B200_NN_WARP", 0) != 0) {
         const long long wantw = (long long)((nq + kNnWarpThreads - 1) / kNnWarpThreads);
         const int gridw = (int)std::max<long long>(1, std::min<long long>(wantw, (long long)ctx->sm_count * 16));
         nn_search_warp_kernel<<<gridw, kNnWarpThreads, kNnWarpShared, st>>>(tv, queries, nq, out_index);
@@ -867,7 +867,7 @@ int icp_b200_target_search_device(icp_b200_target* t, const double* queries, uin
     ICP_CUDA(ctx, cudaGetLastError());
     ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][1], st));
     ctx->info.kernel_launches += 1;
-    if (!(t->dim == 2 && tv.pf != nullptr && env_int("ICP_B200_NN_WARP", 1) != 0)) ctx->info.grid_ctas = (uint32_t)grid;
+    if (!(t->dim == 2 && tv.pf != nullptr && env_int("ICP_B200_NN_WARP", 0) != 0)) ctx->info.grid_ctas = (uint32_t)grid;
     ctx->info.block_threads = threads; ctx->info.smem_bytes = 0;
     if (synchronize) {
         ICP_CUDA(ctx, cudaStreamSynchronize(st));

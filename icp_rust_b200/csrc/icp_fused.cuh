@@ -36,7 +36,7 @@
 namespace icp {
 
 constexpr int kChainUnroll = 8;  // rows arrays are zero-padded to a multiple of 2x this many points
-constexpr int kMaxWarps = 32;
+constexpr int kMaxWarps = 16;   // widest fused / lean instance: 512 threads
 
 enum PairStatus : int32_t {
     kPairOk = 0,
@@ -581,6 +581,7 @@ template <int THREADS, int PPT, int DIM, bool SHARED_TARGET, int MINB, bool ORDE
 ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
 {
     constexpr int NW = THREADS / 32;
+    static_assert(NW <= kMaxWarps, "FusedCtl holds per-warp slots for kMaxWarps warps");
     constexpr int NCAP = THREADS * PPT;
     static_assert(NCAP % (2 * kChainUnroll) == 0, "row arrays are padded to twice the chain unroll");
     ICP_SHARED_DYN(smem);

@@ -49,7 +49,7 @@ constexpr int kLeanHistBase = 3;
 constexpr int kLeanWin = 128;   // covers median +- 1 sigma: the MAD's bins (+-0.67 sigma) fall inside
 constexpr int kLeanCentre = kSelBins / 2 + 1;
 constexpr int kLeanWinLo = kLeanCentre - kLeanWin / 2;
-constexpr int kLeanCap = 24;
+constexpr int kLeanCap = 20;   // 10 KB of buckets: three CTAs of the 1152-point instance share an SM
 
 struct LeanSel {
     SelShared s;                 // histograms + lists of the general selection; list[] also ranks the short path
@@ -69,7 +69,7 @@ struct LeanLayout {
     FusedLayout f;               // target arrays, build temporaries, residual rows (gn_r)
     uint32_t bins;               // u32[ncap]: this stage's bin of (axis 0 | axis 1 << 16) per point
     uint32_t pos;                // u32[ncap]: sorted position of the point's match in the previous outer iteration
-    uint32_t dmatch;             // double2[ncap]: the matched target point of this outer iteration (xy)
+    uint32_t dmatch;             // shared targets only, double2[ncap]: the matched target point of this outer iteration (xy)
     uint32_t off_sel, off_ctl, total;
 };
 
@@ -79,8 +79,10 @@ ICP_HD LeanLayout lean_layout(int dim, int ncap, int mcap, int cell_budget, bool
     L.f = fused_layout(dim, ncap, mcap, cell_budget, shared_target, false);
     L.bins = align16(L.f.gn_r + 16u * (uint32_t)ncap);
     L.pos = align16(L.bins + 4u * (uint32_t)ncap);
+    // matched points: a per-pair target stays resident in shared memory, so the match is re-read through
+    // its sorted position (pos); a shared target lives in HBM, its matches are copied here
     L.dmatch = align16(L.pos + 4u * (uint32_t)ncap);
-    uint32_t u = align128(L.dmatch + 16u * (uint32_t)ncap);
+    uint32_t u = align128(L.dmatch + (shared_target ? 16u * (uint32_t)ncap : 0u));
     if (u < L.f.u_bytes) u = L.f.u_bytes;
     L.off_sel = u;
     L.off_ctl = align16(L.off_sel + (uint32_t)sizeof(LeanSel));
@@ -500,6 +502,7 @@ template <int THREADS, int PPT, int DIM, bool SHARED_TARGET, int MINB, bool SVC>
 ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
 {
     constexpr int NW = THREADS / 32;
+    static_assert(NW <= kMaxWarps, "FusedCtl holds per-warp slots for kMaxWarps warps");
     constexpr int WT0 = SVC ? 64 : 0;            // first worker thread
     constexpr int WTHREADS = THREADS - WT0;      // threads that own points
     constexpr int NCAP = WTHREADS * PPT;
@@ -520,6 +523,15 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
     const int tid = (int)threadIdx.x, lane = lane_id(), warp = warp_id();
     const bool worker = !SVC || warp >= 2;
     const int wtid = tid - WT0;                  // point i = wtid + k * WTHREADS belongs to worker wtid
+    // the target point matched to source point i in the current outer iteration (xy, get_xy lib.rs:86-89)
+    auto matched = [&](int i) -> double2 {
+        if (SHARED_TARGET) return d2v[i];
+        const uint32_t pos = prev_pos[i];
+        double2 d;
+        d.x = reinterpret_cast<const double*>(U + L.nn_x)[pos];
+        d.y = reinterpret_cast<const double*>(U + L.nn_y)[pos];
+        return d;
+    };
 
     lean_zero_lh<THREADS>(sel->lh[0]);
     lean_zero_lh<THREADS>(sel->lh[1]);
@@ -606,7 +618,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                     double2 q;
                     q.x = 0.; q.y = 0.;
                     if (i < n) transform_apply(T, src[(size_t)i * DIM + 0], src[(size_t)i * DIM + 1], &q.x, &q.y);
-                    else d2v[i] = q;   // slots beyond the scan: zero points, finite residuals, weight 0
+                    else if (SHARED_TARGET) d2v[i] = q;   // slots beyond the scan: weight 0 whatever they hold
+                    else prev_pos[i] = 0u;
                     r2v[i] = q;
                 }
             }
@@ -636,7 +649,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                     idx = r.idx;
                     prev_pos[i] = (uint32_t)r.pos;
                 }
-                d2v[i] = d;
+                if (SHARED_TARGET) d2v[i] = d;
                 hpart += mix64(((uint64_t)(uint32_t)i << 32) | (uint64_t)(uint32_t)idx);
                 if (p.out_corr) {
                     if (p.corr_mode == 2) p.out_corr[corr_base + (uint64_t)it * (uint64_t)n + (uint64_t)i] = idx;
@@ -655,7 +668,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
             // every thread; the rows below belong to the workers)
 #pragma unroll
             for (int k = 0; k < PPT; ++k) {
-                const double2 q = worker ? r2v[wtid + k * WTHREADS] : d2v[0];
+                const double2 q = r2v[worker ? wtid + k * WTHREADS : 0];
                 sx[k] = q.x; sy[k] = q.y;
             }   // (a worker reads and later overwrites only its own slots of r2v: no barrier needed here)
             ICP_LT_MARK(1)
@@ -680,7 +693,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                             const int i = wtid + k * WTHREADS;
                             double tx_, ty_;
                             transform_apply(Ti, sx[k], sy[k], &tx_, &ty_);
-                            const double2 d = d2v[i];
+                            const double2 d = matched(i);
                             double2 rr;
                             rr.x = tx_ - d.x;
                             rr.y = ty_ - d.y;
@@ -801,7 +814,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                         const int i = wtid + k * WTHREADS;
                         double tx_, ty_;
                         transform_apply(Ti, sx[k], sy[k], &tx_, &ty_);
-                        const double2 d = d2v[i];
+                        const double2 d = matched(i);
                         const double rx = tx_ - d.x, ry = ty_ - d.y;
                         const double rh = huber_rho(rx * rx + ry * ry);
                         e = e + (i < n ? rh : 0.);

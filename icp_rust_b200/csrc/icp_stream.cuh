@@ -174,10 +174,14 @@ ICP_DEV void cta_scan_cells(const uint32_t* cnt, uint32_t* cstart, uint32_t ncel
     __syncthreads();
 }
 
+#ifndef ICP_STREAM_MINB
+#define ICP_STREAM_MINB 1
+#endif
 template <int THREADS, int DIM, bool SHARED_TARGET>
-ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, 1) icp_stream_kernel(StreamParams sp)
+ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(StreamParams sp)
 {
     constexpr int NW = THREADS / 32;
+    static_assert(NW <= kMaxWarps, "FusedCtl holds per-warp slots for kMaxWarps warps");
     const FusedParams& p = sp.f;
     ICP_SHARED_DYN(smem);
     SelShared* sel = reinterpret_cast<SelShared*>(smem);

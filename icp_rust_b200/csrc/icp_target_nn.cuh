@@ -238,7 +238,22 @@ ICP_DEV void nn_walk(const TargetView& tv, const NnQuery& Q, Visit&& visit)
         }
         if (p1 == p0) break;
         ICP_NN_COUNT(cand, p1 - p0);
-        for (int p = p0; p < p1; ++p) {
+        // candidates in ascending position, two per 16-byte load where the position is even (pf is
+        // 16-byte aligned): a lane's fetches are the L1/TEX unit's work — one wavefront per load
+        int p = p0;
+        if ((p & 1) != 0) {
+            const float2 v = tv.pf[p];
+            const float ex = qrx - v.x, ey = qry - v.y;
+            visit(p, nn_fma(ex, ex, ey * ey));
+            ++p;
+        }
+        for (; p + 1 < p1; p += 2) {
+            const float4 w = *reinterpret_cast<const float4*>(tv.pf + p);
+            const float ex0 = qrx - w.x, ey0 = qry - w.y, ex1 = qrx - w.z, ey1 = qry - w.w;
+            visit(p, nn_fma(ex0, ex0, ey0 * ey0));
+            visit(p + 1, nn_fma(ex1, ex1, ey1 * ey1));
+        }
+        if (p < p1) {
             const float2 v = tv.pf[p];
             const float ex = qrx - v.x, ey = qry - v.y;
             visit(p, nn_fma(ex, ex, ey * ey));

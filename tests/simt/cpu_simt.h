@@ -20,6 +20,7 @@
 
 struct double2 { double x, y; };
 struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
 struct uint4 { uint32_t x, y, z, w; };
 static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }

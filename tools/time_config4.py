@@ -1,44 +1,32 @@
-"""Timing of the config-4 shape (3-D, 16,384-point clouds cut from the bundled frames) on the
-streaming kernel.  usage: time_config4.py [pairs]"""
-import os, sys, time
+"""Timing of BASELINE config 4 (icp_rust_b200/workloads.py: pairs (frame i, frame i+1 mod 20) of the
+bundled 3-D recording x 16,384 points, seeded initial perturbation, 20 iterations) on the streaming
+kernel.  usage: time_config4.py [pairs=296] [check=16]   (env ICP_B200_STREAM_CELLS_PER_POINT sweeps the grid)"""
+import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import icp_rust_b200 as icp
+from icp_rust_b200.workloads import config4_pairs
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 296
-z = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "scans3d.npz"))
-pts, off = z["points"], z["offsets"]
-fr = [pts[off[k]:off[k + 1]][:16384] for k in range(3)]
-rng = np.random.default_rng(4)
-srcs, dsts, T0 = [], [], []
-for b in range(B):
-    i, j = [(0, 1), (1, 2), (0, 2), (1, 0), (2, 1), (2, 0)][b % 6]
-    th = rng.uniform(-3, 3); c, s = np.cos(th), np.sin(th); t = rng.uniform(-1, 1, 2)
-    R = np.array([[c, -s], [s, c]])
-    mv = lambda p: np.column_stack([p[:, :2] @ R.T + t, p[:, 2]])
-    srcs.append(mv(fr[i])); dsts.append(mv(fr[j]))
-    e = rng.uniform(-0.01, 0.01); T0.append([np.cos(e), -np.sin(e), np.sin(e), np.cos(e), rng.uniform(-0.02, 0.02), rng.uniform(-0.02, 0.02)])
-src = np.concatenate(srcs); dst = np.concatenate(dsts)
-o = (np.arange(B + 1, dtype=np.uint64) * 16384).astype(np.uint32)
+check = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+src, dst, off, T0 = config4_pairs(B)
 ctx = icp.Context(0)
+best = None
 for rep in range(3):
     t = time.time()
-    g = ctx.estimate_batch(src, o, dst, o, np.array(T0), 20, dim=3)
+    g = ctx.estimate_batch(src, off, dst, off, T0, 20, dim=3)
     dt = time.time() - t
     info = ctx.call_info()
-    print(f"config4 shape: {B} pairs x 16384 pts: wall {dt*1e3:.1f} ms, kernel {info['kernel_ms']:.1f} ms -> {B/(info['kernel_ms']*1e-3):.0f} pairs/s (kernel), {B*16384*20/(info['kernel_ms']*1e-3)/1e9:.2f} G NN queries/s incl. solve; grid {info['grid_ctas']}x{info['block_threads']}")
-print("accepted per outer iteration:", (g["inner"] & 0xffff).mean(), "status ok:", (g["status"] == 0).all())
-
-# CPU oracle on the first pairs of the same batch (exact kd-tree, one pair per host thread): parity at
-# this size and a baseline for the shape
-import oracle
-nchk = min(B, os.cpu_count() or 1)
-oo = (np.arange(nchk + 1, dtype=np.uint64) * 16384).astype(np.uint32)
-t = time.time()
-o = oracle.icp_estimate_batch(3, src[:nchk * 16384], oo, dst[:nchk * 16384], oo, np.array(T0)[:nchk], 20,
-                              nn_mode=oracle.NN_KDTREE, nthreads=nchk)
-dt = time.time() - t
-print(f"oracle: {nchk} pairs on {nchk} host threads in {dt:.2f} s -> {nchk / dt:.1f} pairs/s; "
-      f"max |T_gpu - T_oracle| = {np.abs(o['T'] - g['T'][:nchk]).max():.3e}; "
-      f"inner counts equal: {bool(np.array_equal(o['inner'], g['inner'][:nchk]))}; "
-      f"correspondence hashes equal: {bool(np.array_equal(o['corr_hash'], g['corr_hash'][:nchk]))}")
+    best = info["kernel_ms"] if best is None else min(best, info["kernel_ms"])
+out = {"pairs": B, "cells_per_point": os.environ.get("ICP_B200_STREAM_CELLS_PER_POINT", "default"),
+       "kernel_ms": best, "pairs_per_s": B / (best * 1e-3), "nn_queries_per_s": B * 16384 * 20 / (best * 1e-3),
+       "grid": [info["grid_ctas"], info["block_threads"]], "accepted_per_outer_iteration": float((g["inner"] & 0xffff).mean()),
+       "status_ok": bool((g["status"] == 0).all()), "redo_pairs": int(g["redo_pairs"])}
+if check:
+    import oracle
+    n = min(B, check)
+    o = oracle.icp_estimate_batch(3, src[:n * 16384], off[:n + 1], dst[:n * 16384], off[:n + 1], T0[:n], 20, nn_mode=oracle.NN_KDTREE)
+    out["oracle_check"] = {"pairs": n, "inner_equal": bool(np.array_equal(o["inner"], g["inner"][:n])),
+                           "corr_hash_equal": bool(np.array_equal(o["corr_hash"], g["corr_hash"][:n])),
+                           "max_abs_transform_difference": float(np.abs(o["T"] - g["T"][:n]).max())}
+print(json.dumps(out))
