@@ -88,6 +88,7 @@ struct icp_b200_context {
     int force_instance = -1;
     int use_lean = 1;       // ICP_B200_LEAN=0: warp-tree batches on the icp_fused.cuh schedule instead of icp_lean.cuh
     int stream_cells_per_point = 8;   // ICP_B200_STREAM_CELLS_PER_POINT: cell budget of the streaming kernel's per-pair grids
+    int stream_nn_group = 0;    // ICP_B200_STREAM_NN_GROUP=1: a group of lanes per query in the streaming kernel's search
     int force_stream = 0;   // ICP_B200_FORCE_STREAM=1: route every warp-tree batch to the streaming kernel (tests)
 };
 
@@ -251,6 +252,7 @@ int launch_plan(icp_b200_context* ctx, const LaunchPlan& pl, const FusedParams& 
         sp.f = fp; sp.n_cap = pl.n_cap; sp.m_cap = pl.m_cap; sp.c_cap = pl.c_cap;
         sp.cells_per_point = (uint32_t)ctx->stream_cells_per_point;
         sp.ordered = pl.stream_ordered ? 1u : 0u;
+        sp.nn_group = (uint32_t)ctx->stream_nn_group;
         pl.skernel<<<grid, pl.threads, pl.smem, stream>>>(sp);
     } else {
         pl.kernel<<<grid, pl.threads, pl.smem, stream>>>(fp);
@@ -645,6 +647,7 @@ int icp_b200_create(int device, icp_b200_context** out)
     ctx->force_instance = env_int("ICP_B200_FORCE_INSTANCE", -1);
     ctx->stream_cells_per_point = std::max(1, std::min(256, env_int("ICP_B200_STREAM_CELLS_PER_POINT", 8)));
     ctx->force_stream = env_int("ICP_B200_FORCE_STREAM", 0);
+    ctx->stream_nn_group = env_int("ICP_B200_STREAM_NN_GROUP", 0);
     ctx->use_lean = env_int("ICP_B200_LEAN", 1);
     ctx->guard = env_int("ICP_B200_GUARD", 1);
     if (const char* gs = getenv("ICP_B200_GUARD_SCALE")) ctx->guard_scale = std::max(0.0, atof(gs));

@@ -65,6 +65,7 @@ struct FusedCtl {
     uint32_t knife;       // tree mode: a decision of this pair fell inside a guard band (GuardBands)
     double T6[6];         // lean schedule: the outer transform (kept out of the threads' registers)
     uint64_t H;           // lean schedule: running correspondence checksum
+    uint32_t heavy_n;     // streaming kernel: source points left to a whole warp's search
 };
 
 // Knife-edge guard of the warp-tree mode.  The tree-reduced sums differ from the reference's

@@ -16,10 +16,18 @@
 // accumulators from tile to tile.  That mode gives bit-identical transforms for scans of any size
 // (it is also the re-run path of large pairs the knife-edge guard flags).
 #pragma once
+#ifdef ICP_STREAM_TIMING
+#include <cstdio>
+#endif
 #include "icp_fused.cuh"
 
 namespace icp {
 
+#ifndef ICP_STREAM_NN_GROUP
+#define ICP_STREAM_NN_GROUP 8
+#endif
+constexpr int kStreamNnGroup = ICP_STREAM_NN_GROUP;   // lanes per query of the correspondence search
+constexpr int kStreamHeavyRows = 48;   // a ball covering more (slab, row) pairs than this is searched by a whole warp
 constexpr int kStreamTile = 256;   // points per shared-memory tile of the ordered chain
 
 struct StreamLayout {   // byte offsets inside one CTA's slab
@@ -27,6 +35,8 @@ struct StreamLayout {   // byte offsets inside one CTA's slab
     uint64_t spos;                         // u32[n_cap]: sorted position of each point's previous match
     uint64_t row_r, row_c, row_b, row_rho; // ordered mode: row terms, padded to whole tiles
     uint64_t gx, gy, gz, gidx, gslot;      // target copy sorted by cell
+    uint64_t grec;                         // the same as array-of-structs records (GridRec): the warp search's view
+    uint64_t heavy;                        // u32[n_cap]: source points whose search is left to a whole warp
     uint64_t gcnt, gcstart;
     uint64_t total;
 };
@@ -52,6 +62,8 @@ ICP_HD StreamLayout stream_layout(int dim, uint32_t n_cap, uint32_t m_cap, uint3
     L.gz = o; if (dim == 3) o = align256(o + 8ull * m_cap);
     L.gidx = o; o = align256(o + 4ull * m_cap);
     L.gslot = o; o = align256(o + 4ull * m_cap);
+    L.grec = o; o = align256(o + (uint64_t)sizeof(GridRec) * m_cap);
+    L.heavy = o; o = align256(o + 4ull * n_cap);
     L.gcnt = o; o = align256(o + 4ull * c_cap);
     L.gcstart = o; o = align256(o + 4ull * (c_cap + 1ull));
     L.total = o;
@@ -63,7 +75,17 @@ struct StreamParams {
     uint32_t n_cap, m_cap, c_cap;
     uint32_t cells_per_point;   // cell budget of a pair's own grid = cells_per_point * m, at most c_cap (0: 2)
     uint32_t ordered;           // reference-order sums (ICP_B200_FLAG_ORDERED_SUMS) instead of the warp tree
+    uint32_t nn_group;          // 1: kStreamNnGroup lanes per query (grid_nn_search_seeded_group); 0: one thread per query
 };
+
+// Phase clock of CTA 0 (debug builds, -DICP_STREAM_TIMING): thread 0 sums clock64() differences.
+#ifdef ICP_STREAM_TIMING
+#define ICP_ST_DECL long long st_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long st_t = clock64(), st_pairs = 0, st_evals = 0;
+#define ICP_ST_MARK(q) { const long long st_now = clock64(); st_acc[q] += st_now - st_t; st_t = st_now; }
+#else
+#define ICP_ST_DECL
+#define ICP_ST_MARK(q)
+#endif
 
 // Shared-memory tile of the ordered chain: the row arrays of kStreamTile points at the 16-byte bank
 // phases chain_run's 128-bit loads expect (icp_fused.cuh fused_layout: r +0, b +16, c alone).
@@ -174,8 +196,11 @@ ICP_DEV void cta_scan_cells(const uint32_t* cnt, uint32_t* cstart, uint32_t ncel
     __syncthreads();
 }
 
+// two CTAs per SM (64 registers per thread, some spills in the selection): the search is bound by the
+// latency of its dependent L2 loads, so the second CTA's 16 warps are worth more than the registers —
+// 3.88k against 2.98k pairs/s on config 4 (profiles/r02_config4.md)
 #ifndef ICP_STREAM_MINB
-#define ICP_STREAM_MINB 1
+#define ICP_STREAM_MINB 2
 #endif
 template <int THREADS, int DIM, bool SHARED_TARGET>
 ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(StreamParams sp)
@@ -203,12 +228,16 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
     for (int q = tid; q < 2 * kSelHistPad; q += THREADS) (&sel->hist[0][0])[q] = 0u;
     int hist_par = 0;
     __syncthreads();
+    ICP_ST_DECL
 
     for (;;) {
         if (tid == 0) { ctl->pair = fused_next_pair(p); ctl->knife = 0u; }
         __syncthreads();
         const uint32_t pair = ctl->pair;
         if (pair >= p.pair_end) break;
+#ifdef ICP_STREAM_TIMING
+        ++st_pairs;
+#endif
         const uint32_t spair = p.shared_src ? 0u : pair;   // ICP_B200_FLAG_SHARED_SOURCE: one scan for every pair
         const int n = (int)(p.src_off[spair + 1] - p.src_off[spair]);
         const double* src = p.src + (size_t)p.src_off[spair] * DIM;
@@ -253,6 +282,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
 
         // ---- IcpD::new: sorted cell list of this pair's target in the slab
         GridView<DIM, uint32_t, uint32_t> gv;
+        GridRec* grec = reinterpret_cast<GridRec*>(slab + L.grec);
         if (SHARED_TARGET) {
             gv.x = p.target.x; gv.y = p.target.y; gv.z = p.target.z;
             gv.idx = p.target.idx; gv.cstart = p.target.cstart; gv.g = p.target.g;
@@ -316,11 +346,17 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
                     gy[pos] = dst[(size_t)j * DIM + 1];
                     if (DIM == 3) gz[pos] = dst[(size_t)j * DIM + 2];
                     gidx[pos] = (uint32_t)j;
+                    GridRec rc;
+                    rc.x = dst[(size_t)j * DIM + 0]; rc.y = dst[(size_t)j * DIM + 1];
+                    rc.z = (DIM == 3) ? dst[(size_t)j * DIM + 2] : 0.0;
+                    rc.idx = (uint32_t)j; rc.pad = 0u;
+                    grec[pos] = rc;
                 }
                 __syncthreads();
             }
         }
 
+        ICP_ST_MARK(0)
         double est_med[2] = {0., 0.}, est_sigma[2] = {0., 0.};
         uint64_t H = 0;  // meaningful in thread 0
         const int npad = ((n + kStreamTile - 1) / kStreamTile) * kStreamTile;   // ordered mode: whole tiles
@@ -330,29 +366,124 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
         for (uint32_t it = 0; it < p.max_iter; ++it) {
             // ---- transform (lib.rs:113-116 / transform_xy lib.rs:52-57) + correspondence search
             uint64_t hpart = 0;
-            for (int i = tid; i < n; i += THREADS) {
-                double2 s;
-                transform_apply(T, src[(size_t)i * DIM + 0], src[(size_t)i * DIM + 1], &s.x, &s.y);
-                const double pz = (DIM == 3) ? src[(size_t)i * DIM + 2] : 0.0;
-                // from the second outer iteration on the previous match seeds the search (icp_target_nn.cuh)
-                const int seed = (it > 0) ? (int)spos[i] : -1;
-                const NnResult<DIM, uint32_t, uint32_t> r =
-                    SHARED_TARGET ? target_nn_search<DIM>(p.target, s.x, s.y, pz, seed)
-                                  : grid_nn_search_auto(gv, s.x, s.y, pz, seed);
-                spos[i] = (uint32_t)r.pos;
-                double2 d;
-                d.x = gv.x[r.pos]; d.y = gv.y[r.pos];   // get_xy (lib.rs:86-89)
-                S0[i] = s;
-                S1[i] = d;
-                hpart += mix64(((uint64_t)(uint32_t)i << 32) | (uint64_t)(uint32_t)r.idx);
-                if (p.out_corr) {
-                    if (p.corr_mode == 2) p.out_corr[corr_base + (uint64_t)it * (uint64_t)n + (uint64_t)i] = r.idx;
-                    else if (p.corr_mode == 1 && it + 1 == p.max_iter) p.out_corr[corr_base + (uint64_t)i] = r.idx;
+            ICP_ST_MARK(6)
+            if (SHARED_TARGET || !sp.nn_group) {
+                // one thread per point; a point whose seeded ball is large (far previous match: a source
+                // point without a counterpart) is put on a list and searched afterwards by a whole warp,
+                // rows spread over the lanes, instead of stalling the other 31 lanes of this warp
+                uint32_t* heavy = reinterpret_cast<uint32_t*>(slab + L.heavy);
+                if (tid == 0) ctl->heavy_n = 0u;
+                __syncthreads();
+                auto finish = [&](int i, double2 s, const NnResult<DIM, uint32_t, uint32_t>& r) {
+                    spos[i] = (uint32_t)r.pos;
+                    double2 d;
+                    if (SHARED_TARGET) { d.x = gv.x[r.pos]; d.y = gv.y[r.pos]; }   // get_xy (lib.rs:86-89)
+                    else { const GridRec m = grec[r.pos]; d.x = m.x; d.y = m.y; }
+                    S0[i] = s;
+                    S1[i] = d;
+                    hpart += mix64(((uint64_t)(uint32_t)i << 32) | (uint64_t)(uint32_t)r.idx);
+                    if (p.out_corr) {
+                        if (p.corr_mode == 2) p.out_corr[corr_base + (uint64_t)it * (uint64_t)n + (uint64_t)i] = r.idx;
+                        else if (p.corr_mode == 1 && it + 1 == p.max_iter) p.out_corr[corr_base + (uint64_t)i] = r.idx;
+                    }
+                };
+                // (visiting the points in the order of their own cell's occupancy, to even out the lanes of a
+                // warp, was measured and dropped: 2.69k against 2.98k pairs/s on config 4 — consecutive
+                // points share their candidates' cache lines, and that coherence is worth more)
+                for (int i = tid; i < n; i += THREADS) {
+                    double2 s;
+                    transform_apply(T, src[(size_t)i * DIM + 0], src[(size_t)i * DIM + 1], &s.x, &s.y);
+                    const double pz = (DIM == 3) ? src[(size_t)i * DIM + 2] : 0.0;
+                    // from the second outer iteration on the previous match seeds the search (icp_target_nn.cuh)
+                    const int seed = (it > 0) ? (int)spos[i] : -1;
+                    if (!SHARED_TARGET && seed >= 0 && grid_ball_rows(gv, grec, s.x, s.y, pz, seed) > kStreamHeavyRows) {
+                        S0[i] = s;
+                        heavy[atomicAdd(&ctl->heavy_n, 1u)] = (uint32_t)i;
+                        continue;
+                    }
+                    const NnResult<DIM, uint32_t, uint32_t> r =
+                        SHARED_TARGET ? target_nn_search<DIM>(p.target, s.x, s.y, pz, seed)
+                                      : grid_nn_search_auto(gv, s.x, s.y, pz, seed, grec);
+                    finish(i, s, r);
+                }
+                __syncthreads();
+                if (!SHARED_TARGET) {
+                    const uint32_t nh = ctl->heavy_n;
+                    for (uint32_t k = (uint32_t)warp; k < nh; k += NW) {
+                        const int i = (int)heavy[k];
+                        const double2 s = S0[i];
+                        const double pz = (DIM == 3) ? src[(size_t)i * DIM + 2] : 0.0;
+                        const int seed = (int)spos[i];
+                        __syncwarp();
+                        bool ok = true;
+                        NnResult<DIM, uint32_t, uint32_t> r = grid_nn_search_seeded_group<DIM, 32>(gv, grec, s.x, s.y, pz, seed, true, &ok);
+                        if (lane == 0) {
+                            if (!ok) r = grid_nn_search(gv, s.x, s.y, pz);
+                            finish(i, s, r);
+                        }
+                        __syncwarp();
+                    }
+                }
+            } else {
+                // pass 1, one thread per point: the transformed point and the seed of its search — the
+                // previous match, in the first iteration the first point of the query's own cell
+                for (int i = tid; i < n; i += THREADS) {
+                    double2 s;
+                    transform_apply(T, src[(size_t)i * DIM + 0], src[(size_t)i * DIM + 1], &s.x, &s.y);
+                    S0[i] = s;
+                    if (it == 0) {
+                        const GridGeom& g = gv.g;
+                        const int cx = grid_coord(s.x, g.ox, g.inv_h, g.gx);
+                        const int cy = grid_coord(s.y, g.oy, g.inv_h, g.gy);
+                        const int cz = (DIM == 3) ? grid_coord(src[(size_t)i * DIM + 2], g.oz, g.inv_h, g.gz) : 0;
+                        const int c = (cz * g.gy + cy) * g.gx + cx;
+                        const uint32_t c0 = gv.cstart[c], c1 = gv.cstart[c + 1];
+                        spos[i] = c1 > c0 ? c0 : 0xffffffffu;
+                    }
+                }
+                __syncthreads();
+                ICP_ST_MARK(1)
+                // pass 2, kNnGroup lanes per point (32 / kNnGroup points per warp at a time): exact ball
+                // walk around the seed (grid_nn_search_seeded_group); a point without a seed (empty own
+                // cell, first iteration) or outside the walk's range takes the ring search
+                constexpr int G = kStreamNnGroup, QPW = 32 / G;
+                const int gq = lane / G;
+                for (int i0 = warp * QPW; i0 < n; i0 += NW * QPW) {
+                    const int i = i0 + gq;
+                    const bool have = i < n;
+                    double2 s;
+                    s.x = 0.; s.y = 0.;
+                    double pz = 0.0;
+                    uint32_t seed = 0xffffffffu;
+                    if (have) {
+                        s = S0[i];
+                        pz = (DIM == 3) ? src[(size_t)i * DIM + 2] : 0.0;   // transform_xy keeps z (lib.rs:52-57)
+                        seed = spos[i];
+                    }
+                    __syncwarp();   // every lane has read its seed before a group leader replaces it
+                    bool ok = true;
+                    NnResult<DIM, uint32_t, uint32_t> r =
+                        grid_nn_search_seeded_group<DIM, G>(gv, grec, s.x, s.y, pz, (int)seed, have && seed != 0xffffffffu, &ok);
+                    if (have && (lane % G) == 0) {
+                        if (seed == 0xffffffffu || !ok) r = grid_nn_search(gv, s.x, s.y, pz);
+                        spos[i] = (uint32_t)r.pos;
+                        const GridRec m = grec[r.pos];
+                        double2 d;
+                        d.x = m.x; d.y = m.y;   // get_xy (lib.rs:86-89)
+                        S1[i] = d;
+                        hpart += mix64(((uint64_t)(uint32_t)i << 32) | (uint64_t)(uint32_t)r.idx);
+                        if (p.out_corr) {
+                            if (p.corr_mode == 2) p.out_corr[corr_base + (uint64_t)it * (uint64_t)n + (uint64_t)i] = r.idx;
+                            else if (p.corr_mode == 1 && it + 1 == p.max_iter) p.out_corr[corr_base + (uint64_t)i] = r.idx;
+                        }
+                    }
+                    __syncwarp();
                 }
             }
             hpart = warp_sum_u64(hpart);
             if (lane == 0) ctl->hash_part[warp] = hpart;
             __syncthreads();   // state of every point is visible to the whole CTA
+            ICP_ST_MARK(2)
             if (tid == 0) {
                 uint64_t h = 0;
                 for (int w = 0; w < NW; ++w) h += ctl->hash_part[w];
@@ -371,6 +502,10 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
                     ks.s0 = S0; ks.s1 = S1; ks.Ti = Ti;
                     double sigma[2];
                     hist_par = cta_calc_stddevs<THREADS, 0>(sel, ks, n, est_med, est_sigma, hist_par, sigma);
+                    ICP_ST_MARK(3)
+#ifdef ICP_STREAM_TIMING
+                    ++st_evals;
+#endif
                     const double g0 = 1. / sigma[0], g1 = 1. / sigma[1];
                     if (ordered) {
                         // row weights (lib.rs:245-250), Jacobian third column (lib.rs:176-184), Huber cost
@@ -426,6 +561,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
                         tree_accumulate_point(acc, Ti, s.x, s.y, ks.get(0, i), sigma, g0, g1);
                     }
                     cta_tree_reduce_solve<NW>(ctl, acc, Ti, prev_error, p.guard);
+                    ICP_ST_MARK(4)
                     const uint32_t decision = (uint32_t)ctl->bcast[7];
                     if (decision != kBreakCap) { why = decision; break; }
                     prev_error = ctl->bcast[6];
@@ -477,6 +613,12 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
         }
         __syncthreads();
     }
+#ifdef ICP_STREAM_TIMING
+    if (blockIdx.x == 0 && tid == 0 && st_pairs > 0)
+        printf("stream timing CTA0: pairs %lld evals %lld | cycles/pair: setup+build %lld seeds %lld search %lld selection %lld accumulate+solve %lld other %lld\n",
+               st_pairs, st_evals, st_acc[0] / st_pairs, st_acc[1] / st_pairs, st_acc[2] / st_pairs, st_acc[3] / st_pairs,
+               st_acc[4] / st_pairs, st_acc[6] / st_pairs);
+#endif
 }
 
 }  // namespace icp

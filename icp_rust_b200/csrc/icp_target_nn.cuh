@@ -415,13 +415,64 @@ constexpr uint32_t kNnMaxPoints = 1u << 31;   // positions and original indices 
 // bound (3-D): a skipped point lies in a slab outside [za, zb] (|dz|/h > Uc), or in a row of slab zz
 // outside [ya, yb] (dy^2 + dz^2 > h^2 (ry^2 + zdc^2) >= h^2 Uc2), or in a column outside [xa, xb]
 // (dx^2 + dy^2 + dz^2 > h^2 (wc^2 + ydc^2 + zdc^2) >= h^2 Uc2): its computed d2 exceeds the seed's.
+// Array-of-structs copy of a sorted target (large per-pair grids in the L2 slab, icp_stream.cuh):
+// one candidate = one 32-byte sector instead of three or four scattered 8-byte loads.
+struct GridRec {
+    double x, y, z;
+    uint32_t idx, pad;
+};
+constexpr int kNnGroupDepth = 4;   // records per lane and step of the group search
+
+ICP_DEV bool nn_better(double d2, int idx, double bd2, int bidx) { return d2 < bd2 || (d2 == bd2 && idx < bidx); }
+
+// Candidates [p0, p1) against `best`, in ascending position, on records: four at a time with their
+// eight 16-byte loads issued before any of them is used — the records sit in L2 (~250 cycles away)
+// and a CTA of the streaming kernel has only 16 warps to hide that with.
+template <int DIM, typename IdxT, typename CellT>
+ICP_DEV void nn_scan_records(const GridRec* rec, int p0, int p1, double qx, double qy, double qz,
+                             NnResult<DIM, IdxT, CellT>& best)
+{
+    auto one = [&](const GridRec& c, int p) {
+        const double dx = qx - c.x, dy = qy - c.y;
+        double d2 = dx * dx + dy * dy;
+        if (DIM == 3) {
+            const double dz = qz - c.z;
+            d2 = d2 + dz * dz;
+        }
+        if (d2 <= best.d2) {
+            const int id = (int)c.idx;
+            if (d2 < best.d2 || id < best.idx) { best.d2 = d2; best.idx = id; best.pos = p; }
+        }
+    };
+    int p = p0;
+    for (; p + 4 <= p1; p += 4) {
+        const GridRec c0 = rec[p], c1 = rec[p + 1], c2 = rec[p + 2], c3 = rec[p + 3];
+        one(c0, p); one(c1, p + 1); one(c2, p + 2); one(c3, p + 3);
+    }
+    for (; p < p1; ++p) {
+        const GridRec c = rec[p];
+        one(c, p);
+    }
+}
+
+// rec != nullptr: candidates are read from the array-of-structs copy (nn_scan_records)
 template <int DIM, typename IdxT, typename CellT>
 ICP_DEV NnResult<DIM, IdxT, CellT> grid_nn_search_seeded(const GridView<DIM, IdxT, CellT>& gv, double qx, double qy,
-                                                         double qz, int seed_pos)
+                                                         double qz, int seed_pos, const GridRec* rec = nullptr)
 {
     const GridGeom& g = gv.g;
     NnResult<DIM, IdxT, CellT> best;
-    {
+    if (rec) {
+        const GridRec s = rec[seed_pos];
+        const double dx = qx - s.x, dy = qy - s.y;
+        best.d2 = dx * dx + dy * dy;
+        if (DIM == 3) {
+            const double dz = qz - s.z;
+            best.d2 = best.d2 + dz * dz;
+        }
+        best.pos = seed_pos;
+        best.idx = (int)s.idx;
+    } else {
         const double dx = qx - gv.x[seed_pos], dy = qy - gv.y[seed_pos];
         best.d2 = dx * dx + dy * dy;
         if (DIM == 3) {
@@ -449,7 +500,8 @@ ICP_DEV NnResult<DIM, IdxT, CellT> grid_nn_search_seeded(const GridView<DIM, Idx
         for (int y2 = ya; y2 <= yb2; ++y2) {
             int xa, xb;
             if (!nn_row_span(Q, y2, g.gx, &xa, &xb)) continue;          // bound (columns)
-            grid_scan_cells(gv, y2 * g.gx, xa, xb, qx, qy, qz, best);
+            if (rec) nn_scan_records(rec, (int)gv.cstart[y2 * g.gx + xa], (int)gv.cstart[y2 * g.gx + xb + 1], qx, qy, qz, best);
+            else grid_scan_cells(gv, y2 * g.gx, xa, xb, qx, qy, qz, best);
         }
         return best;
     }
@@ -491,6 +543,10 @@ ICP_DEV NnResult<DIM, IdxT, CellT> grid_nn_search_seeded(const GridView<DIM, Idx
             ++yy;
         }
         if (p1 == p0) break;
+        if (rec) {
+            nn_scan_records(rec, p0, p1, qx, qy, qz, best);
+            continue;
+        }
         for (int p = p0; p < p1; ++p) {
             const double dx = qx - gv.x[p], dy = qy - gv.y[p];
             double d2 = dx * dx + dy * dy;
@@ -507,11 +563,177 @@ ICP_DEV NnResult<DIM, IdxT, CellT> grid_nn_search_seeded(const GridView<DIM, Idx
     return best;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same seeded ball walk by a GROUP OF LANES for one query (large per-pair grids, icp_stream.cuh):
+// 3-D LiDAR clouds put 50-150 points into a cell near the sensor, so a query meets a few LONG
+// contiguous runs of candidates.  One thread per query walks them at ~7 of 32 lanes with three
+// scattered 8-byte loads per candidate; here the G lanes of a group
+//   - each take one (slab, row) of the ball's cover and form its span with the bounds above,
+//   - then scan every non-empty span together, G consecutive 32-byte records per step (one
+//     coalesced access), each lane keeping its own best on the exact binary64 d2,
+//   - and finish with a shuffle arg-min on (d2, original index): the minimum of a totally ordered
+//     set does not depend on the order it is reduced in, so the result is the per-thread walk's.
+// (One query per whole warp was measured first: 1.57k pairs/s on config 4 against 2.76k for one
+// thread per query — a warp then has a single dependent chain of L2 round trips in flight.)
+// Records: the target sorted by cell as array-of-structs {x, y, z, idx} (GridRec), written by the
+// grid build next to the SoA arrays.  All lanes pass the same arguments and return the same result.
+// G lanes (a power of two, 4..32) work on one query; a warp holds 32 / G queries at a time and stays
+// converged: every step each group scans G consecutive records of its current span, groups that have
+// run out of candidates idle until the slowest one is done.  Call with all 32 lanes; the lanes of a
+// group pass the same query; `active` false for a group without a query (it only takes part in the
+// shuffles).  `ok` false on return (group-uniform) when the query is outside the walk's range: the
+// caller then runs grid_nn_search for it.
+template <int DIM, int G, typename IdxT, typename CellT>
+ICP_DEV NnResult<DIM, IdxT, CellT> grid_nn_search_seeded_group(const GridView<DIM, IdxT, CellT>& gv, const GridRec* rec,
+                                                               double qx, double qy, double qz, int seed_pos, bool active,
+                                                               bool* ok)
+{
+    const GridGeom& g = gv.g;
+    const int lane = lane_id();
+    const int gl = lane & (G - 1);          // lane within the group
+    const int gbase = lane & ~(G - 1);      // first lane of the group
+    NnResult<DIM, IdxT, CellT> best;
+    best.d2 = 1.0 / 0.0; best.idx = 0x7fffffff; best.pos = -1;
+    NnQuery Q;
+    Q.tx = 0.; Q.ty = 0.; Q.txf = 0.f; Q.tyf = 0.f; Q.sx = 0.f; Q.sy = 0.f; Q.Uc2 = 0.f;
+    float tzf = 0.f, Uc2 = 0.f, sz = 0.f;
+    int za = 0, zb = -1, ya = 0, ny = 1;
+    bool good = false;
+    if (active) {
+        const GridRec s = rec[seed_pos];
+        const double dx = qx - s.x, dy = qy - s.y;
+        best.d2 = dx * dx + dy * dy;
+        if (DIM == 3) {
+            const double dz = qz - s.z;
+            best.d2 = best.d2 + dz * dz;
+        }
+        best.pos = seed_pos;
+        best.idx = (int)s.idx;
+        Q.tx = nn_cell_coord(qx, g.ox, g.inv_h);
+        Q.ty = nn_cell_coord(qy, g.oy, g.inv_h);
+        Q.txf = (float)Q.tx; Q.tyf = (float)Q.ty;
+        tzf = (DIM == 3) ? (float)nn_cell_coord(qz, g.oz, g.inv_h) : 0.0f;
+        const float ihf = (float)g.inv_h;
+        Uc2 = ((float)best.d2 * ihf) * ihf * 1.000001f + 1e-30f;      // as in nn_query_setup
+        good = (fabsf(Q.txf) + fabsf(Q.tyf) + fabsf(tzf) <= 1e9f) && (Uc2 <= 1e12f) && (best.d2 >= 0.0);
+        if (good) {
+            const float Uc = sqrtf(Uc2) * 1.000001f;
+            Q.sx = (fabsf(Q.txf) + 1.0f) * 3.6e-7f;
+            Q.sy = (fabsf(Q.tyf) + 1.0f) * 3.6e-7f;
+            sz = (DIM == 3) ? (fabsf(tzf) + 1.0f) * 3.6e-7f : 0.0f;
+            za = 0; zb = 0;
+            if (DIM == 3) {
+                za = nn_floor_clamp(tzf - Uc - sz, g.gz - 1);                   // bound (slabs)
+                zb = nn_floor_clamp(tzf + Uc + sz, g.gz - 1);
+            }
+            // rows of the widest slab: a superset of every slab's rows (each lane re-derives its slab's bound)
+            ya = nn_floor_clamp(Q.tyf - Uc - Q.sy, g.gy - 1);                   // bound (rows)
+            const int yb = nn_floor_clamp(Q.tyf + Uc + Q.sy, g.gy - 1);
+            ny = yb - ya + 1;
+        }
+    }
+    *ok = good || !active;
+    const int nrows = good ? (zb - za + 1) * ny : 0;
+    const int max_rows = __reduce_max_sync(ICP_FULL_MASK, nrows);
+    for (int r0 = 0; r0 < max_rows; r0 += G) {
+        // ---- lane gl of the group: span of row r0 + gl
+        int p0 = 0, p1 = 0;
+        const int r = r0 + gl;
+        if (r < nrows) {
+            const int zz = za + r / ny, yy = ya + r % ny;
+            float rem2 = Uc2;
+            bool live = true;
+            if (DIM == 3) {
+                const float zf = (float)zz;
+                const float zdc = fmaxf(fmaxf(zf - tzf, tzf - (zf + 1.0f)) - sz, 0.0f) * 0.999999f;
+                rem2 = Uc2 - zdc * zdc;
+                live = !(rem2 < 0.0f);
+            }
+            if (live) {
+                Q.Uc2 = rem2;    // nn_row_span tests wc^2 + ydc^2 against Uc2 - zdc^2 (bound (3-D))
+                int xa, xb;
+                if (nn_row_span(Q, yy, g.gx, &xa, &xb)) {                // bound (columns)
+                    const int base = (zz * g.gy + yy) * g.gx;
+                    p0 = (int)gv.cstart[base + xa];
+                    p1 = (int)gv.cstart[base + xb + 1];
+                }
+            }
+        }
+        // ---- the group's non-empty spans, G records per step
+        uint32_t todo = (__ballot_sync(ICP_FULL_MASK, p1 > p0) >> gbase) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+        int off = 0;
+        while (__any_sync(ICP_FULL_MASK, todo != 0u)) {
+            const int src = todo ? gbase + __ffs((int)todo) - 1 : lane;
+            const int s0 = __shfl_sync(ICP_FULL_MASK, p0, src), s1 = __shfl_sync(ICP_FULL_MASK, p1, src);
+            if (todo) {
+                // kNnGroupDepth records per lane and step, all loads issued before the first use: the
+                // records sit in L2 and the step is otherwise one dependent round trip
+                const int pb = s0 + off + gl;
+                GridRec c[kNnGroupDepth];
+#pragma unroll
+                for (int k = 0; k < kNnGroupDepth; ++k) {
+                    const int p = pb + k * G;
+                    c[k] = rec[p < s1 ? p : s0];      // a clamped (harmless) load keeps the batch branch-free
+                }
+#pragma unroll
+                for (int k = 0; k < kNnGroupDepth; ++k) {
+                    const int p = pb + k * G;
+                    const double dx = qx - c[k].x, dy = qy - c[k].y;
+                    double d2 = dx * dx + dy * dy;
+                    if (DIM == 3) {
+                        const double dz = qz - c[k].z;
+                        d2 = d2 + dz * dz;
+                    }
+                    if (p < s1 && nn_better(d2, (int)c[k].idx, best.d2, best.idx)) { best.d2 = d2; best.idx = (int)c[k].idx; best.pos = p; }
+                }
+                off += kNnGroupDepth * G;
+                if (s0 + off >= s1) { todo &= todo - 1u; off = 0; }
+            }
+        }
+    }
+    // ---- arg-min over the group's lanes on (d2, original index)
+#pragma unroll
+    for (int m = G / 2; m > 0; m >>= 1) {
+        const double od2 = shfl_xor_f64(best.d2, m);
+        const int oidx = (int)__shfl_xor_sync(ICP_FULL_MASK, (uint32_t)best.idx, m);
+        const int opos = (int)__shfl_xor_sync(ICP_FULL_MASK, (uint32_t)best.pos, m);
+        if (nn_better(od2, oidx, best.d2, best.idx)) { best.d2 = od2; best.idx = oidx; best.pos = opos; }
+    }
+    return best;
+}
+
+// Number of (slab, row) pairs the seeded ball walk of a query would visit — the cost measure the
+// streaming kernel uses to hand queries with a far seed (a source point without a counterpart: its
+// previous match is decimetres away and the ball covers hundreds of mostly empty rows) to a whole
+// warp instead of stalling the 31 other lanes of their own warp.  0: outside the walk's range.
+template <int DIM, typename IdxT, typename CellT>
+ICP_DEV int grid_ball_rows(const GridView<DIM, IdxT, CellT>& gv, const GridRec* rec, double qx, double qy, double qz,
+                           int seed_pos)
+{
+    const GridGeom& g = gv.g;
+    const GridRec s = rec[seed_pos];
+    const double dx = qx - s.x, dy = qy - s.y;
+    double d2 = dx * dx + dy * dy;
+    if (DIM == 3) {
+        const double dz = qz - s.z;
+        d2 = d2 + dz * dz;
+    }
+    const float txf = (float)nn_cell_coord(qx, g.ox, g.inv_h), tyf = (float)nn_cell_coord(qy, g.oy, g.inv_h);
+    const float tzf = (DIM == 3) ? (float)nn_cell_coord(qz, g.oz, g.inv_h) : 0.0f;
+    const float ihf = (float)g.inv_h;
+    const float Uc2 = ((float)d2 * ihf) * ihf * 1.000001f + 1e-30f;
+    if (!(fabsf(txf) + fabsf(tyf) + fabsf(tzf) <= 1e9f) || !(Uc2 <= 1e12f) || !(d2 >= 0.0)) return 0;
+    const float Uc = sqrtf(Uc2) * 1.000001f;
+    const int ny = nn_floor_clamp(tyf + Uc + 1.0f, g.gy - 1) - nn_floor_clamp(tyf - Uc - 1.0f, g.gy - 1) + 1;
+    const int nz = (DIM == 3) ? nn_floor_clamp(tzf + Uc + 1.0f, g.gz - 1) - nn_floor_clamp(tzf - Uc - 1.0f, g.gz - 1) + 1 : 1;
+    return ny * nz;
+}
+
 // Search of a per-pair grid with whatever seed is at hand: the previous match (seed_pos >= 0), else
 // the first point of the query's own cell, else (empty cell) the ring search.
 template <int DIM, typename IdxT, typename CellT>
 ICP_DEV NnResult<DIM, IdxT, CellT> grid_nn_search_auto(const GridView<DIM, IdxT, CellT>& gv, double qx, double qy,
-                                                       double qz, int seed_pos)
+                                                       double qz, int seed_pos, const GridRec* rec = nullptr)
 {
     if (seed_pos < 0) {
         const GridGeom& g = gv.g;
@@ -520,9 +742,9 @@ ICP_DEV NnResult<DIM, IdxT, CellT> grid_nn_search_auto(const GridView<DIM, IdxT,
         const int cz = (DIM == 3) ? grid_coord(qz, g.oz, g.inv_h, g.gz) : 0;
         const int c = (cz * g.gy + cy) * g.gx + cx;
         const int p0 = (int)gv.cstart[c], p1 = (int)gv.cstart[c + 1];
-        if (p1 > p0) seed_pos = p0;
+        if (p1 > p0) seed_pos = p0;   // (the BEST point of the own cell as seed was measured: 2.80k against 2.98k pairs/s)
     }
-    return seed_pos >= 0 ? grid_nn_search_seeded(gv, qx, qy, qz, seed_pos) : grid_nn_search(gv, qx, qy, qz);
+    return seed_pos >= 0 ? grid_nn_search_seeded(gv, qx, qy, qz, seed_pos, rec) : grid_nn_search(gv, qx, qy, qz);
 }
 
 // seed_pos >= 0: a sorted position of the target (the previous outer iteration's match); -1: none

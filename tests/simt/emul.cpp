@@ -47,7 +47,8 @@ extern "C" int simt_set_schedule(int mode)
 // streaming kernel; shared_src: ICP_B200_FLAG_SHARED_SOURCE.
 static double g_guard_scale = 0.0, g_band_delta_scale = 1.0;
 static double* g_out_cost = nullptr;
-static int g_stream_ordered = 0, g_shared_src = 0;
+static int g_stream_ordered = 0, g_shared_src = 0, g_stream_nn_group = 0;
+extern "C" void simt_set_stream_nn_group(int v) { g_stream_nn_group = v; }
 static uint32_t g_last_redo = 0;
 extern "C" void simt_set_options(double guard_scale, double* out_cost, int stream_ordered, int shared_src,
                                  double delta_band_scale)
@@ -169,6 +170,7 @@ extern "C" int simt_icp_stream(int dim, int threads, unsigned grid, const double
         }
     };
     sp.ordered = (uint32_t)g_stream_ordered;
+    sp.nn_group = (uint32_t)g_stream_nn_group;
     run(sp);
     g_last_redo = 0;
     if (guard) {

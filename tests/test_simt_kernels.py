@@ -171,9 +171,11 @@ def test_stream_l_shape(dim, threads):  # lib.rs:510-595 through icp_stream.cuh
     _compare(g, _oracle_ref([src], [dst], [init], 20), [src], 20, ordered=False)
 
 
+@pytest.mark.parametrize("nn_group", [False, True])
 @pytest.mark.parametrize("schedule", [0, 7])
-def test_stream_real_scans_and_degenerates(scans2d, schedule):
+def test_stream_real_scans_and_degenerates(scans2d, schedule, nn_group):
     E.set_schedule(schedule)
+    E.set_stream_nn_group(nn_group)
     try:
         rng = np.random.default_rng(3)
         a = rng.normal(0, 100, (40, 2))
@@ -185,8 +187,27 @@ def test_stream_real_scans_and_degenerates(scans2d, schedule):
         # same bits as the fused kernel's warp-tree mode?  Not required (different summation
         # tree); but statuses and counts are.
         assert (g["status"] == 0).all()
+        if nn_group:   # 3-D clouds through the group search as well
+            srcs3, dsts3 = _noisy_pairs(2, 400, 17, dim=3)
+            g = E.icp_stream(srcs3, dsts3, [I6] * 2, max_iter=3, threads=64, grid=1)
+            _compare(g, _oracle_ref(srcs3, dsts3, [I6] * 2, 3), srcs3, 3, ordered=False)
     finally:
         E.set_schedule(0)
+        E.set_stream_nn_group(False)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_stream_far_points_take_the_warp_search(dim):
+    """Source points without a counterpart (their match is far: the seeded ball covers many rows) are
+    searched by a whole warp after the per-thread pass; same indices, counts and transforms."""
+    srcs, dsts = _noisy_pairs(2, 500, 41, dim=dim)
+    rng = np.random.default_rng(9)
+    for s_ in srcs:
+        far = rng.choice(len(s_), 12, replace=False)
+        s_[far, :2] += rng.uniform(120, 260, (12, 2)) * rng.choice([-1, 1], (12, 2))
+    T0 = [I6] * 2
+    g = E.icp_stream(srcs, dsts, T0, max_iter=4, threads=64, grid=2)
+    _compare(g, _oracle_ref(srcs, dsts, T0, 4), srcs, 4, ordered=False)
 
 
 def test_stream_crowded_bins_zoom():
