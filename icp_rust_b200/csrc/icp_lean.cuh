@@ -430,6 +430,8 @@ ICP_DEV void lean_accumulate_point(double acc[16], const Transform& Ti, double s
 {
     const double a0 = -sy, a1 = sx;   // jacobian(), lib.rs:176-184
     const double b0 = Ti.r00 * a0 + Ti.r01 * a1, b1 = Ti.r10 * a0 + Ti.r11 * a1;
+    // (a 20-bit hardware seed + Newton steps in FMA arithmetic instead of the correctly rounded quotient and
+    // root was measured: 156k against 166k pairs/s — its dependent FMA chain is longer than the division's)
     const double w0r = huber_drho_of_residual(rr.x), w1r = huber_drho_of_residual(rr.y);
     const double w0 = valid ? w0r : 0., w1 = valid ? w1r : 0.;
     const double wb0 = w0 * b0, wb1 = w1 * b1;
