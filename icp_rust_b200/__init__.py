@@ -277,6 +277,15 @@ class Target:
         except Exception:
             pass
 
+    def update(self, add=None, remove_idx=None):
+        """icp_b200_target_update: drop the points `remove_idx` names (survivors close up), append `add`."""
+        add = np.zeros((0, self.dim)) if add is None else np.ascontiguousarray(add, dtype=np.float64).reshape(-1, self.dim)
+        rem = np.zeros(0, dtype=np.uint32) if remove_idx is None else np.ascontiguousarray(remove_idx, dtype=np.uint32)
+        rc = self.ctx._L.icp_b200_target_update(self._h, add.ctypes.data if add.size else None, add.shape[0],
+                                                rem.ctypes.data if rem.size else None, rem.size)
+        self.ctx._check(rc)
+        self.m = self.m - len(np.unique(rem)) + add.shape[0]
+
     def search(self, queries):
         """KdTree::search(&q).0 for every row of queries (src/lib.rs:121,164)."""
         q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, self.dim)

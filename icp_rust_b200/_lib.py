@@ -39,7 +39,7 @@ EXPORTS = [
     "icp_b200_estimate_batch_device", "icp_b200_icp2d_estimate", "icp_b200_icp3d_estimate",
     "icp_b200_target_create", "icp_b200_target_destroy", "icp_b200_target_estimate_batch",
     "icp_b200_target_estimate_batch_device", "icp_b200_target_search", "icp_b200_target_search_device",
-    "icp_b200_calc_stddevs_batch",
+    "icp_b200_calc_stddevs_batch", "icp_b200_target_update",
 ]
 
 _cuda = None
@@ -70,6 +70,7 @@ def cuda_lib():
         L.icp_b200_target_create.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
         L.icp_b200_target_destroy.argtypes = [C.c_void_p]
         L.icp_b200_target_destroy.restype = None
+        L.icp_b200_target_update.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.icp_b200_target_estimate_batch.argtypes = [C.c_void_p, C.POINTER(Batch)]
         L.icp_b200_target_estimate_batch_device.argtypes = [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_int]
         L.icp_b200_target_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]

@@ -100,6 +100,10 @@ struct icp_b200_target {
     DevBuf pts, x, y, z, idx, cstart, cnt, slot, keys;
     DevBuf pf, seed;          // 2-D fast search (icp_target_nn.cuh); seed_ptr null when it is off
     const uint32_t* seed_ptr = nullptr;
+    std::vector<double> host_pts;             // the point set (AoS), kept for icp_b200_target_update
+    double bbox[6] = {0, 0, 0, 0, 0, 0};      // bounding box the geometry was built for (min xyz, max xyz)
+    uint32_t m_built = 0;                     // point count the geometry was built for
+    DevBuf idx_prev, remap, where, seed2;     // scratch of the incremental update
     DevBuf queries, out_idx;
 };
 
@@ -717,30 +721,25 @@ int icp_b200_icp3d_estimate(icp_b200_context* ctx, const double* dst_xyz, uint32
 }
 
 // ---------------------------------------------------------------------------------------------
-int icp_b200_target_create(icp_b200_context* ctx, uint32_t dim, const double* dst, uint32_t m, icp_b200_target** out)
+// (Re)builds the whole device structure of a target from t->host_pts: bounding box -> geometry -> counting sort ->
+// binary32 copies -> jump-flooded seeds.  Used by icp_b200_target_create and, when an update leaves the
+// geometry it was built for, by icp_b200_target_update.
+static int target_build(icp_b200_target* t)
 {
-    if (!ctx || !out) return ICP_B200_ERR_INVALID_ARGUMENT;
-    *out = nullptr;
-    if (dim != 2 && dim != 3) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "dim must be 2 or 3");
-    if (m && !dst) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null dst");
-    ICP_CUDA(ctx, cudaSetDevice(ctx->device));
-    icp_b200_target* t = new (std::nothrow) icp_b200_target();
-    if (!t) return ICP_B200_ERR_OUT_OF_MEMORY;
-    t->ctx = ctx; t->dim = dim; t->m = m;
-    ctx->info = icp_b200_call_info{};
+    icp_b200_context* ctx = t->ctx;
+    const uint32_t dim = t->dim, m = (uint32_t)(t->host_pts.size() / dim);
+    const double* dst = t->host_pts.data();
+    t->m = m;
+    t->seed_ptr = nullptr;
     cudaStream_t st = ctx->stream[0];
-    auto bail = [&](int rc) { icp_b200_target_destroy(t); return rc; };
-#define ICP_T(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cudaGetLastError(); return bail(fail(ctx, ICP_B200_ERR_CUDA, #call, e__)); } } while (0)
+#define ICP_T(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cudaGetLastError(); return fail(ctx, e__ == cudaErrorMemoryAllocation ? ICP_B200_ERR_OUT_OF_MEMORY : ICP_B200_ERR_CUDA, #call, e__); } } while (0)
     if (m == 0) {  // an empty target is representable; estimating against it reports EMPTY_TARGET
         t->g = grid_make_geom(0, 0, 0, 0, 0, 0, (int)dim, 1);
         ICP_T(t->cstart.ensure(8));
         ICP_T(cudaMemsetAsync(t->cstart.p, 0, 8, st));
         ICP_T(cudaStreamSynchronize(st));
-        *out = t;
         return ICP_B200_OK;
     }
-    for (uint64_t q = 0; q < (uint64_t)m * dim; ++q)
-        if (!(std::fabs(dst[q]) <= kF64Max)) return bail(fail(ctx, ICP_B200_ERR_NON_FINITE, "target holds NaN/Inf"));
     ICP_T(t->pts.ensure((size_t)m * dim * 8));
     ICP_T(t->x.ensure((size_t)m * 8));
     ICP_T(t->y.ensure((size_t)m * 8));
@@ -763,12 +762,14 @@ int icp_b200_target_create(icp_b200_context* ctx, uint32_t dim, const double* ds
         unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
         double d; std::memcpy(&d, &b, 8); return d;
     };
+    for (int q = 0; q < 6; ++q) t->bbox[q] = unkey(keys[q]);
     // cell budget per point, bounded (cell tables stay L2-resident).  2-D targets search a seeded disc
     // (icp_target_nn.cuh): empty cells cost nothing there, so the cells are small; the ring search of
     // 3-D targets pays for every empty cell it crosses.
     const int cells_per_point = env_int("ICP_B200_TARGET_CELLS_PER_POINT", dim == 2 ? 32 : 2);
     long long budget = std::max<long long>(64, std::min<long long>((long long)m * cells_per_point, 1ll << 24));
-    t->g = grid_make_geom(unkey(keys[0]), unkey(keys[1]), unkey(keys[2]), unkey(keys[3]), unkey(keys[4]), unkey(keys[5]), (int)dim, (int)budget);
+    t->g = grid_make_geom(t->bbox[0], t->bbox[1], t->bbox[2], t->bbox[3], t->bbox[4], t->bbox[5], (int)dim, (int)budget);
+    t->m_built = m;
     const uint32_t ncells = (uint32_t)(t->g.gx * t->g.gy * t->g.gz);
     ICP_T(t->cnt.ensure((size_t)ncells * 4));
     ICP_T(t->cstart.ensure((size_t)(ncells + 1) * 4));
@@ -787,7 +788,7 @@ int icp_b200_target_create(icp_b200_context* ctx, uint32_t dim, const double* ds
     target_scan_kernel<<<1, 1024, 128, st>>>(tb, ncells);
     if (dim == 2) target_scatter_kernel<2><<<blocks, 256, 0, st>>>(tb); else target_scatter_kernel<3><<<blocks, 256, 0, st>>>(tb);
     ICP_T(cudaGetLastError());
-    ctx->info.kernel_launches = 4;
+    ctx->info.kernel_launches += 4;
     if (fast2d) {
         // jump flooding: steps 2^k >= half the grid ... 1, then 1 once more; cnt[] is free after the scan
         const int cblocks = (int)std::min<uint32_t>((ncells + 255) / 256, (uint32_t)ctx->sm_count * 16);
@@ -810,8 +811,140 @@ int icp_b200_target_create(icp_b200_context* ctx, uint32_t dim, const double* ds
         t->seed_ptr = t->seed.as<uint32_t>();
     }
     ICP_T(cudaStreamSynchronize(st));
-#undef ICP_T
+    return ICP_B200_OK;
+}
+
+int icp_b200_target_create(icp_b200_context* ctx, uint32_t dim, const double* dst, uint32_t m, icp_b200_target** out)
+{
+    if (!ctx || !out) return ICP_B200_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (dim != 2 && dim != 3) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "dim must be 2 or 3");
+    if (m && !dst) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null dst");
+    ICP_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (uint64_t q = 0; q < (uint64_t)m * dim; ++q)
+        if (!(std::fabs(dst[q]) <= kF64Max)) return fail(ctx, ICP_B200_ERR_NON_FINITE, "target holds NaN/Inf");
+    icp_b200_target* t = new (std::nothrow) icp_b200_target();
+    if (!t) return ICP_B200_ERR_OUT_OF_MEMORY;
+    t->ctx = ctx; t->dim = dim;
+    try {
+        t->host_pts.assign(dst, dst + (size_t)m * dim);   // the library's copy of `dst` (the reference borrows it for 'a)
+    } catch (const std::bad_alloc&) {
+        delete t;
+        return ICP_B200_ERR_OUT_OF_MEMORY;
+    }
+    ctx->info = icp_b200_call_info{};
+    const int rc = target_build(t);
+    if (rc != ICP_B200_OK) {
+        icp_b200_target_destroy(t);
+        return rc;
+    }
     *out = t;
+    return ICP_B200_OK;
+}
+
+// Icp2d::new on a CHANGED point set without paying for a new one (the reference rebuilds its kd-tree for
+// every frame: src/lib.rs:97-102, examples/scan2d.rs:87).  New point set = the old one without the points
+// `remove_idx` names (the survivors keep their order: indices close up), then `add` appended.
+// As long as the added points lie inside the bounding box the grid was built for and the point count stays
+// within a factor two of it, the update keeps the geometry and the cell tables' size: it re-sorts the points
+// into the existing cells (count / scan / scatter), carries every cell's seed over to the new position of the
+// point it named (a removed point hands over to its successor) and refloods the seeds once around the cells
+// that received points — no bounding-box round trip, no allocation, 2 of the 14 seed passes.  Seeds only bound
+// a search disc (icp_target_nn.cuh): whatever they are, searches return the exact nearest neighbour.
+// Otherwise the structure is rebuilt (target_build).
+int icp_b200_target_update(icp_b200_target* t, const double* add, uint32_t n_add, const uint32_t* remove_idx,
+                           uint32_t n_remove)
+{
+    if (!t) return ICP_B200_ERR_INVALID_ARGUMENT;
+    icp_b200_context* ctx = t->ctx;
+    const uint32_t dim = t->dim, m_old = t->m;
+    if ((n_add && !add) || (n_remove && !remove_idx)) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null add / remove_idx");
+    for (uint64_t q = 0; q < (uint64_t)n_add * dim; ++q)
+        if (!(std::fabs(add[q]) <= kF64Max)) return fail(ctx, ICP_B200_ERR_NON_FINITE, "added points hold NaN/Inf");
+    ICP_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->info = icp_b200_call_info{};
+    std::vector<uint8_t> gone(m_old, 0);
+    for (uint32_t k = 0; k < n_remove; ++k) {
+        if (remove_idx[k] >= m_old) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "remove_idx out of range");
+        gone[remove_idx[k]] = 1;
+    }
+    // survivors close up; remap[old index] = new index of the point, for a removed point that of its successor
+    std::vector<uint32_t> remap(m_old);
+    std::vector<double> np;
+    np.reserve(((size_t)m_old + n_add) * dim);
+    uint32_t kept = 0;
+    for (uint32_t j = 0; j < m_old; ++j) {
+        remap[j] = kept;
+        if (!gone[j]) {
+            np.insert(np.end(), t->host_pts.begin() + (size_t)j * dim, t->host_pts.begin() + (size_t)(j + 1) * dim);
+            ++kept;
+        }
+    }
+    np.insert(np.end(), add, add + (size_t)n_add * dim);
+    const uint32_t m = kept + n_add;
+    bool inside = true;
+    for (uint32_t k = 0; k < n_add && inside; ++k)
+        for (uint32_t d = 0; d < dim; ++d)
+            inside = inside && add[(size_t)k * dim + d] >= t->bbox[d] && add[(size_t)k * dim + d] <= t->bbox[3 + d];
+    t->host_pts.swap(np);
+    const bool incremental = inside && m_old > 0 && m > 0 && m >= t->m_built / 2 && m <= 2 * (uint64_t)t->m_built &&
+                             env_int("ICP_B200_TARGET_INCREMENTAL", 1) != 0;
+    if (!incremental) return target_build(t);
+    for (uint32_t j = 0; j < m_old; ++j) remap[j] = std::min(remap[j], m - 1);   // a removed tail hands over to the last point
+
+    cudaStream_t st = ctx->stream[0];
+    const uint32_t ncells = (uint32_t)(t->g.gx * t->g.gy * t->g.gz);
+    const bool fast2d = t->seed_ptr != nullptr;
+    // the old order of the sorted points survives the re-sort in idx_prev (the seeds name sorted positions)
+    if (fast2d) {
+        ICP_CUDA(ctx, t->idx_prev.ensure((size_t)m_old * 4));
+        ICP_CUDA(ctx, cudaMemcpyAsync(t->idx_prev.p, t->idx.p, (size_t)m_old * 4, cudaMemcpyDeviceToDevice, st));
+        ICP_CUDA(ctx, t->remap.ensure((size_t)m_old * 4));
+        ICP_CUDA(ctx, cudaMemcpyAsync(t->remap.p, remap.data(), (size_t)m_old * 4, cudaMemcpyHostToDevice, st));
+        ICP_CUDA(ctx, t->where.ensure((size_t)m * 4));
+    }
+    ICP_CUDA(ctx, t->pts.ensure((size_t)m * dim * 8));
+    ICP_CUDA(ctx, t->x.ensure((size_t)m * 8));
+    ICP_CUDA(ctx, t->y.ensure((size_t)m * 8));
+    if (dim == 3) ICP_CUDA(ctx, t->z.ensure((size_t)m * 8));
+    ICP_CUDA(ctx, t->idx.ensure((size_t)m * 4));
+    ICP_CUDA(ctx, t->slot.ensure((size_t)m * 4));
+    if (fast2d) ICP_CUDA(ctx, t->pf.ensure((size_t)m * 8));
+    ICP_CUDA(ctx, cudaMemcpyAsync(t->pts.p, t->host_pts.data(), (size_t)m * dim * 8, cudaMemcpyHostToDevice, st));
+    ctx->info.h2d_bytes += (uint64_t)m * dim * 8 + (fast2d ? (uint64_t)m_old * 4 : 0);
+    // seeds move to the second buffer while cnt[] (the flood's other buffer) counts the cells again
+    if (fast2d) {
+        ICP_CUDA(ctx, t->seed2.ensure((size_t)ncells * 4));
+        ICP_CUDA(ctx, cudaMemcpyAsync(t->seed2.p, t->seed.p, (size_t)ncells * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    ICP_CUDA(ctx, cudaMemsetAsync(t->cnt.p, 0, (size_t)ncells * 4, st));
+    TargetBuild tb{};
+    tb.pts = t->pts.as<double>(); tb.m = m; tb.g = t->g;
+    tb.cnt = t->cnt.as<uint32_t>(); tb.slot = t->slot.as<uint32_t>(); tb.cstart = t->cstart.as<uint32_t>();
+    tb.x = t->x.as<double>(); tb.y = t->y.as<double>(); tb.z = t->z.as<double>(); tb.idx = t->idx.as<uint32_t>();
+    tb.pf = fast2d ? t->pf.as<float2>() : nullptr;
+    tb.where = fast2d ? t->where.as<uint32_t>() : nullptr;
+    const int blocks = (int)std::min<uint32_t>((m + 255) / 256, (uint32_t)ctx->sm_count * 8);
+    if (dim == 2) target_count_kernel<2><<<blocks, 256, 0, st>>>(tb); else target_count_kernel<3><<<blocks, 256, 0, st>>>(tb);
+    target_scan_kernel<<<1, 1024, 128, st>>>(tb, ncells);
+    if (dim == 2) target_scatter_kernel<2><<<blocks, 256, 0, st>>>(tb); else target_scatter_kernel<3><<<blocks, 256, 0, st>>>(tb);
+    ICP_CUDA(ctx, cudaGetLastError());
+    ctx->info.kernel_launches += 3;
+    if (fast2d) {
+        const int cblocks = (int)std::min<uint32_t>((ncells + 255) / 256, (uint32_t)ctx->sm_count * 16);
+        target_seed_remap_kernel<<<cblocks, 256, 0, st>>>(t->seed2.as<uint32_t>(), ncells, t->idx_prev.as<uint32_t>(), m_old,
+                                                          t->remap.as<uint32_t>(), t->where.as<uint32_t>(), m, t->seed.as<uint32_t>());
+        if (n_add)
+            target_seed_added_kernel<<<(int)std::min<uint32_t>((n_add + 255) / 256, 4096u), 256, 0, st>>>(
+                t->g, t->pts.as<double>(), kept, m, t->where.as<uint32_t>(), t->seed.as<uint32_t>());
+        // one reflood around the touched cells: two passes of step 1 (seed -> seed2 -> seed)
+        target_seed_pass_kernel<<<cblocks, 256, 0, st>>>(t->g, tb.x, tb.y, t->seed.as<uint32_t>(), t->seed2.as<uint32_t>(), 1);
+        target_seed_pass_kernel<<<cblocks, 256, 0, st>>>(t->g, tb.x, tb.y, t->seed2.as<uint32_t>(), t->seed.as<uint32_t>(), 1);
+        ICP_CUDA(ctx, cudaGetLastError());
+        ctx->info.kernel_launches += 3 + (n_add ? 1 : 0);
+    }
+    ICP_CUDA(ctx, cudaStreamSynchronize(st));
+    t->m = m;
     return ICP_B200_OK;
 }
 
@@ -819,7 +952,8 @@ void icp_b200_target_destroy(icp_b200_target* t)
 {
     if (!t) return;
     if (t->ctx) cudaSetDevice(t->ctx->device);
-    DevBuf* bufs[] = {&t->pts, &t->x, &t->y, &t->z, &t->idx, &t->cstart, &t->cnt, &t->slot, &t->keys, &t->queries, &t->out_idx, &t->pf, &t->seed};
+    DevBuf* bufs[] = {&t->pts, &t->x, &t->y, &t->z, &t->idx, &t->cstart, &t->cnt, &t->slot, &t->keys, &t->queries, &t->out_idx, &t->pf, &t->seed,
+                      &t->idx_prev, &t->remap, &t->where, &t->seed2};
     for (DevBuf* b : bufs) b->release();
     delete t;
 }

@@ -27,6 +27,7 @@ struct TargetBuild {
     uint32_t* idx;
     unsigned long long* bbox_keys;  // [6] min xyz, max xyz as order-preserving keys
     float2* pf;            // null: no binary32 copies (3-D, degenerate geometry)
+    uint32_t* where;       // nullable [m]: sorted position of every point (incremental update: seeds are carried over)
 };
 
 template <int DIM>
@@ -107,6 +108,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, 1) target_scatter_kernel(TargetBuild b)
         b.y[pos] = b.pts[(size_t)j * DIM + 1];
         if (DIM == 3) b.z[pos] = b.pts[(size_t)j * DIM + 2];
         b.idx[pos] = j;
+        if (b.where) b.where[j] = pos;
         if (DIM == 2 && b.pf) {
             const GridGeom& g = b.g;
             const double px = b.pts[(size_t)j * 2 + 0], py = b.pts[(size_t)j * 2 + 1];
@@ -149,6 +151,34 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, 1) target_seed_pass_kernel(GridGeom g, co
             if (d < bd || (d == bd && s < best)) { bd = d; best = s; }
         }
         out[c] = best;
+    }
+}
+
+// Incremental update (icp_b200_target_update): every cell keeps the point its seed named — old sorted position
+// -> old index -> new index (a removed point hands over to its successor) -> new sorted position.
+ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, 1) target_seed_remap_kernel(const uint32_t* seed_old, uint32_t ncells, const uint32_t* idx_old,
+                                                                    uint32_t m_old, const uint32_t* remap, const uint32_t* where,
+                                                                    uint32_t m_new, uint32_t* seed_new)
+{
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += gridDim.x * blockDim.x) {
+        const uint32_t s = seed_old[c];
+        uint32_t out = kNnNoSeed;
+        if (s < m_old) {
+            const uint32_t ni = remap[idx_old[s]];
+            if (ni < m_new) out = where[ni];
+        }
+        seed_new[c] = out;
+    }
+}
+
+// ... and a cell that received an added point is seeded with it (any point of a cell bounds its queries' discs).
+ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, 1) target_seed_added_kernel(GridGeom g, const double* pts, uint32_t first, uint32_t m,
+                                                                    const uint32_t* where, uint32_t* seed)
+{
+    for (uint32_t j = first + blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+        const int cx = grid_coord(pts[(size_t)j * 2 + 0], g.ox, g.inv_h, g.gx);
+        const int cy = grid_coord(pts[(size_t)j * 2 + 1], g.oy, g.inv_h, g.gy);
+        seed[(uint32_t)cy * (uint32_t)g.gx + (uint32_t)cx] = where[j];   // several added points in one cell: any of them
     }
 }
 

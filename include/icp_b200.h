@@ -163,6 +163,17 @@ int icp_b200_target_create(icp_b200_context *ctx, uint32_t dim, const double *ds
                            icp_b200_target **out);
 void icp_b200_target_destroy(icp_b200_target *target);
 
+/* The same target with a changed point set, without building a new one — `Icp2d::new` on the next frame's
+ * map (the reference rebuilds its kd-tree per frame: src/lib.rs:97-102, examples/scan2d.rs:87).  New point
+ * set = the old one without the points `remove_idx` names (the survivors keep their order, so their indices
+ * close up), then the `n_add` points of `add` (HOST pointers) appended: searches and estimates return
+ * indices into that new array.  While the added points stay inside the bounding box of the last full build
+ * and the point count within a factor two of it, the grid geometry, the cell tables and the seeds are kept
+ * and only re-sorted / carried over (see icp_b200.cu); otherwise the structure is rebuilt.  Either way every
+ * later search is exact.  Not to be called while work using the target is in flight. */
+int icp_b200_target_update(icp_b200_target *target, const double *add, uint32_t n_add,
+                           const uint32_t *remove_idx, uint32_t n_remove);
+
 /* estimate() of every `src` scan against the one shared target; HOST pointers
  * (batch->dst / dst_off are ignored). */
 int icp_b200_target_estimate_batch(icp_b200_target *target, const icp_b200_batch *batch);

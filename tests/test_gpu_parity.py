@@ -570,3 +570,52 @@ def test_config4_baseline_shape(ctx, icp, frames3d_20):
     assert np.array_equal(g["inner"], o["inner"])
     assert np.array_equal(g["corr_hash"], o["corr_hash"])
     assert np.abs(g["T"] - o["T"]).max() <= TOL
+
+
+def test_target_update_matches_fresh_build(ctx, icp):
+    """icp_b200_target_update: after a series of removals and additions — inside the
+    bounding box (incremental path: geometry and seeds kept) and outside it (rebuild) — every search
+    equals a freshly built target's and the oracle's on the same point set; estimates too."""
+    rng = np.random.default_rng(21)
+    m = icp.synth_map(30000, seed=7)
+    pts = m.copy()
+    t = icp.Target(pts, ctx)
+    scans, off, T0 = icp.synth_map_scans(6, beams=1080, seed=7)
+    q = np.concatenate([scans[off[b]:off[b + 1]] @ T0[b, :4].reshape(2, 2).T + T0[b, 4:6] for b in range(6)]
+                       + [rng.uniform(m.min(0), m.max(0), (500, 2))])
+    for step in range(5):
+        rem = rng.choice(len(pts), size=int(rng.integers(1, 3000)), replace=False).astype(np.uint32)
+        if step == 1:
+            rem = np.concatenate([rem, rem[:50]])          # duplicates in remove_idx are tolerated
+        if step == 2:
+            rem = np.arange(len(pts) - 400, len(pts), dtype=np.uint32)   # a removed tail
+        base = pts[rng.integers(0, len(pts), 2500)]
+        add = base + rng.normal(0, 15.0, base.shape)
+        lo, hi = m.min(0), m.max(0)
+        add = np.clip(add, lo, hi)                          # inside the box of the build: incremental path
+        if step == 3:
+            add = np.concatenate([add, [[hi[0] + 5000.0, hi[1] + 100.0]]])   # outside: the structure is rebuilt
+        t.update(add, rem)
+        keep = np.ones(len(pts), bool)
+        keep[rem] = False
+        pts = np.concatenate([pts[keep], add])
+        assert t.m == len(pts)
+        got = t.search(q)
+        fresh = icp.Target(pts, ctx)
+        assert np.array_equal(got, fresh.search(q)), f"step {step}"
+        fresh.close()
+        assert np.array_equal(got, oracle.nn_search(pts, q, oracle.NN_KDTREE)), f"step {step}"
+    n = 4
+    g = t.estimate_batch(scans[:n * 1080], off[:n + 1], T0[:n], 10)
+    o = oracle.icp_estimate_batch(2, scans[:n * 1080], off[:n + 1], pts, None, T0[:n], 10)
+    assert np.array_equal(g["inner"], o["inner"]) and np.array_equal(g["corr_hash"], o["corr_hash"])
+    # 3-D target, everything removed, then refilled
+    p3 = rng.normal(0, 1, (2000, 3))
+    t3 = icp.Target(p3, ctx)
+    t3.update(None, np.arange(2000, dtype=np.uint32))
+    assert t3.m == 0
+    t3.update(p3[:700] * 0.5, None)
+    q3 = rng.normal(0, 1, (300, 3))
+    assert np.array_equal(t3.search(q3), oracle.nn_search(p3[:700] * 0.5, q3, oracle.NN_BRUTE))
+    t3.close()
+    t.close()
