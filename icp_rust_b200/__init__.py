@@ -352,6 +352,8 @@ def synth_scan_pairs(count, beams=1080, seed=20240807, first_pair=0, noise_mm=3.
     """Synthetic 2-D scan pairs of BASELINE.json config 2 (see csrc/synth.c).  Returns
     (src (count*beams,2), dst, offsets (count+1,), true_T (count,6))."""
     L = synth_lib()
+    if (count + 1) * beams >= 2 ** 32:
+        raise ValueError("count * beams exceeds the 32-bit offset tables of a batch")
     src = out_src if out_src is not None else np.empty((count * beams, 2))
     dst = out_dst if out_dst is not None else np.empty((count * beams, 2))
     tt = np.empty((count, 6))

@@ -169,18 +169,19 @@ int plan_launch(icp_b200_context* ctx, uint32_t dim, bool shared_target, bool or
     auto fits = [&](const Instance* c) { return c->ordered == ordered && (uint32_t)c->capacity(lean_of(c)) >= max_n; };
     if (ctx->force_instance >= 0 && ctx->force_instance < kNumInstances && fits(kInstances[ctx->force_instance]))
         inst = kInstances[ctx->force_instance];
-    for (int i = 0; !inst && i < kNumInstances; ++i)
-        if (fits(kInstances[i])) inst = kInstances[i];
-    if (inst) {
-        plan->inst = inst;
+    auto shape = [&](const Instance* c) {      // fills the plan for instance c; false when it does not fit one SM
+        plan->inst = c;
         plan->mcap = (int)((max_m + 7u) & ~7u);
-        plan->lean = lean_of(inst);
-        plan->layout = fused_layout((int)dim, inst->capacity(plan->lean), plan->mcap, ctx->cell_budget, shared_target, ordered);
+        plan->lean = lean_of(c);
+        plan->layout = fused_layout((int)dim, c->capacity(plan->lean), plan->mcap, ctx->cell_budget, shared_target, ordered);
         if (plan->lean)
-            plan->layout.total = lean_layout((int)dim, inst->capacity(true), plan->mcap, ctx->cell_budget, shared_target).total;
-        if (!shared_target && max_m > 65528u) inst = nullptr;                   // u16 indices of the shared-memory grid
-        else if ((int)plan->layout.total > ctx->max_smem_optin) inst = nullptr;  // does not fit one SM
-    }
+            plan->layout.total = lean_layout((int)dim, c->capacity(true), plan->mcap, ctx->cell_budget, shared_target).total;
+        if (!shared_target && max_m > 65528u) return false;                      // u16 indices of the shared-memory grid
+        return (int)plan->layout.total <= ctx->max_smem_optin;
+    };
+    if (inst && !shape(inst)) inst = nullptr;
+    for (int i = 0; !inst && i < kNumInstances; ++i)     // the first instance that holds the scan AND fits an SM
+        if (fits(kInstances[i]) && shape(kInstances[i])) inst = kInstances[i];
     if (ctx->force_stream && !ordered) inst = nullptr;
     if (!inst) {
         // large scans: streaming kernel (warp-tree sums, or the tiled reference-order chain)
@@ -980,6 +981,8 @@ int icp_b200_target_search_device(icp_b200_target* t, const double* queries, uin
     if (nq == 0) return ICP_B200_OK;
     if (!queries || !out_index) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null queries / out_index");
     if (t->m == 0) return fail(ctx, ICP_B200_ERR_EMPTY_TARGET, "search on an empty target");
+    if (t->dim == 2 && (reinterpret_cast<uintptr_t>(queries) & 15u) != 0)
+        return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "2-D queries must be 16-byte aligned (they are read as 128-bit loads)");
     ICP_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = ensure_events(ctx);
     if (rc != ICP_B200_OK) return rc;

@@ -197,6 +197,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, 2) nn_search_kernel(TargetView tv, const 
         } else {
             qx = queries[q * 3 + 0]; qy = queries[q * 3 + 1]; qz = queries[q * 3 + 2];
         }
+        // the reference would panic comparing NaN distances; a non-finite query gets index -1
+        if (!(fabs(qx) <= kF64Max) || !(fabs(qy) <= kF64Max) || !(fabs(qz) <= kF64Max)) { out_idx[q] = -1; continue; }
         const NnResult<DIM, uint32_t, uint32_t> r = target_nn_search<DIM>(tv, qx, qy, qz);
         out_idx[q] = r.idx;
     }

@@ -16,9 +16,20 @@
  *    and its output transform equals its initial transform.
  *  - There is no CPU fallback: without a CUDA device every compute entry returns
  *    ICP_B200_ERR_NO_DEVICE / ICP_B200_ERR_CUDA.
- *  - Threading: a context owns one device, its streams and scratch memory.  Calls on ONE context
- *    must be serialised by the caller; different contexts (also on the same device) are
- *    independent and may be used from different threads.
+ *  - Threading: a context owns one device, its streams and scratch memory (work counters, the
+ *    re-run list of the guard, per-CTA slabs).  Calls on ONE context must be serialised by the
+ *    caller, and that includes work still in flight: after an asynchronous device-pointer call
+ *    (synchronize == 0) the next call on the same context must be issued on the SAME stream, or
+ *    after that stream has been synchronised.  Different contexts (also on the same device) are
+ *    independent and may be used from different threads: one context per thread.
+ *  - Host-pointer entries copy with cudaMemcpyAsync on two streams so that transfers overlap
+ *    compute.  That overlap needs PINNED (page-locked) caller buffers (cudaHostAlloc /
+ *    cudaHostRegister); pageable memory works but every copy then serialises.
+ *  - Parity: results are checked against oracle/, a C restatement of the crate.  Its median is the
+ *    mathematically exact order statistic ((b + c) / 2 of the true middle pair for even n);
+ *    src/stats.rs:23-26 reads input[n/2 - 1] after a second select_nth_unstable_by, which the
+ *    Rust standard library does not promise to leave in place — rust/tests/dump_golden.rs prints
+ *    what a real toolchain does so that a maintainer can pin it (DESIGN.md "Oracle").
  */
 #ifndef ICP_B200_H
 #define ICP_B200_H
@@ -181,7 +192,8 @@ int icp_b200_target_estimate_batch_device(icp_b200_target *target, const icp_b20
                                           void *stream, int synchronize);
 
 /* The correspondence search alone: KdTree::search(&q).0 for q in queries
- * (src/lib.rs:121,164).  out_index[i] = index into the target's `dst`. */
+ * (src/lib.rs:121,164).  out_index[i] = index into the target's `dst`; -1 for a non-finite query
+ * (the reference would panic).  Device form: 2-D queries must be 16-byte aligned. */
 int icp_b200_target_search(icp_b200_target *target, const double *queries, uint64_t n_queries,
                            int32_t *out_index);
 int icp_b200_target_search_device(icp_b200_target *target, const double *queries, uint64_t n_queries,
