@@ -624,14 +624,17 @@ def single_pair_latency(icp, ctx, reps=20):
             o = oracle.icp_estimate(src, dst, None, MAX_ITER, nn_mode=oracle.NN_KDTREE)
         cpu_ms = (time.perf_counter() - t) / reps * 1e3
         est = icp.Icp2d.new(dst, ctx)
-        est.estimate(src, I, MAX_ITER)
-        t = time.perf_counter()
-        for _ in range(reps):
-            T = est.estimate(src, I, MAX_ITER)
-        gpu_ms = (time.perf_counter() - t) / reps * 1e3
+        out = {}
+        for ordered in (False, True):
+            est.estimate(src, I, MAX_ITER, ordered=ordered)
+            t = time.perf_counter()
+            for _ in range(reps):
+                T = est.estimate(src, I, MAX_ITER, ordered=ordered)
+            out[ordered] = ((time.perf_counter() - t) / reps * 1e3, T.to_array())
         return {"pair": "bundled 2-D scans 001 -> 002 (%d / %d points), 20 iterations" % (len(src), len(dst)),
-                "cpu_oracle_ms": cpu_ms, "c_abi_single_pair_ms": gpu_ms,
-                "bit_identical": bool(np.array_equal(T.to_array(), o["T"]))}
+                "cpu_oracle_ms": cpu_ms, "c_abi_single_pair_ms": out[False][0],
+                "max_abs_transform_difference": float(np.abs(out[False][1] - o["T"]).max()),
+                "ordered_sums_ms": out[True][0], "ordered_sums_bit_identical": bool(np.array_equal(out[True][1], o["T"]))}
     except Exception as e:  # pragma: no cover
         return {"error": repr(e)}
 

@@ -317,15 +317,21 @@ class _IcpBase:
     def new(cls, dst, ctx=None):
         return cls(dst, ctx)
 
-    def estimate(self, src, initial_transform, max_iter: int) -> Transform:
-        """Estimates the transform that converts the `src` points to `dst` (src/lib.rs:104-130 / 146-173)."""
+    def estimate(self, src, initial_transform, max_iter: int, ordered: bool = False) -> Transform:
+        """Estimates the transform that converts the `src` points to `dst` (src/lib.rs:104-130 / 146-173).
+        ordered=False: guarded warp-tree sums (the reference's decisions, transform within 1e-9, lowest
+        latency); ordered=True: reference-order sums, bit-identical transform."""
         src = np.ascontiguousarray(src, dtype=np.float64).reshape(-1, self.DIM)
         T0 = _as_T6(initial_transform)
+        off = np.array([0, len(src)], dtype=np.uint32)
         if self._target is not None:
-            off = np.array([0, len(src)], dtype=np.uint32)
-            # one pair: the reference's exact sums (any scan size)
             res = self._target.estimate_batch(src, off, T0[None], max_iter, want_inner=False, want_hash=False,
-                                              ordered=True)
+                                              ordered=ordered)
+            return Transform.from_array(res["T"][0])
+        if ordered:
+            doff = np.array([0, len(self.dst)], dtype=np.uint32)
+            res = self.ctx.estimate_batch(src, off, self.dst, doff, T0[None], max_iter, dim=self.DIM, want_inner=False,
+                                          want_hash=False, ordered=True)
             return Transform.from_array(res["T"][0])
         out = np.zeros(6)
         L = self.ctx._L

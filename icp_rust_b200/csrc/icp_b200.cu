@@ -88,6 +88,7 @@ struct icp_b200_context {
     int force_instance = -1;
     int use_lean = 1;       // ICP_B200_LEAN=0: warp-tree batches on the icp_fused.cuh schedule instead of icp_lean.cuh
     int stream_cells_per_point = 8;   // ICP_B200_STREAM_CELLS_PER_POINT: cell budget of the streaming kernel's per-pair grids
+    int single_ordered = 0;     // ICP_B200_SINGLE_ORDERED=1: the single-pair entries use ordered sums
     int stream_nn_group = 0;    // ICP_B200_STREAM_NN_GROUP=1: a group of lanes per query in the streaming kernel's search
     int force_stream = 0;   // ICP_B200_FORCE_STREAM=1: route every warp-tree batch to the streaming kernel (tests)
 };
@@ -653,6 +654,7 @@ int icp_b200_create(int device, icp_b200_context** out)
     ctx->stream_cells_per_point = std::max(1, std::min(256, env_int("ICP_B200_STREAM_CELLS_PER_POINT", 8)));
     ctx->force_stream = env_int("ICP_B200_FORCE_STREAM", 0);
     ctx->stream_nn_group = env_int("ICP_B200_STREAM_NN_GROUP", 0);
+    ctx->single_ordered = env_int("ICP_B200_SINGLE_ORDERED", 0);
     ctx->use_lean = env_int("ICP_B200_LEAN", 1);
     ctx->guard = env_int("ICP_B200_GUARD", 1);
     if (const char* gs = getenv("ICP_B200_GUARD_SCALE")) ctx->guard_scale = std::max(0.0, atof(gs));
@@ -705,7 +707,10 @@ static int single_pair(icp_b200_context* ctx, uint32_t dim, const double* dst, u
     icp_b200_batch b{};
     b.dim = dim; b.batch = 1; b.max_iter = max_iter; b.corr_mode = ICP_B200_CORR_NONE;
     b.src = src; b.src_off = so; b.dst = dst; b.dst_off = dof; b.init_T = T0; b.out_T = out;
-    b.flags = ICP_B200_FLAG_ORDERED_SUMS;  // one pair: the reference's exact sums (any scan size)
+    // One pair is a latency problem: the guarded warp-tree mode (same decisions, transform within 1e-9) finishes a
+    // 666-point pair in well under half the time of the reference-order sums, whose 2n dependent additions per
+    // evaluation cannot be spread over threads.  ICP_B200_SINGLE_ORDERED=1 asks for the bit-identical transform.
+    b.flags = ctx->single_ordered ? ICP_B200_FLAG_ORDERED_SUMS : 0u;
     return estimate_host_impl(ctx, nullptr, &b);
 }
 

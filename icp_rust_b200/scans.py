@@ -66,7 +66,7 @@ def load_fixture(name):
     return [pts[off[k]:off[k + 1]] for k in range(len(off) - 1)]
 
 
-def scan_chain(scans, max_iter=20, ctx=None, first=0, count=None):
+def scan_chain(scans, max_iter=20, ctx=None, first=0, count=None, ordered=True):
     """The loop of examples/scan2d.rs:62-105 / scan3d.rs:104-148 without the window.
     Returns (transforms, path): `transforms[k]` aligns scans[first] to scans[first+1+k], warm-started
     from transforms[k-1]; `path[k]` is the translation of its inverse."""
@@ -79,7 +79,7 @@ def scan_chain(scans, max_iter=20, ctx=None, first=0, count=None):
     transforms, path = [], []
     last = len(scans) if count is None else min(len(scans), first + 1 + count)
     for k in range(first + 1, last):
-        T = cls.new(scans[k], ctx).estimate(src, T, max_iter)
+        T = cls.new(scans[k], ctx).estimate(src, T, max_iter, ordered=ordered)   # ordered: the reference's own bits
         transforms.append(T)
         path.append(T.inverse().t.copy())
     return transforms, np.array(path).reshape(-1, 2)

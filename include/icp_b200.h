@@ -157,7 +157,9 @@ int icp_b200_estimate_batch(icp_b200_context *ctx, const icp_b200_batch *batch);
 int icp_b200_estimate_batch_device(icp_b200_context *ctx, const icp_b200_batch *batch,
                                    void *stream, int synchronize);
 
-/* Single-pair wrappers with the reference's argument order:
+/* Single-pair wrappers with the reference's argument order (default reduction mode: guarded warp-tree sums,
+ * transform within 1e-9 of the reference arithmetic; environment ICP_B200_SINGLE_ORDERED=1 when the context is
+ * created: ordered sums, bit-identical transform, about twice the latency):
  *   Icp2d::new(dst) (src/lib.rs:97) + Icp2d::estimate(src, initial_transform, max_iter)
  *   (src/lib.rs:105-110); Icp3d twins (src/lib.rs:139, 148-153). */
 int icp_b200_icp2d_estimate(icp_b200_context *ctx, const double *dst_xy, uint32_t n_dst,

@@ -106,7 +106,9 @@ def test_l_shape_reference_test(ctx, icp, dim):  # lib.rs:510-551 / 554-595
     for p, q in zip(src, dst):
         assert np.linalg.norm(est.transform(p[:2]) - q[:2]) < 1e-3
     o = oracle.icp_estimate(src, dst, init, 20)
-    assert np.array_equal(est.to_array(), o["T"])
+    assert np.abs(est.to_array() - o["T"]).max() <= TOL     # single-pair entry: guarded warp-tree sums
+    cls = icp.Icp2d if dim == 2 else icp.Icp3d
+    assert np.array_equal(cls.new(dst, ctx).estimate(src, icp.Transform.from_array(init), 20, ordered=True).to_array(), o["T"])
     for ordered in (True, False):
         g = _run(ctx, icp, [src], [dst], [init], 20, dim=dim, ordered=ordered)
         _check_vs_oracle(g, [src], [dst], [init], 20, ordered=ordered)
