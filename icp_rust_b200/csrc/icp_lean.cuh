@@ -425,6 +425,16 @@ ICP_DEV_NOINLINE void lean_general_selection(LeanSel* sel, const double2* r2v, i
 // the medians, and warp 0 applies g and R once.  Same quantities as lib.rs:242-255 up to summation
 // rounding (tree mode: decisions are guarded, transforms agree to ~1e-13).
 // acc: 0-4 axis 0 (A B C D E), 5-9 axis 1, 10 Huber cost (lib.rs:47-48), 11-15 unused (zero).
+// The two Huber weights and the Huber cost of one point.  (Out of line — to shrink the evaluation loop, whose
+// 14k instructions exceed the instruction cache: ncu shows 2.2 warps per issue slot waiting for instructions
+// with three CTAs per SM — was measured: same throughput, the quotients and the root are not what is large.)
+ICP_DEV void lean_huber3(double rx, double ry, double* w0, double* w1, double* rho)
+{
+    *w0 = huber_drho_of_residual(rx);
+    *w1 = huber_drho_of_residual(ry);
+    *rho = huber_rho(rx * rx + ry * ry);
+}
+
 // @region lean_accumulate
 ICP_DEV void lean_accumulate_point(double acc[16], const Transform& Ti, double sx, double sy, double2 rr, bool valid)
 {
@@ -432,14 +442,14 @@ ICP_DEV void lean_accumulate_point(double acc[16], const Transform& Ti, double s
     const double b0 = Ti.r00 * a0 + Ti.r01 * a1, b1 = Ti.r10 * a0 + Ti.r11 * a1;
     // (a 20-bit hardware seed + Newton steps in FMA arithmetic instead of the correctly rounded quotient and
     // root was measured: 156k against 166k pairs/s — its dependent FMA chain is longer than the division's)
-    const double w0r = huber_drho_of_residual(rr.x), w1r = huber_drho_of_residual(rr.y);
+    double w0r, w1r, rho;
+    lean_huber3(rr.x, rr.y, &w0r, &w1r, &rho);
     const double w0 = valid ? w0r : 0., w1 = valid ? w1r : 0.;
     const double wb0 = w0 * b0, wb1 = w1 * b1;
     acc[0] = acc[0] + w0; acc[1] = acc[1] + wb0; acc[2] = acc[2] + wb0 * b0;
     acc[3] = acc[3] + w0 * rr.x; acc[4] = acc[4] + wb0 * rr.x;
     acc[5] = acc[5] + w1; acc[6] = acc[6] + wb1; acc[7] = acc[7] + wb1 * b1;
     acc[8] = acc[8] + w1 * rr.y; acc[9] = acc[9] + wb1 * rr.y;
-    const double rho = huber_rho(rr.x * rr.x + rr.y * rr.y);
     acc[10] = acc[10] + (valid ? rho : 0.);
 }
 

@@ -199,7 +199,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, 2) nn_search_kernel(TargetView tv, const 
         }
         // the reference would panic comparing NaN distances; a non-finite query gets index -1
         if (!(fabs(qx) <= kF64Max) || !(fabs(qy) <= kF64Max) || !(fabs(qz) <= kF64Max)) { out_idx[q] = -1; continue; }
-        const NnResult<DIM, uint32_t, uint32_t> r = target_nn_search<DIM>(tv, qx, qy, qz);
+        const NnResult<DIM, uint32_t, uint32_t> r = target_nn_search<DIM>(tv, qx, qy, qz, -1, false);
         out_idx[q] = r.idx;
     }
 }

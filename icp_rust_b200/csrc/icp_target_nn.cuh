@@ -283,7 +283,10 @@ ICP_DEV NnResult<2, uint32_t, uint32_t> nn_exact_pass(const TargetView& tv, cons
 }
 
 // Exact 1-NN on a 2-D shared target with seeds.  Requires tv.m > 0, tv.seed, tv.pf.
-ICP_DEV NnResult<2, uint32_t, uint32_t> target_nn_search2(const TargetView& tv, double qx, double qy, int seed_pos = -1)
+// need_d2 false (the stand-alone search kernel wants the index only): the winner's exact d2 is not formed,
+// which saves its two 8-byte coordinate fetches — the kernel is bound by L1/TEX wavefronts, one per fetch.
+ICP_DEV NnResult<2, uint32_t, uint32_t> target_nn_search2(const TargetView& tv, double qx, double qy, int seed_pos = -1,
+                                                          bool need_d2 = true)
 {
     const NnQuery Q = nn_query_setup(tv, qx, qy, seed_pos);
     if (Q.slow) return nn_ring_search(tv, qx, qy);
@@ -297,7 +300,12 @@ ICP_DEV NnResult<2, uint32_t, uint32_t> target_nn_search2(const TargetView& tv, 
     });
     const float thr = nn_filter_band(f.m1, Q.a);
     // a single candidate inside the band, and the exact winner is inside the band: it is the winner
-    if (f.m2 > thr && f.m1 < 3.0e38f) return nn_result_at(tv, qx, qy, f.pos);
+    if (f.m2 > thr && f.m1 < 3.0e38f) {
+        if (need_d2) return nn_result_at(tv, qx, qy, f.pos);
+        NnResult<2, uint32_t, uint32_t> r;
+        r.d2 = 0.0; r.pos = f.pos; r.idx = (int)tv.idx[f.pos];
+        return r;
+    }
     return nn_exact_pass(tv, Q, qx, qy, thr);
 }
 
@@ -750,10 +758,10 @@ ICP_DEV NnResult<DIM, IdxT, CellT> grid_nn_search_auto(const GridView<DIM, IdxT,
 // seed_pos >= 0: a sorted position of the target (the previous outer iteration's match); -1: none
 template <int DIM>
 ICP_DEV NnResult<DIM, uint32_t, uint32_t> target_nn_search(const TargetView& tv, double qx, double qy, double qz,
-                                                          int seed_pos = -1)
+                                                          int seed_pos = -1, bool need_d2 = true)
 {
     if constexpr (DIM == 2) {
-        if (tv.pf != nullptr) return target_nn_search2(tv, qx, qy, seed_pos);
+        if (tv.pf != nullptr) return target_nn_search2(tv, qx, qy, seed_pos, need_d2);
     }
     GridView<DIM, uint32_t, uint32_t> gv;
     gv.x = tv.x; gv.y = tv.y; gv.z = tv.z; gv.idx = tv.idx; gv.cstart = tv.cstart; gv.g = tv.g;

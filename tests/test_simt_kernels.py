@@ -243,8 +243,7 @@ def _map_queries(seed, count=6, beams=360):
     return np.concatenate(out)
 
 
-@pytest.mark.parametrize("fast", [True, "warp"])
-@pytest.mark.parametrize("cells_per_point", [2, 32, 200])
+@pytest.mark.parametrize("cells_per_point,fast", [(2, True), (32, True), (200, True), (32, "warp")])
 def test_target_search_fast_path_is_exact(cells_per_point, fast):
     """Seeded, binary32-filtered disc search == brute force on a map sampled densely along walls:
     near-ties (neighbours on a wall), exact duplicates, queries on target points, far outside."""
