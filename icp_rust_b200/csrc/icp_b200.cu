@@ -181,6 +181,14 @@ int plan_launch(icp_b200_context* ctx, uint32_t dim, bool shared_target, bool or
         return (int)plan->layout.total <= ctx->max_smem_optin;
     };
     if (inst && !shape(inst)) inst = nullptr;
+    // Fewer pairs than SMs (the reference's own call pattern is ONE pair per frame, examples/scan2d.rs:87-88): every
+    // pair has an SM to itself and latency is what counts — the widest instance with dedicated service warps first
+    // (384 threads, 0.59 ms against 0.69 ms for the bundled 666-point pair), then the wide ones for larger scans.
+    if (!inst && !ordered && pairs < (uint32_t)ctx->sm_count) {
+        static const int kLatencyOrder[] = {3, 5, 7, 6};
+        for (int i : kLatencyOrder)
+            if (!inst && i < kNumInstances && fits(kInstances[i]) && shape(kInstances[i])) inst = kInstances[i];
+    }
     for (int i = 0; !inst && i < kNumInstances; ++i)     // the first instance that holds the scan AND fits an SM
         if (fits(kInstances[i]) && shape(kInstances[i])) inst = kInstances[i];
     if (ctx->force_stream && !ordered) inst = nullptr;
