@@ -680,7 +680,9 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
             // every thread; the rows below belong to the workers)
 #pragma unroll
             for (int k = 0; k < PPT; ++k) {
-                const double2 q = r2v[worker ? wtid + k * WTHREADS : 0];
+                double2 q;
+                q.x = 0.; q.y = 0.;
+                if (worker) q = r2v[wtid + k * WTHREADS];   // (service warps own no points and must not touch the rows)
                 sx[k] = q.x; sy[k] = q.y;
             }   // (a worker reads and later overwrites only its own slots of r2v: no barrier needed here)
             ICP_LT_MARK(1)

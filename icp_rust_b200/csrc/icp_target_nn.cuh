@@ -238,25 +238,38 @@ ICP_DEV void nn_walk(const TargetView& tv, const NnQuery& Q, Visit&& visit)
         }
         if (p1 == p0) break;
         ICP_NN_COUNT(cand, p1 - p0);
-        // candidates in ascending position, two per 16-byte load where the position is even (pf is
-        // 16-byte aligned): a lane's fetches are the L1/TEX unit's work — one wavefront per load
-        int p = p0;
-        if ((p & 1) != 0) {
-            const float2 v = tv.pf[p];
-            const float ex = qrx - v.x, ey = qry - v.y;
+        // candidates in ascending position; a lane's fetches are the L1/TEX unit's work — one wavefront per load
+        // instruction — so they are as wide as alignment allows: 8 bytes up to an even position, 16 bytes up to a
+        // multiple of four, then FOUR candidates per 256-bit load (sm_100 LDG.E.256; pf is 256-byte aligned)
+        auto one = [&](int p, float x, float y) {
+            const float ex = qrx - x, ey = qry - y;
             visit(p, nn_fma(ex, ex, ey * ey));
+        };
+        int p = p0;
+        if ((p & 1) != 0 && p < p1) {
+            const float2 v = tv.pf[p];
+            one(p, v.x, v.y);
             ++p;
         }
-        for (; p + 1 < p1; p += 2) {
+        if ((p & 2) != 0 && p + 2 <= p1) {
             const float4 w = *reinterpret_cast<const float4*>(tv.pf + p);
-            const float ex0 = qrx - w.x, ey0 = qry - w.y, ex1 = qrx - w.z, ey1 = qry - w.w;
-            visit(p, nn_fma(ex0, ex0, ey0 * ey0));
-            visit(p + 1, nn_fma(ex1, ex1, ey1 * ey1));
+            one(p, w.x, w.y); one(p + 1, w.z, w.w);
+            p += 2;
         }
-        if (p < p1) {
+        if ((p & 3) == 0) {
+            for (; p + 4 <= p1; p += 4) {
+                const icp_f32x8 w = icp_ldg256(tv.pf + p);
+                one(p, w.v[0], w.v[1]); one(p + 1, w.v[2], w.v[3]); one(p + 2, w.v[4], w.v[5]); one(p + 3, w.v[6], w.v[7]);
+            }
+        }
+        if ((p & 1) == 0 && p + 2 <= p1) {
+            const float4 w = *reinterpret_cast<const float4*>(tv.pf + p);
+            one(p, w.x, w.y); one(p + 1, w.z, w.w);
+            p += 2;
+        }
+        for (; p < p1; ++p) {
             const float2 v = tv.pf[p];
-            const float ex = qrx - v.x, ey = qry - v.y;
-            visit(p, nn_fma(ex, ex, ey * ey));
+            one(p, v.x, v.y);
         }
     }
 }
@@ -433,6 +446,16 @@ constexpr int kNnGroupDepth = 4;   // records per lane and step of the group sea
 
 ICP_DEV bool nn_better(double d2, int idx, double bd2, int bidx) { return d2 < bd2 || (d2 == bd2 && idx < bidx); }
 
+// One record = one 256-bit load (sm_100 LDG.E.256; the records are 32-byte aligned and were written by this kernel)
+ICP_DEV GridRec nn_load_record(const GridRec* rec, int p)
+{
+    static_assert(sizeof(GridRec) == 32, "one record per 256-bit load");
+    const icp_f32x8 w = icp_ldg256_rw(rec + p);
+    GridRec r;
+    memcpy(&r, &w, 32);
+    return r;
+}
+
 // Candidates [p0, p1) against `best`, in ascending position, on records: four at a time with their
 // eight 16-byte loads issued before any of them is used — the records sit in L2 (~250 cycles away)
 // and a CTA of the streaming kernel has only 16 warps to hide that with.
@@ -454,11 +477,11 @@ ICP_DEV void nn_scan_records(const GridRec* rec, int p0, int p1, double qx, doub
     };
     int p = p0;
     for (; p + 4 <= p1; p += 4) {
-        const GridRec c0 = rec[p], c1 = rec[p + 1], c2 = rec[p + 2], c3 = rec[p + 3];
+        const GridRec c0 = nn_load_record(rec, p), c1 = nn_load_record(rec, p + 1), c2 = nn_load_record(rec, p + 2), c3 = nn_load_record(rec, p + 3);
         one(c0, p); one(c1, p + 1); one(c2, p + 2); one(c3, p + 3);
     }
     for (; p < p1; ++p) {
-        const GridRec c = rec[p];
+        const GridRec c = nn_load_record(rec, p);
         one(c, p);
     }
 }
@@ -681,7 +704,7 @@ ICP_DEV NnResult<DIM, IdxT, CellT> grid_nn_search_seeded_group(const GridView<DI
 #pragma unroll
                 for (int k = 0; k < kNnGroupDepth; ++k) {
                     const int p = pb + k * G;
-                    c[k] = rec[p < s1 ? p : s0];      // a clamped (harmless) load keeps the batch branch-free
+                    c[k] = nn_load_record(rec, p < s1 ? p : s0);      // a clamped (harmless) load keeps the batch branch-free
                 }
 #pragma unroll
                 for (int k = 0; k < kNnGroupDepth; ++k) {
