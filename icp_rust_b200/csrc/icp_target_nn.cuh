@@ -238,38 +238,26 @@ ICP_DEV void nn_walk(const TargetView& tv, const NnQuery& Q, Visit&& visit)
         }
         if (p1 == p0) break;
         ICP_NN_COUNT(cand, p1 - p0);
-        // candidates in ascending position; a lane's fetches are the L1/TEX unit's work — one wavefront per load
-        // instruction — so they are as wide as alignment allows: 8 bytes up to an even position, 16 bytes up to a
-        // multiple of four, then FOUR candidates per 256-bit load (sm_100 LDG.E.256; pf is 256-byte aligned)
-        auto one = [&](int p, float x, float y) {
-            const float ex = qrx - x, ey = qry - y;
-            visit(p, nn_fma(ex, ex, ey * ey));
-        };
+        // candidates in ascending position, two per 16-byte load where the position is even (pf is
+        // 16-byte aligned): a lane's fetches are the L1/TEX unit's work — one wavefront per load.
+        // (Four per 256-bit load — sm_100's LDG.E.256 — was measured: 4.79 against 6.33 G queries/s.)
         int p = p0;
-        if ((p & 1) != 0 && p < p1) {
+        if ((p & 1) != 0) {
             const float2 v = tv.pf[p];
-            one(p, v.x, v.y);
+            const float ex = qrx - v.x, ey = qry - v.y;
+            visit(p, nn_fma(ex, ex, ey * ey));
             ++p;
         }
-        if ((p & 2) != 0 && p + 2 <= p1) {
+        for (; p + 1 < p1; p += 2) {
             const float4 w = *reinterpret_cast<const float4*>(tv.pf + p);
-            one(p, w.x, w.y); one(p + 1, w.z, w.w);
-            p += 2;
+            const float ex0 = qrx - w.x, ey0 = qry - w.y, ex1 = qrx - w.z, ey1 = qry - w.w;
+            visit(p, nn_fma(ex0, ex0, ey0 * ey0));
+            visit(p + 1, nn_fma(ex1, ex1, ey1 * ey1));
         }
-        if ((p & 3) == 0) {
-            for (; p + 4 <= p1; p += 4) {
-                const icp_f32x8 w = icp_ldg256(tv.pf + p);
-                one(p, w.v[0], w.v[1]); one(p + 1, w.v[2], w.v[3]); one(p + 2, w.v[4], w.v[5]); one(p + 3, w.v[6], w.v[7]);
-            }
-        }
-        if ((p & 1) == 0 && p + 2 <= p1) {
-            const float4 w = *reinterpret_cast<const float4*>(tv.pf + p);
-            one(p, w.x, w.y); one(p + 1, w.z, w.w);
-            p += 2;
-        }
-        for (; p < p1; ++p) {
+        if (p < p1) {
             const float2 v = tv.pf[p];
-            one(p, v.x, v.y);
+            const float ex = qrx - v.x, ey = qry - v.y;
+            visit(p, nn_fma(ex, ex, ey * ey));
         }
     }
 }
@@ -446,15 +434,9 @@ constexpr int kNnGroupDepth = 4;   // records per lane and step of the group sea
 
 ICP_DEV bool nn_better(double d2, int idx, double bd2, int bidx) { return d2 < bd2 || (d2 == bd2 && idx < bidx); }
 
-// One record = one 256-bit load (sm_100 LDG.E.256; the records are 32-byte aligned and were written by this kernel)
-ICP_DEV GridRec nn_load_record(const GridRec* rec, int p)
-{
-    static_assert(sizeof(GridRec) == 32, "one record per 256-bit load");
-    const icp_f32x8 w = icp_ldg256_rw(rec + p);
-    GridRec r;
-    memcpy(&r, &w, 32);
-    return r;
-}
+// One record = two 16-byte loads of one 32-byte sector.  (One 256-bit load — sm_100's LDG.E.256 — was
+// measured: 3.68k against 3.83k pairs/s on config 4.)
+ICP_DEV GridRec nn_load_record(const GridRec* rec, int p) { return rec[p]; }
 
 // Candidates [p0, p1) against `best`, in ascending position, on records: four at a time with their
 // eight 16-byte loads issued before any of them is used — the records sit in L2 (~250 cycles away)

@@ -31,26 +31,6 @@ static __device__ __forceinline__ double2 smem_ld2(smem_ref r, int idx)
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(r + 16u * (uint32_t)idx) : "memory");
     return v;
 }
-// One 256-bit global load (sm_100: LDG.E.256): eight consecutive floats from a 32-byte aligned address.
-// A lane's fetches are L1/TEX wavefronts, one per load instruction: four binary32 candidates per fetch.
-struct icp_f32x8 { float v[8]; };
-static __device__ __forceinline__ icp_f32x8 icp_ldg256(const void* p)
-{
-    icp_f32x8 r;
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
-                 : "l"(p));
-    return r;
-}
-// ... the same without the read-only path, for data the running kernel itself wrote (per-CTA slabs)
-static __device__ __forceinline__ icp_f32x8 icp_ldg256_rw(const void* p)
-{
-    icp_f32x8 r;
-    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
-                 : "l"(p) : "memory");
-    return r;
-}
 // Named barriers (PTX bar.sync / bar.arrive with an id and a thread count): `arrive` does not wait.
 // Writes a thread made before arriving are visible to the threads that leave the matching sync.
 static __device__ __forceinline__ void icp_bar_sync(int id, int count)

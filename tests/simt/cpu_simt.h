@@ -193,10 +193,6 @@ static inline int __syncthreads_or(int pred)
 }
 static inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_exchange(0); }
 
-struct icp_f32x8 { float v[8]; };
-static inline icp_f32x8 icp_ldg256(const void* p) { icp_f32x8 r; std::memcpy(&r, p, 32); return r; }
-static inline icp_f32x8 icp_ldg256_rw(const void* p) { return icp_ldg256(p); }
-
 // named barriers: bar.arrive (does not wait) / bar.sync with an id and a thread count
 static inline void icp_bar_arrive(int id, int count)
 {
