@@ -244,13 +244,18 @@ def run_gpu(args, rank, local_rank, world):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
 
-    def dev_step(j, ordered=args.ordered):
+    # Consecutive steps use different input and output arrays (NBUF = 2), so every step may carry
+    # ICP_B200_FLAG_INDEPENDENT: its thread blocks start on the SMs the previous step's last pairs
+    # leave idle.  --no-overlap times the steps strictly one after the other.
+    step_flags = 0 if args.no_overlap else icp.FLAG_INDEPENDENT
+
+    def dev_step(j, ordered=args.ordered, flags=None):
         d = devb[j % NBUF]
         ctx.estimate_batch_device(dict(src=d["src"].data_ptr(), src_off=d["off"].data_ptr(), dst=d["dst"].data_ptr(),
                                        dst_off=d["off"].data_ptr(), init_T=d["T0"].data_ptr(), out_T=d["out"].data_ptr(),
                                        out_status=d["status"].data_ptr()),
                                   B, MAX_ITER, dim=2, max_src=BEAMS, max_dst=BEAMS, stream=stream.cuda_stream,
-                                  synchronize=False, ordered=ordered)
+                                  synchronize=False, ordered=ordered, flags=step_flags if flags is None else flags)
 
     def host_step(j):
         h = host[j % NBUF]
@@ -275,19 +280,32 @@ def run_gpu(args, rank, local_rank, world):
     torch.cuda.synchronize()
     barrier()
     torch.cuda.synchronize()
+    # the K timed steps: two events around all of them (an event between two steps would serialise them)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     w0 = time.time()
     evs[0].record(stream)
     for j in range(K):
         dev_step(W + j)
-        evs[j + 1].record(stream)
+    evs[K].record(stream)
     torch.cuda.synchronize()
     barrier()
     torch.cuda.synchronize()
     w1 = time.time()
     ms_total = max_over_ranks(evs[0].elapsed_time(evs[K]))
-    launch_ms = float(np.mean([evs[j].elapsed_time(evs[j + 1]) for j in range(K)]))
+    # the same steps strictly one after the other, an event after each: the duration of ONE launch,
+    # which the roofline figures are quoted on
+    for j in range(2):   # the re-run launch of a serialised step has more thread blocks: its slabs grow once
+        dev_step(j, flags=0)
+    torch.cuda.synchronize()
+    evs[0].record(stream)
+    for j in range(K):
+        dev_step(W + j, flags=0)
+        evs[j + 1].record(stream)
+    torch.cuda.synchronize()
+    each_ms = [evs[j].elapsed_time(evs[j + 1]) for j in range(K)]
+    launch_ms = float(np.mean(each_ms))
     launch_ms = max_over_ranks(launch_ms)
+    serial_value = world * B / (launch_ms * 1e-3)
     info = ctx.call_info()
     launches = info["kernel_launches"] * K
     for d in devb:
@@ -390,6 +408,13 @@ def run_gpu(args, rank, local_rank, world):
                     "d2h_bytes_per_step": int(hinfo["d2h_bytes"]), "ms_per_step": e2e_s / K * 1e3,
                     "bit_identical_to_device_path": same},
             "gpu_launches": int(launches),
+            "step_overlap": {"flag": None if args.no_overlap else "ICP_B200_FLAG_INDEPENDENT",
+                             "steps_one_after_the_other": {"value": serial_value, "unit": UNIT, "ms_per_step": launch_ms,
+                                                           "ms_min_max": [min(each_ms), max(each_ms)]},
+                             "note": "`value` times K back-to-back asynchronous calls on one stream; with the flag a step's "
+                                     "thread blocks start on the SMs the previous step's last pairs leave idle (programmatic "
+                                     "dependent launch; the tenth round of 444 resident pairs of a 4096-pair step is a quarter "
+                                     "full).  The roofline is quoted on one launch timed alone (launch_ms)."},
             "roofline": {"kernel": ("icp_fused_kernel" if args.ordered else "icp_lean_kernel") + f"<{info['block_threads']} threads>",
                          "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
@@ -678,6 +703,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ordered", action="store_true", help="ICP_B200_FLAG_ORDERED_SUMS: reference-order sums")
     ap.add_argument("--headline-only", action="store_true", help="skip the nn_search / config3 / config4 side measurements")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="time the device steps without ICP_B200_FLAG_INDEPENDENT (each waits for the previous one's last pair)")
     ap.add_argument("--no-config5", action="store_true", help="skip the 1M-pair strong-scaling leg of multi-GPU runs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

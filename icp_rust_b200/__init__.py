@@ -22,6 +22,7 @@ CORR_NONE, CORR_LAST, CORR_ALL = 0, 1, 2
 FLAG_ORDERED_SUMS = 1  # ICP_B200_FLAG_ORDERED_SUMS: reference-order sums, bit-identical transforms
 FLAG_SHARED_SOURCE = 2  # one source scan, `batch` initial transforms
 FLAG_NO_GUARD = 4  # default mode without the knife-edge guard / ordered re-run
+FLAG_INDEPENDENT = 8  # asynchronous device-pointer call that touches nothing the previous call writes: may overlap its tail
 ABI_VERSION = 3
 BREAK_CAP, BREAK_NONE, BREAK_DELTA, BREAK_ERROR = 0, 1, 2, 3
 PAIR_OK, PAIR_EMPTY_TARGET, PAIR_TOO_LARGE, PAIR_NON_FINITE = 0, 1, 2, 3

@@ -57,6 +57,12 @@ constexpr int kMaxChunks = 64;
 // ordered re-run | count of flagged pairs
 constexpr int kCtrWork = 0, kCtrErr = kMaxChunks, kCtrRedoWork = kMaxChunks + 1, kCtrRedoCount = kMaxChunks + 2;
 constexpr int kCtrWords = kMaxChunks + 3;
+// Counters of the device-pointer calls: two alternating sets (call parity) the kernels clean up
+// themselves (FusedParams::fin_counter), so back-to-back calls need no memset between them and may
+// overlap at their boundary (ICP_B200_FLAG_INDEPENDENT).  Words of set s at s * kDevSetWords.
+constexpr int kDevWork = 0, kDevFin = 1, kDevRedoWork = 2, kDevRedoFin = 3, kDevRedoCount = 4, kDevRedoSeen = 5;
+constexpr int kDevSetWords = 8, kDevErr = 2 * kDevSetWords, kDevWords = kDevErr + 1;
+constexpr int kOverlapRedoGrid = 8;   // CTAs of the re-run launch of an overlapping call (they wait on an SM each)
 
 int env_int(const char* name, int dflt)
 {
@@ -79,6 +85,11 @@ struct icp_b200_context {
     DevBuf counters;       // kCtrWords words (layout above)
     DevBuf workspace[2];
     DevBuf redo_list, redo_workspace;   // flagged pairs of the call in flight / slabs of their ordered re-run
+    // device-pointer calls: per-parity state, so that a call may start while the previous one drains
+    DevBuf dev_counters, dev_workspace[2], dev_redo_list[2], dev_redo_workspace[2];
+    uint64_t dev_calls = 0;
+    bool dev_dirty = true;  // the counters need a memset (first call, or a call that failed midway)
+    int pdl = 1;            // ICP_B200_PDL=0: never overlap calls (ICP_B200_FLAG_INDEPENDENT is ignored)
     int guard = 1;          // ICP_B200_GUARD=0: no knife-edge guard (as ICP_B200_FLAG_NO_GUARD on every call)
     double guard_scale = 1.0;   // ICP_B200_GUARD_SCALE: multiplies the guard bands (tests force re-runs with it)
     DevBuf stats_in, stats_off, stats_out;
@@ -234,7 +245,8 @@ int validate_batch(icp_b200_context* ctx, const icp_b200_batch* b, bool shared_t
     if (!b->src_off || !b->init_T || !b->out_T) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null src_off / init_T / out_T");
     if (!shared_target && !b->dst_off) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "null dst_off");
     if (b->corr_mode < 0 || b->corr_mode > 2) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "bad corr_mode");
-    if (b->flags & ~(uint32_t)(ICP_B200_FLAG_ORDERED_SUMS | ICP_B200_FLAG_SHARED_SOURCE | ICP_B200_FLAG_NO_GUARD))
+    if (b->flags & ~(uint32_t)(ICP_B200_FLAG_ORDERED_SUMS | ICP_B200_FLAG_SHARED_SOURCE | ICP_B200_FLAG_NO_GUARD |
+                               ICP_B200_FLAG_INDEPENDENT))
         return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "unknown flag bits");
     if (b->corr_mode != ICP_B200_CORR_NONE && !b->out_corr) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "corr_mode set but out_corr is null");
     return ICP_B200_OK;
@@ -259,17 +271,30 @@ void fill_params(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_
     }
 }
 
-int launch_plan(icp_b200_context* ctx, const LaunchPlan& pl, const FusedParams& fp, int grid, cudaStream_t stream)
+// `overlap`: launch with the programmatic-serialization attribute — the kernel may become resident
+// while the kernel before it on `stream` drains (icp_fused.cuh fused_launch_entry has the rules).
+int launch_plan(icp_b200_context* ctx, const LaunchPlan& pl, const FusedParams& fp, int grid, cudaStream_t stream,
+                bool overlap = false)
 {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)pl.threads);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap ? 1u : 0u;
     if (pl.stream) {
         StreamParams sp{};
         sp.f = fp; sp.n_cap = pl.n_cap; sp.m_cap = pl.m_cap; sp.c_cap = pl.c_cap;
         sp.cells_per_point = (uint32_t)ctx->stream_cells_per_point;
         sp.ordered = pl.stream_ordered ? 1u : 0u;
         sp.nn_group = (uint32_t)ctx->stream_nn_group;
-        pl.skernel<<<grid, pl.threads, pl.smem, stream>>>(sp);
+        ICP_CUDA(ctx, cudaLaunchKernelEx(&cfg, pl.skernel, sp));
     } else {
-        pl.kernel<<<grid, pl.threads, pl.smem, stream>>>(fp);
+        ICP_CUDA(ctx, cudaLaunchKernelEx(&cfg, pl.kernel, fp));
     }
     ICP_CUDA(ctx, cudaGetLastError());
     ctx->info.kernel_launches += 1;
@@ -279,26 +304,34 @@ int launch_plan(icp_b200_context* ctx, const LaunchPlan& pl, const FusedParams& 
 // Device-pointer launch of pairs [begin, end) on `stream`.  `guarded` (tree mode with the knife-edge
 // guard): pairs with a decision inside a guard band are appended to the call's redo list on the
 // device (one list and one count per call, shared by its chunks).
+// `dev_set` >= 0: a device-pointer call — the counters, workspace and flagged-pair list of that
+// parity, cleaned up by the kernels; `overlap`: the launch may start while its predecessor drains.
 int launch_range(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_target* tgt, const LaunchPlan& plan,
-                 bool guarded, uint32_t begin, uint32_t end, int chunk_slot, int ws_slot, cudaStream_t stream)
+                 bool guarded, uint32_t begin, uint32_t end, int chunk_slot, int ws_slot, cudaStream_t stream,
+                 int dev_set = -1, bool overlap = false)
 {
     FusedParams p{};
     fill_params(ctx, b, tgt, &p);
-    p.work_counter = ctx->counters.as<uint32_t>() + kCtrWork + chunk_slot;
-    p.workspace = ctx->workspace[ws_slot].as<unsigned char>();
+    uint32_t* dev = dev_set >= 0 ? ctx->dev_counters.as<uint32_t>() + dev_set * kDevSetWords : nullptr;
+    p.work_counter = dev ? dev + kDevWork : ctx->counters.as<uint32_t>() + kCtrWork + chunk_slot;
+    p.workspace = dev ? ctx->dev_workspace[dev_set].as<unsigned char>() : ctx->workspace[ws_slot].as<unsigned char>();
+    if (dev) {
+        p.fin_counter = dev + kDevFin;
+        p.out_error = ctx->dev_counters.as<int32_t>() + kDevErr;
+    }
     p.ws_stride = plan.ws_stride;
     p.pair_begin = begin; p.pair_end = end;
     p.mcap = plan.mcap;
     p.ncap = plan.stream ? (int)plan.n_cap : plan.inst->capacity(plan.lean);
     if (guarded) {
-        p.redo_list = ctx->redo_list.as<uint32_t>();
-        p.redo_count = ctx->counters.as<uint32_t>() + kCtrRedoCount;
+        p.redo_list = dev ? ctx->dev_redo_list[dev_set].as<uint32_t>() : ctx->redo_list.as<uint32_t>();
+        p.redo_count = dev ? dev + kDevRedoCount : ctx->counters.as<uint32_t>() + kCtrRedoCount;
         p.guard.det = kGuardDet * ctx->guard_scale;
         p.guard.delta = kGuardDelta * ctx->guard_scale;
         p.guard.err = kGuardErr * ctx->guard_scale;
     }
     const int grid = (int)std::min<uint32_t>((uint32_t)plan.grid, end - begin);
-    int rc = launch_plan(ctx, plan, p, grid, stream);
+    int rc = launch_plan(ctx, plan, p, grid, stream, overlap);
     if (rc != ICP_B200_OK) return rc;
     ctx->info.grid_ctas = (uint32_t)grid;
     ctx->info.block_threads = (uint32_t)plan.threads;
@@ -311,32 +344,47 @@ int launch_range(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_
 // A lone 1080-point pair takes a few milliseconds in reference order (2n dependent additions per
 // evaluation), so the re-run is issued once per call, not once per chunk.
 int launch_redo(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_target* tgt, const LaunchPlan& redo,
-                cudaStream_t stream)
+                cudaStream_t stream, int dev_set = -1, bool overlap = false)
 {
     FusedParams r{};
     fill_params(ctx, b, tgt, &r);
-    r.pair_list = ctx->redo_list.as<uint32_t>();
-    r.pair_count = ctx->counters.as<uint32_t>() + kCtrRedoCount;
-    r.work_counter = ctx->counters.as<uint32_t>() + kCtrRedoWork;
-    r.workspace = ctx->redo_workspace.as<unsigned char>();
+    if (dev_set >= 0) {
+        uint32_t* dev = ctx->dev_counters.as<uint32_t>() + dev_set * kDevSetWords;
+        r.pair_list = ctx->dev_redo_list[dev_set].as<uint32_t>();
+        r.pair_count = dev + kDevRedoCount;
+        r.work_counter = dev + kDevRedoWork;
+        r.fin_counter = dev + kDevRedoFin;
+        r.redo_seen = dev + kDevRedoSeen;
+        r.out_error = ctx->dev_counters.as<int32_t>() + kDevErr;
+        r.workspace = ctx->dev_redo_workspace[dev_set].as<unsigned char>();
+    } else {
+        r.pair_list = ctx->redo_list.as<uint32_t>();
+        r.pair_count = ctx->counters.as<uint32_t>() + kCtrRedoCount;
+        r.work_counter = ctx->counters.as<uint32_t>() + kCtrRedoWork;
+        r.workspace = ctx->redo_workspace.as<unsigned char>();
+    }
     r.ws_stride = redo.ws_stride;
     r.pair_begin = 0; r.pair_end = b.batch;
     r.mcap = redo.mcap;
     r.ncap = redo.stream ? (int)redo.n_cap : redo.inst->capacity(false);
-    return launch_plan(ctx, redo, r, (int)std::min<uint32_t>((uint32_t)redo.grid, b.batch), stream);
+    return launch_plan(ctx, redo, r, (int)std::min<uint32_t>((uint32_t)redo.grid, b.batch), stream, overlap);
 }
 
 // The ordered plan that re-runs flagged pairs, when this call wants the guard.
 int plan_redo(icp_b200_context* ctx, const icp_b200_batch* b, bool shared, uint32_t max_n, uint32_t max_m, LaunchPlan* redo,
-              bool* use)
+              bool* use, int dev_set = -1, bool overlap = false)
 {
     *use = false;
     if ((b->flags & (ICP_B200_FLAG_ORDERED_SUMS | ICP_B200_FLAG_NO_GUARD)) || !ctx->guard) return ICP_B200_OK;
     int rc = plan_launch(ctx, b->dim, shared, true, max_n, max_m, b->batch, redo);
     if (rc != ICP_B200_OK) return rc;
-    redo->grid = std::min(redo->grid, ctx->sm_count);   // a handful of pairs: one CTA per SM is plenty
-    ICP_CUDA(ctx, ctx->redo_list.ensure((size_t)b->batch * 4));
-    ICP_CUDA(ctx, ctx->redo_workspace.ensure((size_t)redo->grid * redo->ws_stride + 256));
+    // a handful of pairs: one CTA per SM is plenty; an overlapping call keeps it to a few CTAs, which
+    // sit on their SMs until the main launch has finished
+    redo->grid = std::min(redo->grid, overlap ? kOverlapRedoGrid : ctx->sm_count);
+    DevBuf& list = dev_set >= 0 ? ctx->dev_redo_list[dev_set] : ctx->redo_list;
+    DevBuf& slabs = dev_set >= 0 ? ctx->dev_redo_workspace[dev_set] : ctx->redo_workspace;
+    ICP_CUDA(ctx, list.ensure((size_t)b->batch * 4));
+    ICP_CUDA(ctx, slabs.ensure((size_t)redo->grid * redo->ws_stride + 256));
     *use = true;
     return ICP_B200_OK;
 }
@@ -380,32 +428,46 @@ int estimate_device_impl(icp_b200_context* ctx, const icp_b200_target* tgt, cons
         }
         ctx->info.d2h_bytes += (uint64_t)off.size() * 4 * (shared ? 1 : 2);
     }
+    // State of this call's parity; the call two back used it and has completed by the time this
+    // call's kernels run (fused_launch_entry).  ICP_B200_FLAG_INDEPENDENT lets the kernels become
+    // resident while the previous call's last pairs finish.
+    const int set = (int)(ctx->dev_calls & 1u);
+    const bool overlap = ctx->pdl && (b->flags & ICP_B200_FLAG_INDEPENDENT) != 0;
     LaunchPlan plan, redo;
     bool use_redo = false;
     rc = plan_launch(ctx, b->dim, shared, (b->flags & ICP_B200_FLAG_ORDERED_SUMS) != 0, max_n, max_m, b->batch, &plan);
     if (rc != ICP_B200_OK) return rc;
-    rc = plan_redo(ctx, b, shared, max_n, max_m, &redo, &use_redo);
+    rc = plan_redo(ctx, b, shared, max_n, max_m, &redo, &use_redo, set, overlap);
     if (rc != ICP_B200_OK) return rc;
-    ICP_CUDA(ctx, ctx->counters.ensure(kCtrWords * 4));
-    ICP_CUDA(ctx, ctx->workspace[0].ensure((size_t)plan.grid * plan.ws_stride + 256));
-    ICP_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, kCtrWords * 4, stream));
-    ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], stream));
-    rc = launch_range(ctx, *b, tgt, plan, use_redo, 0, b->batch, 0, 0, stream);
+    ICP_CUDA(ctx, ctx->dev_counters.ensure(kDevWords * 4));
+    ICP_CUDA(ctx, ctx->dev_workspace[set].ensure((size_t)plan.grid * plan.ws_stride + 256));
+    if (ctx->dev_dirty) ICP_CUDA(ctx, cudaMemsetAsync(ctx->dev_counters.p, 0, kDevWords * 4, stream));
+    ctx->dev_dirty = true;   // until every launch of this call is in the stream
+    ctx->dev_calls += 1;
+    // events only around a synchronous call: a record between two calls would serialise them
+    if (synchronize) ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], stream));
+    rc = launch_range(ctx, *b, tgt, plan, use_redo, 0, b->batch, 0, 0, stream, set, overlap);
     if (rc != ICP_B200_OK) return rc;
     if (use_redo) {
-        rc = launch_redo(ctx, *b, tgt, redo, stream);
+        rc = launch_redo(ctx, *b, tgt, redo, stream, set, overlap);
         if (rc != ICP_B200_OK) return rc;
     }
-    ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][1], stream));
+    ctx->dev_dirty = false;
     if (synchronize) {
+        ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][1], stream));
         int32_t err = 0;
         uint32_t nredo = 0;
-        ICP_CUDA(ctx, cudaMemcpyAsync(&err, ctx->counters.as<int32_t>() + kCtrErr, 4, cudaMemcpyDeviceToHost, stream));
-        ICP_CUDA(ctx, cudaMemcpyAsync(&nredo, ctx->counters.as<uint32_t>() + kCtrRedoCount, 4, cudaMemcpyDeviceToHost, stream));
+        const uint32_t* dev = ctx->dev_counters.as<uint32_t>() + set * kDevSetWords;
+        ICP_CUDA(ctx, cudaMemcpyAsync(&err, ctx->dev_counters.as<int32_t>() + kDevErr, 4, cudaMemcpyDeviceToHost, stream));
+        if (use_redo) ICP_CUDA(ctx, cudaMemcpyAsync(&nredo, dev + kDevRedoSeen, 4, cudaMemcpyDeviceToHost, stream));
         ICP_CUDA(ctx, cudaStreamSynchronize(stream));
         ICP_CUDA(ctx, cudaEventElapsedTime(&ctx->info.kernel_ms, ctx->ev[0][0], ctx->ev[0][1]));
         ctx->info.redo_pairs = nredo;
-        if (err != 0) return fail(ctx, pair_status_to_error(err), "at least one scan pair was rejected (see out_status)");
+        if (err != 0) {
+            // the error word is sticky across asynchronous calls; reading it resets it
+            ICP_CUDA(ctx, cudaMemsetAsync(ctx->dev_counters.as<int32_t>() + kDevErr, 0, 4, stream));
+            return fail(ctx, pair_status_to_error(err), "at least one scan pair was rejected (see out_status)");
+        }
     }
     return ICP_B200_OK;
 }
@@ -665,6 +727,7 @@ int icp_b200_create(int device, icp_b200_context** out)
     ctx->single_ordered = env_int("ICP_B200_SINGLE_ORDERED", 0);
     ctx->use_lean = env_int("ICP_B200_LEAN", 1);
     ctx->guard = env_int("ICP_B200_GUARD", 1);
+    ctx->pdl = env_int("ICP_B200_PDL", 1);
     if (const char* gs = getenv("ICP_B200_GUARD_SCALE")) ctx->guard_scale = std::max(0.0, atof(gs));
     *out = ctx;
     return ICP_B200_OK;
@@ -678,7 +741,9 @@ void icp_b200_destroy(icp_b200_context* ctx)
     DevBuf* bufs[] = {&ctx->src, &ctx->dst, &ctx->src_off, &ctx->dst_off, &ctx->init_T, &ctx->out_T, &ctx->out_inner,
                       &ctx->out_corr, &ctx->out_hash, &ctx->out_status, &ctx->counters, &ctx->workspace[0],
                       &ctx->workspace[1], &ctx->stats_in, &ctx->stats_off, &ctx->stats_out, &ctx->out_cost,
-                      &ctx->redo_list, &ctx->redo_workspace};
+                      &ctx->redo_list, &ctx->redo_workspace, &ctx->dev_counters, &ctx->dev_workspace[0],
+                      &ctx->dev_workspace[1], &ctx->dev_redo_list[0], &ctx->dev_redo_list[1],
+                      &ctx->dev_redo_workspace[0], &ctx->dev_redo_workspace[1]};
     for (DevBuf* b : bufs) b->release();
     if (ctx->events_ok) {
         for (int i = 0; i < kMaxChunks; ++i)

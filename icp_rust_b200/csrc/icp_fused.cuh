@@ -162,7 +162,46 @@ struct FusedParams {
     GuardBands guard;
     double* out_cost;           // [B] nullable: huber_error (lib.rs:45-50) of the last inner solve
     uint32_t shared_src;        // every pair aligns the scan src[0 .. src_off[1])
+    // Self-cleaning counters (device-pointer calls, which run back to back without a host memset):
+    // the last CTA to leave the launch zeroes work_counter and fin_counter; the re-run launch also
+    // moves *pair_count to *redo_seen and zeroes it.  Null: the host zeroes the counters per call.
+    uint32_t* fin_counter;
+    uint32_t* redo_seen;
 };
+
+// Entry of every ICP launch.  With programmatic dependent launch (ICP_B200_FLAG_INDEPENDENT) the
+// next call's CTAs fill the SMs this call's last pairs leave idle.  Two rules keep the library's
+// per-call state (two alternating sets of counters, workspaces and flagged-pair lists) safe:
+//  - the re-run launch reads the list its main launch wrote, so all of it waits for that launch;
+//  - CTA 0 of a main launch waits for the previous call to complete BEFORE it releases its own
+//    dependents, so the call after this one cannot start while the call before it still runs.
+ICP_DEV void fused_launch_entry(const FusedParams& p)
+{
+    if (p.pair_list) {
+        icp_pdl_launch_dependents();
+        icp_pdl_wait();
+    } else {
+        if (blockIdx.x == 0) icp_pdl_wait();
+        icp_pdl_launch_dependents();
+    }
+}
+
+// Exit of every ICP launch (thread 0 of each CTA, after its last pair).
+ICP_DEV void fused_launch_exit(const FusedParams& p)
+{
+    if (!p.fin_counter) return;
+    __threadfence();
+    if (atomicAdd(p.fin_counter, 1u) + 1u == gridDim.x) {
+        *p.work_counter = 0u;
+        *p.fin_counter = 0u;
+        if (p.pair_list) {
+            uint32_t* count = const_cast<uint32_t*>(p.pair_count);
+            *p.redo_seen = *count;
+            *count = 0u;
+        }
+        __threadfence();
+    }
+}
 
 // Next pair of this launch (thread 0 only): a contiguous range, or the flagged-pair list.
 // Returns a value >= p.pair_end when the work is exhausted.
@@ -606,6 +645,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
 
     for (int q = tid; q < 2 * kSelHistPad; q += THREADS) (&sel->hist[0][0])[q] = 0u;
     int hist_par = 0;
+    fused_launch_entry(p);
     __syncthreads();
 
     for (;;) {
@@ -957,6 +997,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
         }
         __syncthreads();  // ctl->pair is rewritten at the top of the loop
     }
+    if (tid == 0) fused_launch_exit(p);
 }
 
 }  // namespace icp

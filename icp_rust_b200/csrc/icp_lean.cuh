@@ -547,6 +547,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
 
     lean_zero_lh<THREADS>(sel->lh[0]);
     lean_zero_lh<THREADS>(sel->lh[1]);
+    fused_launch_entry(p);
     __syncthreads();
     ICP_LT_DECL
 
@@ -860,6 +861,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
         ++lt_n;
 #endif
     }
+    if (tid == 0) fused_launch_exit(p);
 #ifdef ICP_LEAN_TIMING
     if (blockIdx.x == 0 && tid == 0 && lt_n > 0)
         printf("lean timing CTA0: pairs %lld evals %lld | cycles/pair: setup+build %lld search %lld tail %lld | cycles/eval: stage0 %lld serve0 %lld stage1 %lld serve1 %lld accumulate %lld reduce+solve %lld\n",

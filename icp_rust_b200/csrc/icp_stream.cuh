@@ -227,6 +227,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
 
     for (int q = tid; q < 2 * kSelHistPad; q += THREADS) (&sel->hist[0][0])[q] = 0u;
     int hist_par = 0;
+    fused_launch_entry(p);
     __syncthreads();
     ICP_ST_DECL
 
@@ -613,6 +614,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
         }
         __syncthreads();
     }
+    if (tid == 0) fused_launch_exit(p);
 #ifdef ICP_STREAM_TIMING
     if (blockIdx.x == 0 && tid == 0 && st_pairs > 0)
         printf("stream timing CTA0: pairs %lld evals %lld | cycles/pair: setup+build %lld seeds %lld search %lld selection %lld accumulate+solve %lld other %lld\n",

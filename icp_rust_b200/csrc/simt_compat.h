@@ -41,6 +41,12 @@ static __device__ __forceinline__ void icp_bar_arrive(int id, int count)
 {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
+// Programmatic dependent launch (griddepcontrol): `launch_dependents` lets the next kernel of the
+// stream start filling SM resources this grid's CTAs release; `wait` blocks the calling thread until
+// the grids this launch depends on have completed and their writes are visible.  Both are no-ops in
+// a launch without the programmatic-serialization attribute.
+static __device__ __forceinline__ void icp_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+static __device__ __forceinline__ void icp_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
 
 #define ICP_FULL_MASK 0xffffffffu

@@ -21,6 +21,7 @@ pub const ICP_B200_CORR_ALL: i32 = 2;
 pub const ICP_B200_FLAG_ORDERED_SUMS: u32 = 1;
 pub const ICP_B200_FLAG_SHARED_SOURCE: u32 = 2;
 pub const ICP_B200_FLAG_NO_GUARD: u32 = 4;
+pub const ICP_B200_FLAG_INDEPENDENT: u32 = 8;
 
 /// icp_b200_batch (include/icp_b200.h): B independent `IcpD::new(dst_b).estimate(src_b, init_b, max_iter)`.
 #[repr(C)]

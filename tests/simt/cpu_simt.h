@@ -207,6 +207,11 @@ static inline void icp_bar_sync(int id, int count)
     else while (b.gen == g) simt::yield();
 }
 
+// programmatic dependent launch: the emulator runs one launch at a time
+static inline void icp_pdl_launch_dependents() {}
+static inline void icp_pdl_wait() {}
+static inline void __threadfence() {}
+
 static inline uint32_t __shfl_sync(unsigned, uint32_t v, int src) { return simt::warp_exchange(v)[src & 31]; }
 static inline int __shfl_sync(unsigned m, int v, int src) { return (int)__shfl_sync(m, (uint32_t)v, src); }
 static inline uint32_t __shfl_xor_sync(unsigned, uint32_t v, int mask)

@@ -108,15 +108,21 @@ extern "C" int simt_icp_fused(int dim, int variant, unsigned grid, const double*
             else { r.ncap = 128; run_fused<32, 4, 3>(r, grid, mode); }
         }
     };
+    // self-cleaning counters (device-pointer calls of the library): the last CTA zeroes them
+    uint32_t fin = 0, fin2 = 0, seen = 0;
+    p.fin_counter = &fin;
     run(p, ordered);
+    if (counter != 0 || fin != 0) return -98;
     g_last_redo = 0;
     if (guard) {   // the ordered re-run of the flagged pairs (icp_b200.cu launch_range)
         FusedParams r = p;
         r.pair_list = redo_list.data(); r.pair_count = &redo_count;
         r.redo_list = nullptr; r.redo_count = nullptr; r.guard = GuardBands{0., 0., 0.};
         r.work_counter = &counter2;
+        r.fin_counter = &fin2; r.redo_seen = &seen;
         run(r, 1);
-        g_last_redo = redo_count;
+        if (counter2 != 0 || fin2 != 0 || redo_count != 0) return -98;
+        g_last_redo = seen;
     }
     return err;
 }

@@ -621,3 +621,72 @@ def test_target_update_matches_fresh_build(ctx, icp):
     assert np.array_equal(t3.search(q3), oracle.nn_search(p3[:700] * 0.5, q3, oracle.NN_BRUTE))
     t3.close()
     t.close()
+
+
+@pytest.mark.parametrize("forced_reruns", [False, True])
+def test_device_pointer_calls_back_to_back(icp, forced_reruns):
+    """icp_b200_estimate_batch_device, asynchronous, with ICP_B200_FLAG_INDEPENDENT: calls of very
+    different sizes queued on one stream without anything between them (each may start while the
+    one before it drains) give, bit for bit, what the same batches give one at a time through the
+    host-pointer entry; with the guard bands forced wide every pair also goes through the re-run
+    launch of its call while the next call is already resident.  The library's per-call state
+    (two parities of counters, workspaces and flagged-pair lists) is reused every other call."""
+    import torch
+    sizes = [600, 37, 1, 900, 5, 444, 2, 148]
+    total = sum(sizes)
+    src, dst, off, _ = icp.synth_scan_pairs(total, beams=1080, first_pair=740000)
+    if forced_reruns:
+        os.environ["ICP_B200_GUARD_SCALE"] = "1e9"
+    try:
+        c = icp.Context(0)
+    finally:
+        os.environ.pop("ICP_B200_GUARD_SCALE", None)
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.Stream(device=dev)
+    want, bufs, first = [], [], 0
+    for n in sizes:
+        s = src[first * 1080:(first + n) * 1080]
+        d = dst[first * 1080:(first + n) * 1080]
+        o = (off[first:first + n + 1] - off[first]).astype(np.uint32)
+        T0 = np.tile(I6, (n, 1))
+        want.append(c.estimate_batch(s, o, d, o, T0, 20))
+        if forced_reruns:
+            assert want[-1]["redo_pairs"] == n
+        bufs.append(dict(src=torch.from_numpy(s.copy()).to(dev), dst=torch.from_numpy(d.copy()).to(dev),
+                         off=torch.from_numpy(o.astype(np.int32)).to(dev), T0=torch.from_numpy(T0).to(dev),
+                         out=torch.zeros((n, 6), dtype=torch.float64, device=dev),
+                         inner=torch.zeros((n, 20), dtype=torch.int32, device=dev),
+                         hash=torch.zeros(n, dtype=torch.int64, device=dev),
+                         status=torch.full((n,), -1, dtype=torch.int32, device=dev)))
+        first += n
+    torch.cuda.synchronize()
+
+    def enqueue(k, flags, synchronize=False):
+        b = bufs[k]
+        c.estimate_batch_device(dict(src=b["src"].data_ptr(), src_off=b["off"].data_ptr(), dst=b["dst"].data_ptr(),
+                                     dst_off=b["off"].data_ptr(), init_T=b["T0"].data_ptr(), out_T=b["out"].data_ptr(),
+                                     out_inner=b["inner"].data_ptr(), out_corr_hash=b["hash"].data_ptr(),
+                                     out_status=b["status"].data_ptr()),
+                                sizes[k], 20, dim=2, max_src=1080, max_dst=1080, stream=stream.cuda_stream,
+                                synchronize=synchronize, flags=flags)
+
+    for rounds, flags in ((3, icp.FLAG_INDEPENDENT), (1, 0)):
+        for b in bufs:
+            b["out"].zero_()
+            b["status"].fill_(-1)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            for _ in range(rounds):
+                for k in range(len(sizes)):
+                    enqueue(k, flags)
+        torch.cuda.synchronize()
+        for k, b in enumerate(bufs):
+            assert np.array_equal(b["out"].cpu().numpy(), want[k]["T"]), f"call {k} ({sizes[k]} pairs), flags {flags}"
+            assert np.array_equal(b["inner"].cpu().numpy().astype(np.uint32), want[k]["inner"])
+            assert np.array_equal(b["hash"].cpu().numpy().astype(np.uint64), want[k]["corr_hash"])
+            assert int(b["status"].abs().sum().item()) == 0
+    # a synchronous call after the asynchronous ones reports its own re-run count
+    enqueue(3, 0, synchronize=True)
+    info = c.call_info()
+    assert info["redo_pairs"] == (sizes[3] if forced_reruns else want[3]["redo_pairs"])
+    c.close()
