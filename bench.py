@@ -249,9 +249,9 @@ def run_gpu(args, rank, local_rank, world):
     # leave idle.  --no-overlap times the steps strictly one after the other.
     step_flags = 0 if args.no_overlap else icp.FLAG_INDEPENDENT
 
-    def dev_step(j, ordered=args.ordered, flags=None):
+    def dev_step(j, ordered=args.ordered, flags=None, c=None):
         d = devb[j % NBUF]
-        ctx.estimate_batch_device(dict(src=d["src"].data_ptr(), src_off=d["off"].data_ptr(), dst=d["dst"].data_ptr(),
+        (c or ctx).estimate_batch_device(dict(src=d["src"].data_ptr(), src_off=d["off"].data_ptr(), dst=d["dst"].data_ptr(),
                                        dst_off=d["off"].data_ptr(), init_T=d["T0"].data_ptr(), out_T=d["out"].data_ptr(),
                                        out_status=d["status"].data_ptr()),
                                   B, MAX_ITER, dim=2, max_src=BEAMS, max_dst=BEAMS, stream=stream.cuda_stream,
@@ -333,6 +333,36 @@ def run_gpu(args, rank, local_rank, world):
         other = {"flag": "ICP_B200_FLAG_ORDERED_SUMS", "value": world * B * K2 / (oms * 1e-3), "unit": UNIT,
                  "ms_per_step": oms / K2, "max_abs_transform_difference_to_default_mode": dmax}
 
+    # ---- the same steps with EVERY outer iteration computed (ICP_B200_FIXED_POINT=0).  By default the
+    # kernels write, rather than recompute, outer iterations that provably repeat (an inner solve that
+    # accepted no update leaves the transform where it was: icp_fused.cuh fused_repeats); outputs are
+    # bit-identical either way.  Reported beside the headline so the two can be told apart.
+    os.environ["ICP_B200_FIXED_POINT"] = "0"
+    try:
+        ctx_full = icp.Context(local_rank)
+    finally:
+        os.environ.pop("ICP_B200_FIXED_POINT")
+    K3 = max(2, K // 2)
+    for j in range(NBUF):
+        dev_step(j, c=ctx_full)
+    torch.cuda.synchronize()
+    full_same = all(bool(torch.equal(devb[j]["out"], dev_out[j])) for j in range(NBUF)) if not args.ordered else None
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for j in range(K3):
+        dev_step(j, c=ctx_full)
+    f1.record(stream)
+    torch.cuda.synchronize()
+    fms = max_over_ranks(f0.elapsed_time(f1))
+    fixed_point = {"env": "ICP_B200_FIXED_POINT", "default": 1,
+                   "every_iteration_computed": {"value": world * B * K3 / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms / K3,
+                                                "bit_identical_transforms": full_same},
+                   "note": "outer iterations after the first one whose inner solve accepts no update are exact repeats "
+                           "(same transform, same correspondences, same solve); the default writes their outputs instead of "
+                           "recomputing them.  Config 2's pairs rarely stop moving within 20 iterations; the bundled "
+                           "3-D frames (config 4) stop after about six."}
+
     # ---- end to end through the host-pointer C-ABI call
     for j in range(NBUF):
         host_step(j)
@@ -376,7 +406,7 @@ def run_gpu(args, rank, local_rank, world):
         except Exception as e:  # pragma: no cover
             c3 = {"error": repr(e)}
         try:
-            c4 = bench_config4(icp, ctx)
+            c4 = bench_config4(icp, ctx, ctx_full=ctx_full)
         except Exception as e:  # pragma: no cover
             c4 = {"error": repr(e)}
 
@@ -408,6 +438,7 @@ def run_gpu(args, rank, local_rank, world):
                     "d2h_bytes_per_step": int(hinfo["d2h_bytes"]), "ms_per_step": e2e_s / K * 1e3,
                     "bit_identical_to_device_path": same},
             "gpu_launches": int(launches),
+            "fixed_point_exit": fixed_point,
             "step_overlap": {"flag": None if args.no_overlap else "ICP_B200_FLAG_INDEPENDENT",
                              "steps_one_after_the_other": {"value": serial_value, "unit": UNIT, "ms_per_step": launch_ms,
                                                            "ms_min_max": [min(each_ms), max(each_ms)]},
@@ -518,7 +549,7 @@ def bench_config3(icp, ctx, scans_n=65536):
             "redo_pairs": int(g["redo_pairs"])}
 
 
-def bench_config4(icp, ctx, pairs=1024, check=16):
+def bench_config4(icp, ctx, pairs=1024, check=16, ctx_full=None):
     """BASELINE config 4: 1024 pairs (frame i, frame i+1 mod 20) of the bundled 3-D recording x 16,384
     points, seeded initial perturbation, 20 iterations (icp_rust_b200/workloads.py); host buffers
     through icp_b200_estimate_batch.  NN queries/s counts the 20 x 16,384 searches of every pair;
@@ -537,12 +568,22 @@ def bench_config4(icp, ctx, pairs=1024, check=16):
     o = oracle.icp_estimate_batch(3, src[:n * CONFIG4_POINTS], off[:n + 1], dst[:n * CONFIG4_POINTS], off[:n + 1], T0[:n],
                                   MAX_ITER, nn_mode=oracle.NN_KDTREE)
     peak, peak_src = measured_peaks()
-    queries = pairs * CONFIG4_POINTS * MAX_ITER
+    outer = computed_outer_iterations(g["inner"])
+    queries = int(outer.sum()) * CONFIG4_POINTS      # searches the kernel ran (copies of a fixed point run none)
     achieved = 28.0 * queries / (best[1] * 1e-3) / 1e9
+    full = None
+    if ctx_full is not None:   # the same call with every outer iteration computed (ICP_B200_FIXED_POINT=0)
+        gf = ctx_full.estimate_batch(src, off, dst, off, T0, MAX_ITER, dim=3)
+        kf = ctx_full.call_info()["kernel_ms"]
+        full = {"value": pairs / (kf * 1e-3), "unit": "pairs/s", "kernel_ms": kf,
+                "nn_queries_per_s": pairs * CONFIG4_POINTS * MAX_ITER / (kf * 1e-3),
+                "bit_identical_outputs": bool(np.array_equal(gf["T"], g["T"]) and np.array_equal(gf["inner"], g["inner"])
+                                              and np.array_equal(gf["corr_hash"], g["corr_hash"]))}
     return {"workload": f"config4: {pairs} pairs (frame i, frame i+1 mod 20) x {CONFIG4_POINTS} 3-D points, {MAX_ITER} outer iterations",
             "value": pairs / (best[1] * 1e-3), "unit": "pairs/s", "kernel_ms": best[1], "host_call_pairs_per_s": pairs / best[0],
             "nn_queries_per_s": queries / (best[1] * 1e-3), "kernel": f"icp_stream_kernel<{info['block_threads']} threads>",
             "grid": info["grid_ctas"], "status_ok": bool((g["status"] == 0).all()), "redo_pairs": int(g["redo_pairs"]),
+            "outer_iterations_computed_per_pair": float(outer.mean()), "every_iteration_computed": full,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": None,
                          "note": "28 B per 3-D query (SURVEY.md 8(d)) over the whole loop's device time: an upper-bound "
@@ -605,7 +646,16 @@ FP64_FLOPS_PER_POINT_STEP = 15      # huber_error per accepted step
 FP64_FLOPS_PER_POINT_OUTER = 8 + 6 * 6   # transform + ~6 exact candidate distances of the seeded search
 
 
-def fp64_roofline(icp, ctx, h, B, launch_ms, sample=256):
+def computed_outer_iterations(inner):
+    """Outer iterations a pair actually computes with the fixed-point exit (icp_fused.cuh
+    fused_repeats): up to and including the first one whose inner solve accepted no update; the
+    ones after it are written as copies.  `inner`: (B, max_iter) words accepted | reason << 16."""
+    idle = (np.asarray(inner) & 0xffff) == 0
+    first = np.where(idle.any(axis=1), idle.argmax(axis=1) + 1, idle.shape[1])
+    return first.astype(np.int64)
+
+
+def fp64_roofline(icp, ctx, h, B, launch_ms, sample=256, fixed_point=True):
     """Secondary roofline of the fused kernel: algorithmic FP64 flops against the FP64
     rate measured on this pool's B200s for the reference's arithmetic (separate multiply and add, no
     FMA: tools/fp64/fp64_peak.cu -> profiles/r01_fp64_peak.json).  Evaluations per pair are counted
@@ -619,15 +669,20 @@ def fp64_roofline(icp, ctx, h, B, launch_ms, sample=256):
                                MAX_ITER, want_inner=True, want_hash=False)
         acc = (g["inner"] & 0xffff).astype(np.int64)
         why = (g["inner"] >> 16).astype(np.int64)
-        evals = float((acc + (why != icp.BREAK_CAP)).sum(axis=1).mean())
-        steps = float(acc.sum(axis=1).mean())
+        # only what the kernel computes counts: outer iterations written as copies of a fixed point
+        # (one evaluation each in the reference) are left out
+        outer = computed_outer_iterations(g["inner"]) if fixed_point else np.full(n, MAX_ITER)
+        live = np.arange(MAX_ITER)[None, :] < outer[:, None]
+        evals = float(((acc + (why != icp.BREAK_CAP)) * live).sum(axis=1).mean())
+        steps = float((acc * live).sum(axis=1).mean())
         flops_pair = BEAMS * (evals * FP64_FLOPS_PER_POINT_EVAL + steps * FP64_FLOPS_PER_POINT_STEP
-                              + MAX_ITER * FP64_FLOPS_PER_POINT_OUTER)
+                              + float(outer.mean()) * FP64_FLOPS_PER_POINT_OUTER)
         tf = flops_pair * B / (launch_ms * 1e-3) / 1e12
         return {"achieved": tf, "peak": pk["fp64_dmul_dadd_tflops"], "unit": "TFLOP/s", "frac": tf / pk["fp64_dmul_dadd_tflops"],
                 "peak_source": "BUILDER-measured (tools/fp64/fp64_peak.cu on this pool's B200, not in MEASURED_PEAKS.json), "
                                "separate DMUL+DADD: profiles/r01_fp64_peak.json; DFMA: %.1f" % pk["fp64_dfma_tflops"],
-                "gn_evaluations_per_pair": evals, "algorithmic_flops_per_pair": flops_pair,
+                "gn_evaluations_per_pair": evals, "outer_iterations_computed_per_pair": float(outer.mean()),
+                "algorithmic_flops_per_pair": flops_pair,
                 "note": "algorithmic flops exclude the exact selections, sqrt/div expansions and index work"}
     except Exception as e:  # pragma: no cover
         return {"error": repr(e)}

@@ -90,6 +90,7 @@ struct icp_b200_context {
     uint64_t dev_calls = 0;
     bool dev_dirty = true;  // the counters need a memset (first call, or a call that failed midway)
     int pdl = 1;            // ICP_B200_PDL=0: never overlap calls (ICP_B200_FLAG_INDEPENDENT is ignored)
+    int fixed_point = 1;    // ICP_B200_FIXED_POINT=0: compute every outer iteration, also the ones that provably repeat
     int guard = 1;          // ICP_B200_GUARD=0: no knife-edge guard (as ICP_B200_FLAG_NO_GUARD on every call)
     double guard_scale = 1.0;   // ICP_B200_GUARD_SCALE: multiplies the guard bands (tests force re-runs with it)
     DevBuf stats_in, stats_off, stats_out;
@@ -259,6 +260,7 @@ void fill_params(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_
     p.out_T = b.out_T; p.out_inner = b.out_inner; p.out_corr = b.out_corr; p.out_hash = b.out_corr_hash;
     p.out_status = b.out_status; p.out_cost = b.out_cost;
     p.shared_src = (b.flags & ICP_B200_FLAG_SHARED_SOURCE) ? 1u : 0u;
+    p.fixed_point = ctx->fixed_point ? 1u : 0u;
     p.out_error = ctx->counters.as<int32_t>() + kCtrErr;
     p.max_iter = b.max_iter; p.corr_mode = b.corr_mode;
     p.cell_budget = ctx->cell_budget;
@@ -728,6 +730,7 @@ int icp_b200_create(int device, icp_b200_context** out)
     ctx->use_lean = env_int("ICP_B200_LEAN", 1);
     ctx->guard = env_int("ICP_B200_GUARD", 1);
     ctx->pdl = env_int("ICP_B200_PDL", 1);
+    ctx->fixed_point = env_int("ICP_B200_FIXED_POINT", 1);
     if (const char* gs = getenv("ICP_B200_GUARD_SCALE")) ctx->guard_scale = std::max(0.0, atof(gs));
     *out = ctx;
     return ICP_B200_OK;

@@ -65,6 +65,7 @@ struct FusedCtl {
     uint32_t knife;       // tree mode: a decision of this pair fell inside a guard band (GuardBands)
     double T6[6];         // lean schedule: the outer transform (kept out of the threads' registers)
     uint64_t H;           // lean schedule: running correspondence checksum
+    uint64_t Hlast;       // lean schedule: the last outer iteration's term of the checksum
     uint32_t heavy_n;     // streaming kernel: source points left to a whole warp's search
 };
 
@@ -167,7 +168,47 @@ struct FusedParams {
     // moves *pair_count to *redo_seen and zeroes it.  Null: the host zeroes the counters per call.
     uint32_t* fin_counter;
     uint32_t* redo_seen;
+    uint32_t fixed_point;       // 1: outer iterations that provably repeat are written, not recomputed (below)
 };
+
+// Fixed point of the outer loop (exact, not a convergence test).  An inner solve that accepts no
+// update (lib.rs:67-77 breaks in its first pass) returns the identity, so lib.rs:127 leaves the
+// outer transform as it was: the next outer iteration transforms the scan to the same points,
+// finds the same correspondences, runs the same inner solve and ends the same way — and so does
+// every iteration after it.  The reference has no exit and computes them all (lib.rs:112-128);
+// the kernels write what they would produce — the same correspondences and inner-iteration word
+// per remaining iteration, the checksum advanced once per iteration — and go to the next pair.
+// `transform_mul(identity, T)` is still applied once, as the reference does (it turns a -0.0 of a
+// caller's initial transform into +0.0; a second application changes nothing).
+// ICP_B200_FIXED_POINT=0 computes every iteration.
+ICP_DEV bool fused_repeats(const FusedParams& p, uint32_t accepted, uint32_t it)
+{
+    return p.fixed_point != 0u && accepted == 0u && it + 1u < p.max_iter;
+}
+
+// Outputs of outer iterations it+1 .. max_iter-1, copies of iteration `it` (whole CTA; the
+// correspondences of iteration `it` were written before a barrier this call sits behind).
+template <int THREADS>
+ICP_DEV void fused_repeat_outputs(const FusedParams& p, uint32_t pair, uint32_t it, int n, uint64_t corr_base, uint32_t word)
+{
+    const int tid = (int)threadIdx.x;
+    if (p.out_corr && p.corr_mode == 2) {
+        const int32_t* from = p.out_corr + corr_base + (uint64_t)it * (uint64_t)n;
+        for (uint32_t j = it + 1u; j < p.max_iter; ++j) {
+            int32_t* to = p.out_corr + corr_base + (uint64_t)j * (uint64_t)n;
+            for (int i = tid; i < n; i += THREADS) to[i] = from[i];
+        }
+    }
+    if (tid == 0 && p.out_inner)
+        for (uint32_t j = it + 1u; j < p.max_iter; ++j) p.out_inner[(size_t)pair * p.max_iter + j] = word;
+}
+
+// The checksum after `times` more iterations that each contribute the term h.
+ICP_DEV uint64_t fused_repeat_hash(uint64_t H, uint64_t h, uint32_t times)
+{
+    for (uint32_t j = 0; j < times; ++j) H = H * 0x100000001B3ull + h;
+    return H;
+}
 
 // Entry of every ICP launch.  With programmatic dependent launch (ICP_B200_FLAG_INDEPENDENT) the
 // next call's CTAs fill the SMs this call's last pairs leave idle.  Two rules keep the library's
@@ -756,7 +797,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                 hpart += mix64(((uint64_t)(uint32_t)i << 32) | (uint64_t)(uint32_t)idx);
                 if (p.out_corr) {
                     if (p.corr_mode == 2) p.out_corr[corr_base + (uint64_t)it * (uint64_t)n + (uint64_t)i] = idx;
-                    else if (p.corr_mode == 1 && it + 1 == p.max_iter) p.out_corr[corr_base + (uint64_t)i] = idx;
+                    // (with the fixed-point exit any iteration can be the last one computed: write each)
+                    else if (p.corr_mode == 1 && (it + 1 == p.max_iter || p.fixed_point)) p.out_corr[corr_base + (uint64_t)i] = idx;
                 }
             };
             if (ORDERED) {
@@ -803,10 +845,10 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
             hpart = warp_sum_u64(hpart);
             if (lane == 0) ctl->hash_part[warp] = hpart;
             __syncthreads();  // search done (ordered: the union region becomes the IRLS row arrays)
+            uint64_t hterm = 0;
             if (tid == 0) {
-                uint64_t h = 0;
-                for (int w = 0; w < NW; ++w) h += ctl->hash_part[w];
-                H = H * 0x100000001B3ull + h;
+                for (int w = 0; w < NW; ++w) hterm += ctl->hash_part[w];
+                H = H * 0x100000001B3ull + hterm;
             }
 
 // @region irls_setup
@@ -943,7 +985,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
                 }
             }
 // @region outer_tail
-            if (p.out_cost && it + 1 == p.max_iter) {
+            const bool repeats = fused_repeats(p, accepted, it);
+            if (p.out_cost && (it + 1 == p.max_iter || repeats)) {
                 // huber_error (lib.rs:45-50) of the inner solve's final transform over this (the last)
                 // iteration's transformed source / matched target points
                 __syncthreads();   // every thread has read the last solve's sums / broadcast
@@ -984,7 +1027,12 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_fused_kernel(FusedParams p)
             }
             T = transform_mul(Ti, T);  // lib.rs:127
             if (tid == 0 && p.out_inner) p.out_inner[(size_t)pair * p.max_iter + it] = accepted | (why << 16);
+            if (repeats) {
+                fused_repeat_outputs<THREADS>(p, pair, it, n, corr_base, accepted | (why << 16));
+                if (tid == 0) H = fused_repeat_hash(H, hterm, p.max_iter - 1u - it);
+            }
             __syncthreads();  // rows are dead; next iteration restages the target
+            if (repeats) break;
         }
         if (tid == 0) {
             p.out_T[(size_t)pair * 6 + 0] = T.r00; p.out_T[(size_t)pair * 6 + 1] = T.r01;

@@ -666,7 +666,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                 hpart += mix64(((uint64_t)(uint32_t)i << 32) | (uint64_t)(uint32_t)idx);
                 if (p.out_corr) {
                     if (p.corr_mode == 2) p.out_corr[corr_base + (uint64_t)it * (uint64_t)n + (uint64_t)i] = idx;
-                    else if (p.corr_mode == 1 && it + 1 == p.max_iter) p.out_corr[corr_base + (uint64_t)i] = idx;
+                    else if (p.corr_mode == 1 && (it + 1 == p.max_iter || p.fixed_point)) p.out_corr[corr_base + (uint64_t)i] = idx;
                 }
             }
             hpart = warp_sum_u64(hpart);
@@ -676,6 +676,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                 uint64_t h = 0;
                 for (int w = 0; w < NW; ++w) h += ctl->hash_part[w];
                 ctl->H = ctl->H * 0x100000001B3ull + h;
+                ctl->Hlast = h;
             }
             // the transformed source points of the thread's own slots (the search walked the scan with
             // every thread; the rows below belong to the workers)
@@ -818,7 +819,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                 }
             }
 // @region lean_outer_tail
-            if (p.out_cost && it + 1 == p.max_iter) {
+            const bool repeats = fused_repeats(p, accepted, it);   // icp_fused.cuh: the remaining iterations are copies
+            if (p.out_cost && (it + 1 == p.max_iter || repeats)) {
                 // huber_error (lib.rs:45-50) of the inner solve's final transform over this (the last)
                 // iteration's transformed source / matched target points
                 __syncthreads();   // every thread has read the last solve's broadcast
@@ -844,8 +846,11 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                 T = transform_mul(Ti, T);
                 ctl->T6[0] = T.r00; ctl->T6[1] = T.r01; ctl->T6[2] = T.r10; ctl->T6[3] = T.r11; ctl->T6[4] = T.tx; ctl->T6[5] = T.ty;
                 if (p.out_inner) p.out_inner[(size_t)pair * p.max_iter + it] = accepted | (why << 16);
+                if (repeats) ctl->H = fused_repeat_hash(ctl->H, ctl->Hlast, p.max_iter - 1u - it);
             }
+            if (repeats) fused_repeat_outputs<THREADS>(p, pair, it, n, corr_base, accepted | (why << 16));
             __syncthreads();  // rows are rewritten by the next search; ctl->bcast by the next solve; T6 is read
+            if (repeats) break;
         }
         if (tid == 0) {
 #pragma unroll

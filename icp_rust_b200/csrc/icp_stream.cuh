@@ -385,7 +385,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
                     hpart += mix64(((uint64_t)(uint32_t)i << 32) | (uint64_t)(uint32_t)r.idx);
                     if (p.out_corr) {
                         if (p.corr_mode == 2) p.out_corr[corr_base + (uint64_t)it * (uint64_t)n + (uint64_t)i] = r.idx;
-                        else if (p.corr_mode == 1 && it + 1 == p.max_iter) p.out_corr[corr_base + (uint64_t)i] = r.idx;
+                        else if (p.corr_mode == 1 && (it + 1 == p.max_iter || p.fixed_point)) p.out_corr[corr_base + (uint64_t)i] = r.idx;
                     }
                 };
                 // (visiting the points in the order of their own cell's occupancy, to even out the lanes of a
@@ -475,7 +475,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
                         hpart += mix64(((uint64_t)(uint32_t)i << 32) | (uint64_t)(uint32_t)r.idx);
                         if (p.out_corr) {
                             if (p.corr_mode == 2) p.out_corr[corr_base + (uint64_t)it * (uint64_t)n + (uint64_t)i] = r.idx;
-                            else if (p.corr_mode == 1 && it + 1 == p.max_iter) p.out_corr[corr_base + (uint64_t)i] = r.idx;
+                            else if (p.corr_mode == 1 && (it + 1 == p.max_iter || p.fixed_point)) p.out_corr[corr_base + (uint64_t)i] = r.idx;
                         }
                     }
                     __syncwarp();
@@ -485,10 +485,10 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
             if (lane == 0) ctl->hash_part[warp] = hpart;
             __syncthreads();   // state of every point is visible to the whole CTA
             ICP_ST_MARK(2)
+            uint64_t hterm = 0;
             if (tid == 0) {
-                uint64_t h = 0;
-                for (int w = 0; w < NW; ++w) h += ctl->hash_part[w];
-                H = H * 0x100000001B3ull + h;
+                for (int w = 0; w < NW; ++w) hterm += ctl->hash_part[w];
+                H = H * 0x100000001B3ull + hterm;
             }
 
             // ---- estimate_transform (lib.rs:59-84)
@@ -571,7 +571,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
                     ++accepted;
                 }
             }
-            if (p.out_cost && it + 1 == p.max_iter) {
+            const bool repeats = fused_repeats(p, accepted, it);   // icp_fused.cuh: the remaining iterations are copies
+            if (p.out_cost && (it + 1 == p.max_iter || repeats)) {
                 // huber_error (lib.rs:45-50) of the inner solve's final transform over this (the last)
                 // iteration's transformed source / matched target points
                 __syncthreads();
@@ -601,7 +602,12 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
             }
             T = transform_mul(Ti, T);  // lib.rs:127
             if (tid == 0 && p.out_inner) p.out_inner[(size_t)pair * p.max_iter + it] = accepted | (why << 16);
+            if (repeats) {
+                fused_repeat_outputs<THREADS>(p, pair, it, n, corr_base, accepted | (why << 16));
+                if (tid == 0) H = fused_repeat_hash(H, hterm, p.max_iter - 1u - it);
+            }
             __syncthreads();
+            if (repeats) break;
         }
         if (tid == 0) {
             p.out_T[(size_t)pair * 6 + 0] = T.r00; p.out_T[(size_t)pair * 6 + 1] = T.r01;

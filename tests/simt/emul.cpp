@@ -47,7 +47,8 @@ extern "C" int simt_set_schedule(int mode)
 // streaming kernel; shared_src: ICP_B200_FLAG_SHARED_SOURCE.
 static double g_guard_scale = 0.0, g_band_delta_scale = 1.0;
 static double* g_out_cost = nullptr;
-static int g_stream_ordered = 0, g_shared_src = 0, g_stream_nn_group = 0;
+static int g_stream_ordered = 0, g_shared_src = 0, g_stream_nn_group = 0, g_fixed_point = 1;
+extern "C" void simt_set_fixed_point(int on) { g_fixed_point = on; }
 extern "C" void simt_set_stream_nn_group(int v) { g_stream_nn_group = v; }
 static uint32_t g_last_redo = 0;
 extern "C" void simt_set_options(double guard_scale, double* out_cost, int stream_ordered, int shared_src,
@@ -83,7 +84,7 @@ extern "C" int simt_icp_fused(int dim, int variant, unsigned grid, const double*
     p.out_status = out_status; p.out_error = &err; p.work_counter = &counter;
     p.pair_begin = 0; p.pair_end = B; p.max_iter = max_iter; p.corr_mode = corr_mode;
     p.cell_budget = cell_budget; p.mcap = mcap; p.sm_count = 1;
-    p.out_cost = g_out_cost; p.shared_src = (uint32_t)g_shared_src;
+    p.out_cost = g_out_cost; p.shared_src = (uint32_t)g_shared_src; p.fixed_point = (uint32_t)g_fixed_point;
     const FusedLayout L = fused_layout(dim, 256 * 6, mcap, cell_budget, false, true);
     std::vector<unsigned char> ws((size_t)grid * (L.nn_bytes + 64));
     p.workspace = ws.data();
@@ -155,7 +156,7 @@ extern "C" int simt_icp_stream(int dim, int threads, unsigned grid, const double
     p.out_status = out_status; p.out_error = &err; p.work_counter = &counter;
     p.pair_begin = 0; p.pair_end = B; p.max_iter = max_iter; p.corr_mode = corr_mode; p.sm_count = 1;
     sp.n_cap = ncap; sp.m_cap = mcap; sp.c_cap = std::max(64u, 2u * mcap);
-    p.out_cost = g_out_cost; p.shared_src = (uint32_t)g_shared_src;
+    p.out_cost = g_out_cost; p.shared_src = (uint32_t)g_shared_src; p.fixed_point = (uint32_t)g_fixed_point;
     const StreamLayout L = stream_layout(dim, sp.n_cap, sp.m_cap, sp.c_cap, false, true);
     std::vector<unsigned char> ws((size_t)grid * L.total + 256, 0xCD);
     p.workspace = ws.data();

@@ -40,6 +40,11 @@ def set_options(guard_scale=0.0, want_cost=0, stream_ordered=False, shared_src=F
                            C.c_double(delta_band_scale))
 
 
+def set_fixed_point(on):
+    """Outer-loop fixed-point exit of the kernels (icp_fused.cuh fused_repeats): on by default."""
+    lib().simt_set_fixed_point(C.c_int(1 if on else 0))
+
+
 def set_stream_nn_group(on):
     """Streaming kernel's search: a group of lanes per query (True) or one thread per query."""
     lib().simt_set_stream_nn_group(C.c_int(1 if on else 0))

@@ -690,3 +690,48 @@ def test_device_pointer_calls_back_to_back(icp, forced_reruns):
     info = c.call_info()
     assert info["redo_pairs"] == (sizes[3] if forced_reruns else want[3]["redo_pairs"])
     c.close()
+
+
+def test_outer_fixed_point_exit_is_exact(icp, scans2d, frames3d_20):
+    """icp_fused.cuh fused_repeats: outer iterations that provably repeat (an inner solve accepted
+    no update, so the outer transform stays) are written, not recomputed.  A context that computes
+    every iteration (ICP_B200_FIXED_POINT=0) gives the same bits in every output — transforms,
+    inner-iteration words, correspondences of all 20 iterations, checksums, final costs — on the
+    bundled 2-D scans (lean and ordered kernels), the config-4 clouds (streaming kernel) and scans
+    against a shared map; and on all three the exit is actually taken."""
+    from icp_rust_b200.workloads import config4_pairs
+    os.environ["ICP_B200_FIXED_POINT"] = "0"
+    try:
+        full = icp.Context(0)
+    finally:
+        os.environ.pop("ICP_B200_FIXED_POINT")
+    fast = icp.Context(0)
+    idx = list(range(0, 120, 3))
+    s2, so = _cat([scans2d[k] for k in idx], 2)
+    d2, do = _cat([scans2d[k + 1] for k in idx], 2)
+    T2 = np.tile(I6, (len(idx), 1))
+    s3, d3, o3, T3 = config4_pairs(6, frames=frames3d_20)
+    m = icp.synth_map(20000, seed=7)
+    sm, om, Tm = icp.synth_map_scans(24, beams=360, seed=7)
+    keys = ("T", "inner", "corr", "corr_hash", "cost", "status")
+    maps = {fast: icp.Target(m, fast), full: icp.Target(m, full)}
+    taken = {}
+    for ordered in (False, True):
+        for name, call in (
+                ("2d", lambda c: c.estimate_batch(s2, so, d2, do, T2, 20, corr_mode=icp.CORR_ALL, want_cost=True, ordered=ordered)),
+                ("3d", lambda c: c.estimate_batch(s3, o3, d3, o3, T3, 20, dim=3, corr_mode=icp.CORR_ALL, want_cost=True, ordered=ordered)),
+                ("map", lambda c: maps[c].estimate_batch(sm, om, Tm, 20, corr_mode=icp.CORR_ALL, want_cost=True, ordered=ordered))):
+            a, b = call(fast), call(full)
+            for k in keys:
+                assert np.array_equal(a[k], b[k]), (name, ordered, k)
+            idle = (a["inner"] & 0xffff) == 0
+            taken[name] = float((idle[:, :-1].any(axis=1)).mean())
+    assert taken["2d"] > 0.5 and taken["3d"] > 0.5, taken
+    # correspondences of the LAST iteration only
+    a = fast.estimate_batch(s2, so, d2, do, T2, 20, corr_mode=icp.CORR_LAST)
+    b = full.estimate_batch(s2, so, d2, do, T2, 20, corr_mode=icp.CORR_LAST)
+    assert np.array_equal(a["corr"], b["corr"])
+    for t in maps.values():
+        t.close()
+    fast.close()
+    full.close()

@@ -514,3 +514,44 @@ def test_lean_dedicated_service_warps(scans2d):
         assert np.array_equal(E.last_cost(), [r["cost"] for r in crefs])
     finally:
         E.set_options()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_outer_fixed_point_exit(dim):
+    """icp_fused.cuh fused_repeats: an inner solve that accepts no update leaves the outer transform
+    unchanged, so every later outer iteration repeats it exactly; the kernels write those
+    iterations' outputs instead of recomputing them.  Every output (transform, inner-iteration
+    words, correspondences of ALL iterations or of the last one, checksum, final cost) equals the
+    run that computes every iteration (ICP_B200_FIXED_POINT=0) bit for bit, and the oracle's."""
+    srcs, dsts = _noisy_pairs(3, 80, 21, dim=dim)
+    srcs.append(srcs[0][:1]); dsts.append(dsts[0])       # n < 2: the first iteration already repeats
+    T0 = [I6] * 4
+    max_iter = 12
+    refs = _oracle_ref(srcs, dsts, T0, max_iter)
+    first_idle = [int(np.argmax((r["inner"] & 0xffff) == 0)) for r in refs]
+    assert all(((r["inner"] & 0xffff) == 0).any() for r in refs) and max(first_idle) < max_iter - 2, \
+        "the test data must reach the fixed point early"
+    runs = [("fused", dict(variant=0, grid=2, ordered=True)), ("fused", dict(variant=0, grid=2, ordered=False)),
+            ("fused", dict(variant=0, grid=2, ordered="lean")), ("fused", dict(variant=0, grid=2, ordered="svc")),
+            ("stream", dict(threads=64, grid=2))]
+    for kind, kw in runs:
+        fn = E.icp_fused if kind == "fused" else E.icp_stream
+        out = {}
+        for on in (True, False):
+            try:
+                E.set_fixed_point(on)
+                E.set_options(want_cost=4)
+                g = fn(srcs, dsts, T0, max_iter, **kw)
+                g["cost"] = E.last_cost().copy()
+                E.set_options(want_cost=4)
+                g["corr_last"] = fn(srcs, dsts, T0, max_iter, corr_mode=1, **kw)["corr"]
+            finally:
+                E.set_fixed_point(True)
+                E.set_options()
+            out[on] = g
+        for k in ("T", "inner", "corr", "corr_hash", "cost", "status", "corr_last"):
+            assert np.array_equal(out[True][k], out[False][k]), (kind, kw, k)
+        _compare(out[True], refs, srcs, max_iter, ordered=(kw.get("ordered") is True))
+        so = out[True]["src_off"]
+        for b, r in enumerate(refs):   # corr_mode LAST holds the last iteration's correspondences
+            assert np.array_equal(out[True]["corr_last"][int(so[b]):int(so[b + 1])], r["corr"][-1])
