@@ -99,8 +99,9 @@ struct icp_b200_context {
     int cell_budget = 4096;
     int force_instance = -1;
     int use_lean = 1;       // ICP_B200_LEAN=0: warp-tree batches on the icp_fused.cuh schedule instead of icp_lean.cuh
-    int stream_cells_per_point = 8;   // ICP_B200_STREAM_CELLS_PER_POINT: cell budget of the streaming kernel's per-pair grids
+    int stream_cells_per_point = 0;   // ICP_B200_STREAM_CELLS_PER_POINT: cell budget of the streaming kernel's per-pair grids (0: 8 in 2-D, 4 in 3-D)
     int single_ordered = 0;     // ICP_B200_SINGLE_ORDERED=1: the single-pair entries use ordered sums
+    int stream_nn_f32 = 1;      // ICP_B200_STREAM_NN_F32=0: the streaming kernel's 3-D searches rank every candidate in binary64
     int stream_nn_group = 0;    // ICP_B200_STREAM_NN_GROUP=1: a group of lanes per query in the streaming kernel's search
     int force_stream = 0;   // ICP_B200_FORCE_STREAM=1: route every warp-tree batch to the streaming kernel (tests)
 };
@@ -167,7 +168,7 @@ struct LaunchPlan {
     StreamKernel skernel = nullptr;
     StreamLayout slayout{};
     bool stream_ordered = false;
-    uint32_t n_cap = 0, m_cap = 0, c_cap = 0;
+    uint32_t n_cap = 0, m_cap = 0, c_cap = 0, cells_per_point = 8;
     int threads = 0;
     uint32_t smem = 0;
     uint64_t ws_stride = 0;
@@ -212,7 +213,10 @@ int plan_launch(icp_b200_context* ctx, uint32_t dim, bool shared_target, bool or
         plan->stream_ordered = ordered;
         plan->n_cap = std::max<uint32_t>(8u, (max_n + 7u) & ~7u);
         plan->m_cap = shared_target ? 0u : std::max<uint32_t>(8u, (max_m + 7u) & ~7u);
-        plan->c_cap = shared_target ? 0u : std::max<uint32_t>(64u, (uint32_t)ctx->stream_cells_per_point * plan->m_cap);
+        // cells per target point: measured on config 4 after the fixed-point exit (1024 pairs): 2 / 4 / 8 / 16
+        // cells -> 6.25k / 6.69k / 6.05k / 5.41k pairs/s
+        plan->cells_per_point = ctx->stream_cells_per_point > 0 ? (uint32_t)ctx->stream_cells_per_point : (dim == 3 ? 4u : 8u);
+        plan->c_cap = shared_target ? 0u : std::max<uint32_t>(64u, plan->cells_per_point * plan->m_cap);
         plan->slayout = stream_layout((int)dim, plan->n_cap, plan->m_cap, plan->c_cap, shared_target, ordered);
         plan->ws_stride = plan->slayout.total;
         plan->skernel = kStreamInstance.k[dim - 2][shared_target ? 1 : 0];
@@ -291,9 +295,10 @@ int launch_plan(icp_b200_context* ctx, const LaunchPlan& pl, const FusedParams& 
     if (pl.stream) {
         StreamParams sp{};
         sp.f = fp; sp.n_cap = pl.n_cap; sp.m_cap = pl.m_cap; sp.c_cap = pl.c_cap;
-        sp.cells_per_point = (uint32_t)ctx->stream_cells_per_point;
+        sp.cells_per_point = pl.cells_per_point;
         sp.ordered = pl.stream_ordered ? 1u : 0u;
         sp.nn_group = (uint32_t)ctx->stream_nn_group;
+        sp.nn_f32 = (uint32_t)ctx->stream_nn_f32;
         ICP_CUDA(ctx, cudaLaunchKernelEx(&cfg, pl.skernel, sp));
     } else {
         ICP_CUDA(ctx, cudaLaunchKernelEx(&cfg, pl.kernel, fp));
@@ -723,9 +728,10 @@ int icp_b200_create(int device, icp_b200_context** out)
     }
     ctx->cell_budget = std::max(16, std::min(65000, env_int("ICP_B200_CELL_BUDGET", 4096)));
     ctx->force_instance = env_int("ICP_B200_FORCE_INSTANCE", -1);
-    ctx->stream_cells_per_point = std::max(1, std::min(256, env_int("ICP_B200_STREAM_CELLS_PER_POINT", 8)));
+    ctx->stream_cells_per_point = std::max(0, std::min(256, env_int("ICP_B200_STREAM_CELLS_PER_POINT", 0)));
     ctx->force_stream = env_int("ICP_B200_FORCE_STREAM", 0);
     ctx->stream_nn_group = env_int("ICP_B200_STREAM_NN_GROUP", 0);
+    ctx->stream_nn_f32 = env_int("ICP_B200_STREAM_NN_F32", 1);
     ctx->single_ordered = env_int("ICP_B200_SINGLE_ORDERED", 0);
     ctx->use_lean = env_int("ICP_B200_LEAN", 1);
     ctx->guard = env_int("ICP_B200_GUARD", 1);

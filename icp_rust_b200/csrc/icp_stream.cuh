@@ -36,6 +36,7 @@ struct StreamLayout {   // byte offsets inside one CTA's slab
     uint64_t row_r, row_c, row_b, row_rho; // ordered mode: row terms, padded to whole tiles
     uint64_t gx, gy, gz, gidx, gslot;      // target copy sorted by cell
     uint64_t grec;                         // the same as array-of-structs records (GridRec): the warp search's view
+    uint64_t grecf;                        // 3-D: binary32 records in cell units (GridRecF): the filter's view
     uint64_t heavy;                        // u32[n_cap]: source points whose search is left to a whole warp
     uint64_t gcnt, gcstart;
     uint64_t total;
@@ -63,6 +64,7 @@ ICP_HD StreamLayout stream_layout(int dim, uint32_t n_cap, uint32_t m_cap, uint3
     L.gidx = o; o = align256(o + 4ull * m_cap);
     L.gslot = o; o = align256(o + 4ull * m_cap);
     L.grec = o; o = align256(o + (uint64_t)sizeof(GridRec) * m_cap);
+    L.grecf = o; if (dim == 3) o = align256(o + (uint64_t)sizeof(GridRecF) * m_cap);
     L.heavy = o; o = align256(o + 4ull * n_cap);
     L.gcnt = o; o = align256(o + 4ull * c_cap);
     L.gcstart = o; o = align256(o + 4ull * (c_cap + 1ull));
@@ -76,6 +78,7 @@ struct StreamParams {
     uint32_t cells_per_point;   // cell budget of a pair's own grid = cells_per_point * m, at most c_cap (0: 2)
     uint32_t ordered;           // reference-order sums (ICP_B200_FLAG_ORDERED_SUMS) instead of the warp tree
     uint32_t nn_group;          // 1: kStreamNnGroup lanes per query (grid_nn_search_seeded_group); 0: one thread per query
+    uint32_t nn_f32;            // 1: 3-D per-pair searches rank candidates on binary32 records first (grid_nn_search_seeded_f32)
 };
 
 // Phase clock of CTA 0 (debug builds, -DICP_STREAM_TIMING): thread 0 sums clock64() differences.
@@ -284,6 +287,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
         // ---- IcpD::new: sorted cell list of this pair's target in the slab
         GridView<DIM, uint32_t, uint32_t> gv;
         GridRec* grec = reinterpret_cast<GridRec*>(slab + L.grec);
+        GridRecF* grecf = (DIM == 3 && !SHARED_TARGET && sp.nn_f32) ? reinterpret_cast<GridRecF*>(slab + L.grecf) : nullptr;
         if (SHARED_TARGET) {
             gv.x = p.target.x; gv.y = p.target.y; gv.z = p.target.z;
             gv.idx = p.target.idx; gv.cstart = p.target.cstart; gv.g = p.target.g;
@@ -352,6 +356,14 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
                     rc.z = (DIM == 3) ? dst[(size_t)j * DIM + 2] : 0.0;
                     rc.idx = (uint32_t)j; rc.pad = 0u;
                     grec[pos] = rc;
+                    if (DIM == 3 && grecf) {   // the same coordinates the walk gives a query (nn_cell_coord), rounded once
+                        GridRecF rf;
+                        rf.x = (float)nn_cell_coord(rc.x, g.ox, g.inv_h);
+                        rf.y = (float)nn_cell_coord(rc.y, g.oy, g.inv_h);
+                        rf.z = (float)nn_cell_coord(rc.z, g.oz, g.inv_h);
+                        rf.idx = (uint32_t)j;
+                        grecf[pos] = rf;
+                    }
                 }
                 __syncthreads();
             }
@@ -404,7 +416,7 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, ICP_STREAM_MINB) icp_stream_kernel(St
                     }
                     const NnResult<DIM, uint32_t, uint32_t> r =
                         SHARED_TARGET ? target_nn_search<DIM>(p.target, s.x, s.y, pz, seed)
-                                      : grid_nn_search_auto(gv, s.x, s.y, pz, seed, grec);
+                                      : grid_nn_search_auto(gv, s.x, s.y, pz, seed, grec, grecf);
                     finish(i, s, r);
                 }
                 __syncthreads();

@@ -814,11 +814,174 @@ ICP_DEV int grid_ball_rows(const GridView<DIM, IdxT, CellT>& gv, const GridRec* 
     return ny * nz;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Binary32 filter for the 3-D record walk (large per-pair grids, icp_stream.cuh; config 4).
+// The exact walk above spends its time on 32-byte records and binary64 arithmetic at ~9 of 32
+// lanes.  Here every candidate is first ranked on a 16-byte record {x, y, z in CELL UNITS from the
+// grid's origin, binary32; original index} — half the bytes, a third of the arithmetic — exactly as
+// target_nn_search2 does on a shared 2-D target, with the same argument:
+//   error: the stored coordinate and the query's coordinate are each rounded once to binary32
+//          (|.| <= A := max|T(q)| + G, G the largest grid dimension) and their difference once more:
+//          each of ex, ey, ez is within a := 2^-23 (A + 2)(1 + 1e-2) of the true (q - p)/h;
+//   bound (filter, 3-D): sqrt(d32) is within sqrt(3) a + 2^-22 sqrt(d32) of the true distance D/h,
+//          so the exact winner w has sqrt(d32(w)) <= sqrt(m1)(1 + 2^-20) + 4a for the binary32
+//          minimum m1: candidates above the band (nn_filter_band3, 6a) cannot win;
+//   a single candidate inside the band IS the winner; two or more (near-ties at the 1e-5-cell
+//   level, duplicates) send the query to the exact binary64 walk above, unchanged.
+// The cover (slabs, rows, columns) is the exact walk's, formed from the seed's exact d2; the own
+// cell first and the shrinking ball work on the filter's running minimum (a candidate with
+// binary32 distance sqrt(m1) is at most (sqrt(m1)(1 + 2^-22) + sqrt(3) a) h away).
+struct GridRecF {
+    float x, y, z;
+    uint32_t idx;
+};
+
+ICP_DEV float nn_filter_band3(float m1, float a)
+{
+    const float t = sqrtf(m1) * 1.000004f + 6.0f * a;
+    return t * t * 1.000001f + 1e-30f;
+}
+
+// Candidates [p0, p1) through the filter, eight 16-byte loads in flight.
+ICP_DEV void nn_scan_records_f32(const GridRecF* recf, int p0, int p1, float qxf, float qyf, float qzf, NnFilterState& f)
+{
+    auto one = [&](const float4& c, int p) {
+        const float ex = qxf - c.x, ey = qyf - c.y, ez = qzf - c.z;
+        const float d32 = nn_fma(ex, ex, nn_fma(ey, ey, ez * ez));
+        f.m2 = fminf(f.m2, fmaxf(d32, f.m1));
+        f.pos = (d32 < f.m1) ? p : f.pos;
+        f.m1 = fminf(f.m1, d32);
+    };
+    const float4* r4 = reinterpret_cast<const float4*>(recf);
+    int p = p0;
+    for (; p + 8 <= p1; p += 8) {
+        const float4 c0 = r4[p], c1 = r4[p + 1], c2 = r4[p + 2], c3 = r4[p + 3];
+        const float4 c4 = r4[p + 4], c5 = r4[p + 5], c6 = r4[p + 6], c7 = r4[p + 7];
+        one(c0, p); one(c1, p + 1); one(c2, p + 2); one(c3, p + 3);
+        one(c4, p + 4); one(c5, p + 5); one(c6, p + 6); one(c7, p + 7);
+    }
+    if (p + 4 <= p1) {
+        const float4 c0 = r4[p], c1 = r4[p + 1], c2 = r4[p + 2], c3 = r4[p + 3];
+        one(c0, p); one(c1, p + 1); one(c2, p + 2); one(c3, p + 3);
+        p += 4;
+    }
+    for (; p < p1; ++p) {
+        const float4 c = r4[p];
+        one(c, p);
+    }
+}
+
+template <typename IdxT, typename CellT>
+ICP_DEV NnResult<3, IdxT, CellT> grid_nn_search_seeded_f32(const GridView<3, IdxT, CellT>& gv, const GridRec* rec,
+                                                           const GridRecF* recf, double qx, double qy, double qz,
+                                                           int seed_pos, int own_base = -1, int own_x = -1)
+{
+    const GridGeom& g = gv.g;
+    const GridRec s = rec[seed_pos];
+    const double sdx = qx - s.x, sdy = qy - s.y, sdz = qz - s.z;
+    const double U2 = (sdx * sdx + sdy * sdy) + sdz * sdz;
+    NnQuery Q;
+    Q.tx = nn_cell_coord(qx, g.ox, g.inv_h);
+    Q.ty = nn_cell_coord(qy, g.oy, g.inv_h);
+    Q.txf = (float)Q.tx; Q.tyf = (float)Q.ty;
+    const float tzf = (float)nn_cell_coord(qz, g.oz, g.inv_h);
+    const float ihf = (float)g.inv_h;
+    float Uc2 = ((float)U2 * ihf) * ihf * 1.000001f + 1e-30f;      // as in nn_query_setup
+    const float amax = fmaxf(fmaxf(fabsf(Q.txf), fabsf(Q.tyf)), fabsf(tzf));
+    const int gmax = g.gx > g.gy ? (g.gx > g.gz ? g.gx : g.gz) : (g.gy > g.gz ? g.gy : g.gz);
+    if (!(amax <= 1e6f) || !(Uc2 <= 1e12f) || !(U2 >= 0.0))
+        return grid_nn_search_seeded(gv, qx, qy, qz, seed_pos, rec, own_base, own_x);
+    const float a = (amax + (float)gmax + 2.0f) * 1.21e-7f;    // 2^-23 (A + 2)(1 + 1e-2)
+    Q.sx = (fabsf(Q.txf) + 1.0f) * 3.6e-7f;
+    Q.sy = (fabsf(Q.tyf) + 1.0f) * 3.6e-7f;
+    const float sz = (fabsf(tzf) + 1.0f) * 3.6e-7f;
+    NnFilterState f;
+    f.m1 = 3.0e38f; f.m2 = 3.0e38f; f.pos = seed_pos;
+    // a closer candidate shrinks the ball: its true distance is at most (sqrt(m1)(1 + 2^-22) + sqrt(3) a) h
+    auto tighten = [&]() {
+        const float uc = sqrtf(f.m1) * 1.000001f + 2.0f * a;
+        const float u2 = uc * uc * 1.000002f;
+        const bool smaller = u2 < Uc2;
+        Uc2 = smaller ? u2 : Uc2;
+        return smaller;
+    };
+    if (own_x >= 0) {
+        nn_scan_records_f32(recf, (int)gv.cstart[own_base + own_x], (int)gv.cstart[own_base + own_x + 1], Q.txf, Q.tyf, tzf, f);
+        tighten();
+    }
+    float Uc = sqrtf(Uc2) * 1.000001f;
+    int zz = nn_floor_clamp(tzf - Uc - sz, g.gz - 1);                   // bound (slabs)
+    int zb = nn_floor_clamp(tzf + Uc + sz, g.gz - 1);
+    int yy = 1, yb = 0;          // rows of the current slab still to visit
+    bool slab_open = false;
+    int pend0 = 0, pend1 = 0;    // second half of a span that was split around the own cell
+    Q.Uc2 = Uc2;
+    for (;;) {
+        int p0 = pend0, p1 = pend1;
+        pend0 = 0; pend1 = 0;
+        while (p1 == p0 && zz <= zb) {
+            if (!slab_open) {
+                const float zf = (float)zz;
+                const float zdc = fmaxf(fmaxf(zf - tzf, tzf - (zf + 1.0f)) - sz, 0.0f) * 0.999999f;
+                const float rem2 = Uc2 - zdc * zdc;
+                if (rem2 < 0.0f) { ++zz; continue; }
+                const float ry = sqrtf(rem2) * 1.000001f;
+                Q.Uc2 = rem2;    // nn_row_span tests wc^2 + ydc^2 against Uc2 - zdc^2
+                yy = nn_floor_clamp(Q.tyf - ry - Q.sy, g.gy - 1);       // bound (rows)
+                yb = nn_floor_clamp(Q.tyf + ry + Q.sy, g.gy - 1);
+                slab_open = true;
+            }
+            if (yy > yb) { slab_open = false; ++zz; continue; }
+            int xa, xb;
+            if (nn_row_span(Q, yy, g.gx, &xa, &xb)) {                    // bound (columns)
+                const int base = (zz * g.gy + yy) * g.gx;
+                p0 = (int)gv.cstart[base + xa];
+                p1 = (int)gv.cstart[base + xb + 1];
+                if (base == own_base && xa <= own_x && own_x <= xb) {   // the own cell has been ranked
+                    pend0 = (int)gv.cstart[base + own_x + 1];
+                    pend1 = p1;
+                    p1 = (int)gv.cstart[base + own_x];
+                    if (p1 == p0) { p0 = pend0; p1 = pend1; pend0 = 0; pend1 = 0; }
+                }
+            }
+            ++yy;
+        }
+        if (p1 == p0) break;
+        const float before = f.m1;
+        nn_scan_records_f32(recf, p0, p1, Q.txf, Q.tyf, tzf, f);
+        if (f.m1 < before && tighten()) {
+            Uc = sqrtf(Uc2) * 1.000001f;
+            const int zb2 = nn_floor_clamp(tzf + Uc + sz, g.gz - 1);                 // bound (slabs)
+            zb = zb2 < zb ? zb2 : zb;
+            if (slab_open) {    // the rows of the current slab that are still ahead
+                const float zf = (float)zz;
+                const float zdc = fmaxf(fmaxf(zf - tzf, tzf - (zf + 1.0f)) - sz, 0.0f) * 0.999999f;
+                const float rem2 = Uc2 - zdc * zdc;
+                if (rem2 < 0.0f) {
+                    slab_open = false; ++zz;
+                } else {
+                    Q.Uc2 = rem2;
+                    const int yb2 = nn_floor_clamp(Q.tyf + sqrtf(rem2) * 1.000001f + Q.sy, g.gy - 1);   // bound (rows)
+                    yb = yb2 < yb ? yb2 : yb;
+                }
+            }
+        }
+    }
+    const float thr = nn_filter_band3(f.m1, a);
+    if (f.m2 > thr && f.m1 < 3.0e38f) {   // a single candidate inside the band: the winner
+        NnResult<3, IdxT, CellT> r;
+        r.d2 = 0.0; r.pos = f.pos; r.idx = (int)recf[f.pos].idx;
+        return r;
+    }
+    return grid_nn_search_seeded(gv, qx, qy, qz, seed_pos, rec, own_base, own_x);
+}
+
 // Search of a per-pair grid with whatever seed is at hand: the previous match (seed_pos >= 0), else
 // the first point of the query's own cell, else (empty cell) the ring search.
 template <int DIM, typename IdxT, typename CellT>
 ICP_DEV NnResult<DIM, IdxT, CellT> grid_nn_search_auto(const GridView<DIM, IdxT, CellT>& gv, double qx, double qy,
-                                                       double qz, int seed_pos, const GridRec* rec = nullptr)
+                                                       double qz, int seed_pos, const GridRec* rec = nullptr,
+                                                       const GridRecF* recf = nullptr)
 {
     if (seed_pos < 0) {
         const GridGeom& g = gv.g;
@@ -831,9 +994,15 @@ ICP_DEV NnResult<DIM, IdxT, CellT> grid_nn_search_auto(const GridView<DIM, IdxT,
             // 3-D records: rank the whole own cell first and leave it out of the walk.  (The best point
             // of the own cell as a mere seed, the cell then scanned again by the walk, was measured
             // before the walk could shrink its ball: 2.80k against 2.98k pairs/s.)
-            if (DIM == 3 && rec) return grid_nn_search_seeded(gv, qx, qy, qz, p0, rec, c - cx, cx);
+            if constexpr (DIM == 3) {
+                if (rec && recf) return grid_nn_search_seeded_f32(gv, rec, recf, qx, qy, qz, p0, c - cx, cx);
+                if (rec) return grid_nn_search_seeded(gv, qx, qy, qz, p0, rec, c - cx, cx);
+            }
             seed_pos = p0;
         }
+    }
+    if constexpr (DIM == 3) {
+        if (seed_pos >= 0 && rec && recf) return grid_nn_search_seeded_f32(gv, rec, recf, qx, qy, qz, seed_pos);
     }
     return seed_pos >= 0 ? grid_nn_search_seeded(gv, qx, qy, qz, seed_pos, rec) : grid_nn_search(gv, qx, qy, qz);
 }

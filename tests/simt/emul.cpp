@@ -50,6 +50,8 @@ static double* g_out_cost = nullptr;
 static int g_stream_ordered = 0, g_shared_src = 0, g_stream_nn_group = 0, g_fixed_point = 1;
 extern "C" void simt_set_fixed_point(int on) { g_fixed_point = on; }
 extern "C" void simt_set_stream_nn_group(int v) { g_stream_nn_group = v; }
+static int g_stream_nn_f32 = 1;
+extern "C" void simt_set_stream_nn_f32(int v) { g_stream_nn_f32 = v; }
 static uint32_t g_last_redo = 0;
 extern "C" void simt_set_options(double guard_scale, double* out_cost, int stream_ordered, int shared_src,
                                  double delta_band_scale)
@@ -178,6 +180,7 @@ extern "C" int simt_icp_stream(int dim, int threads, unsigned grid, const double
     };
     sp.ordered = (uint32_t)g_stream_ordered;
     sp.nn_group = (uint32_t)g_stream_nn_group;
+    sp.nn_f32 = (uint32_t)g_stream_nn_f32;
     run(sp);
     g_last_redo = 0;
     if (guard) {

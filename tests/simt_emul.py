@@ -45,6 +45,12 @@ def set_fixed_point(on):
     lib().simt_set_fixed_point(C.c_int(1 if on else 0))
 
 
+def set_stream_nn_f32(on):
+    """Streaming kernel's 3-D searches: binary32 filter on 16-byte records first (True, default) or
+    every candidate in binary64."""
+    lib().simt_set_stream_nn_f32(C.c_int(1 if on else 0))
+
+
 def set_stream_nn_group(on):
     """Streaming kernel's search: a group of lanes per query (True) or one thread per query."""
     lib().simt_set_stream_nn_group(C.c_int(1 if on else 0))

@@ -555,3 +555,43 @@ def test_outer_fixed_point_exit(dim):
         so = out[True]["src_off"]
         for b, r in enumerate(refs):   # corr_mode LAST holds the last iteration's correspondences
             assert np.array_equal(out[True]["corr_last"][int(so[b]):int(so[b + 1])], r["corr"][-1])
+
+
+def test_stream_3d_binary32_filter_ties_and_duplicates():
+    """grid_nn_search_seeded_f32 (icp_target_nn.cuh): the streaming kernel's 3-D searches rank the
+    candidates on binary32 records first; exact ties (two target points mirrored about a source
+    point), duplicated target points (same coordinates, different index), near-ties below the
+    filter's resolution and a cloud far from the origin must come out as the oracle's brute force
+    has them (lowest index on ties), with the filter on and off."""
+    rng = np.random.default_rng(77)
+    for shift in (0.0, 4096.0):
+        dst = rng.uniform(0, 10, (500, 3))
+        dst[:, 2] *= 0.3
+        src = rng.uniform(0.5, 9.5, (160, 3))
+        src[:, 2] *= 0.3
+        extra = []
+        for k in range(0, 40):            # exact ties: mirrored pairs at a power-of-two offset
+            d = 2.0 ** -(3 + k % 4)
+            axis = k % 3
+            e = np.zeros(3); e[axis] = d
+            extra += [src[k] + e, src[k] - e]
+        for k in range(40, 60):           # near-ties: 1e-9 apart in distance
+            e = np.array([0.05, 0.0, 0.0])
+            extra += [src[k] + e, src[k] - e * (1 + 1e-9)]
+        dup = dst[:30].copy()             # duplicates of existing points (higher indices lose)
+        dst = np.concatenate([dst, np.array(extra), dup]) + shift
+        src = src + shift
+        perm = rng.permutation(len(dst))
+        dst = dst[perm]
+        refs = _oracle_ref([src], [dst], [I6], 3)
+        outs = []
+        for on in (True, False):
+            try:
+                E.set_stream_nn_f32(on)
+                g = E.icp_stream([src], [dst], [I6], 3, threads=64, grid=1)
+            finally:
+                E.set_stream_nn_f32(True)
+            _compare(g, refs, [src], 3, ordered=False)
+            outs.append(g)
+        for k in ("T", "inner", "corr", "corr_hash"):
+            assert np.array_equal(outs[0][k], outs[1][k]), k
