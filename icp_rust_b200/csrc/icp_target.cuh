@@ -184,8 +184,11 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, 1) target_seed_added_kernel(GridGeom g, c
 
 // One thread per query.  queries: AoS f64.  out_idx: original index of the exact nearest target
 // point (lowest index on ties).
+#ifndef ICP_NN_MINB
+#define ICP_NN_MINB 2
+#endif
 template <int DIM>
-ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, 2) nn_search_kernel(TargetView tv, const double* queries,
+ICP_GLOBAL void ICP_LAUNCH_BOUNDS(256, ICP_NN_MINB) nn_search_kernel(TargetView tv, const double* queries,
                                                           unsigned long long nq, int32_t* out_idx)
 {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;

@@ -247,7 +247,10 @@ ICP_DEV void nn_walk(const TargetView& tv, const NnQuery& Qin, Visit&& visit)
         ICP_NN_COUNT(cand, p1 - p0);
         // candidates in ascending position, two per 16-byte load where the position is even (pf is
         // 16-byte aligned): a lane's fetches are the L1/TEX unit's work — one wavefront per load.
-        // (Four per 256-bit load — sm_100's LDG.E.256 — was measured: 4.79 against 6.33 G queries/s.)
+        // (Four per 256-bit load — sm_100's LDG.E.256 — was measured: 4.79 against 6.33 G queries/s.  Two
+        // 16-byte loads in flight per trip: 5.03 G at the 80 registers it takes, 5.79 G held to 64; config 3
+        // 49.9k against 55.3k scans/s.  The walk is bound by L1/TEX wavefronts and issue slots, not by the
+        // latency of its one load in flight.)
         int p = p0;
         const float m1_before = m1w;
         if ((p & 1) != 0) {
