@@ -1084,7 +1084,15 @@ int icp_b200_target_search_device(icp_b200_target* t, const double* queries, uin
     ICP_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], st));
     // ICP_B200_NN_WARP=1: the warp-cooperative union walk (measured slower on scan queries: 3.55 against 5.90 G
     // queries/s — consecutive beams are ~60 mm apart at 10 m, their discs barely overlap; kept for A/B runs)
-    if (t->dim == 2 && tv.pf != nullptr && env_int("ICP_B200_NN_WARP", 0) != 0) {
+    const int nn_group = (t->dim == 2 && tv.pf != nullptr) ? env_int("ICP_B200_NN_GROUP", 0) : 0;
+    if (nn_group == 4 || nn_group == 8) {
+        // G lanes per query (target_nn_search2_group): a warp takes 32 / G consecutive queries at a time
+        const long long chunks = (long long)((nq + (32 / nn_group) - 1) / (32 / nn_group));
+        const long long wantg = (chunks + kNnGroupThreads / 32 - 1) / (kNnGroupThreads / 32);
+        const int gridg = (int)std::max<long long>(1, std::min<long long>(wantg, (long long)ctx->sm_count * 32));
+        if (nn_group == 4) nn_search_group_kernel<4><<<gridg, kNnGroupThreads, 0, st>>>(tv, queries, nq, out_index);
+        else nn_search_group_kernel<8><<<gridg, kNnGroupThreads, 0, st>>>(tv, queries, nq, out_index);
+    } else if (t->dim == 2 && tv.pf != nullptr && env_int("ICP_B200_NN_WARP", 0) != 0) {
         const long long wantw = (long long)((nq + kNnWarpThreads - 1) / kNnWarpThreads);
         const int gridw = (int)std::max<long long>(1, std::min<long long>(wantw, (long long)ctx->sm_count * 16));
         nn_search_warp_kernel<<<gridw, kNnWarpThreads, kNnWarpShared, st>>>(tv, queries, nq, out_index);

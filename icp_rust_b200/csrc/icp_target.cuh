@@ -235,4 +235,31 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(kNnWarpThreads, 4) nn_search_warp_kernel(Targe
 }
 constexpr uint32_t kNnWarpShared = (uint32_t)(sizeof(NnWarpScratch) * (kNnWarpThreads / 32));
 
+// Group search kernel (2-D targets with seeds and binary32 copies): G lanes per query
+// (target_nn_search2_group); a warp takes 32 / G consecutive queries at a time.
+constexpr int kNnGroupThreads = 256;
+template <int G>
+ICP_GLOBAL void ICP_LAUNCH_BOUNDS(kNnGroupThreads, 4) nn_search_group_kernel(TargetView tv, const double* queries,
+                                                                             unsigned long long nq, int32_t* out_idx)
+{
+    constexpr unsigned long long QPW = 32 / G;
+    const int lane = lane_id();
+    const unsigned long long chunks = (nq + QPW - 1ull) / QPW;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * (kNnGroupThreads / 32);
+    for (unsigned long long c = (unsigned long long)blockIdx.x * (kNnGroupThreads / 32) + (unsigned long long)warp_id(); c < chunks;
+         c += nwarps) {
+        const unsigned long long q = c * QPW + (unsigned long long)(lane / G);
+        bool active = q < nq;
+        double qx = 0., qy = 0.;
+        if (active) {
+            const double2 v = reinterpret_cast<const double2*>(queries)[q];
+            qx = v.x; qy = v.y;
+        }
+        // the reference would panic comparing NaN distances; a non-finite query gets index -1
+        const bool finite = (fabs(qx) <= kF64Max) && (fabs(qy) <= kF64Max);
+        const int pos = target_nn_search2_group<G>(tv, qx, qy, active && finite);
+        if (active && (lane & (G - 1)) == 0) out_idx[q] = finite ? (int32_t)tv.idx[pos] : -1;
+    }
+}
+
 }  // namespace icp

@@ -440,6 +440,116 @@ ICP_DEV int target_nn_search2_warp(const TargetView& tv, double qx, double qy, N
     return nn_exact_pass(tv, Q, qx, qy, thr).pos;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same search by a GROUP of G lanes per query (G = 4 or 8; 32 / G queries per warp at a time).
+// The private walk is bound by the L1/TEX unit: a lane's every fetch is a wavefront of its own
+// (~47 per query: ~12 cell-table entries, ~30 candidate pairs, the seed) and only ~13 of 32 lanes
+// are active in the candidate loop.  Here the lanes of a group share ONE query:
+//   rows        lane j of the group takes rows ya + j, ya + j + G, ... of the disc: its chord
+//               (nn_row_span), the chord's two cell-table entries, one segment per 32-cell block;
+//   candidates  the segments are handed round the group (two shuffles each) and scanned by all G
+//               lanes, two candidates per lane and step from consecutive 16-byte words — G words
+//               are one wavefront — each lane keeping its own filter state (m1, m2, position);
+//   finish      shuffle-merge of the filter states (the second smallest of a union is
+//               min(m2, m2', max(m1, m1'))), band test, and for a query with two or more
+//               candidates inside the band the exact pass, run by the group's first lane.
+// Same bounds, same filter, same exact pass as target_nn_search2: identical results.  The loops are
+// warp-uniform (a group that has run out of rows or candidates idles until the slowest is done):
+// queries of one warp are consecutive entries of the query array — consecutive beams of a scan.
+// Call with all 32 lanes; the lanes of a group pass the same query; `active` false for a group
+// without one.  Returns the sorted position of the nearest point (group-uniform), -1 if !active.
+template <int G>
+ICP_DEV int target_nn_search2_group(const TargetView& tv, double qx, double qy, bool active)
+{
+    const int lane = lane_id();
+    const int gl = lane & (G - 1), gbase = lane & ~(G - 1);
+    const int gx = tv.g.gx;
+    NnQuery Q;
+    Q.slow = true; Q.ya = 1; Q.yb = 0; Q.seed = 0u; Q.a = 0.0f; Q.tx = 0.; Q.ty = 0.;
+    Q.txf = 0.0f; Q.tyf = 0.0f; Q.sx = 0.0f; Q.sy = 0.0f; Q.Uc2 = 0.0f; Q.U2 = 0.;
+    if (active) Q = nn_query_setup(tv, qx, qy);
+    const bool walk = active && !Q.slow;
+    NnFilterState f;
+    f.m1 = 3.0e38f; f.m2 = 3.0e38f; f.pos = (int)Q.seed;
+    auto visit = [&](int p, float d32) {
+        f.m2 = fminf(f.m2, fmaxf(d32, f.m1));
+        f.pos = (d32 < f.m1) ? p : f.pos;
+        f.m1 = fminf(f.m1, d32);
+    };
+    const int NY = __reduce_max_sync(ICP_FULL_MASK, walk ? Q.yb - Q.ya + 1 : 0);
+    for (int r0 = 0; r0 < NY; r0 += G) {
+        // this lane's row of the disc
+        const int yy = Q.ya + r0 + gl;
+        int xa = 0, xb = -1;
+        bool row = walk && yy <= Q.yb && nn_row_span(Q, yy, gx, &xa, &xb);
+        const int rowbase = yy * gx;
+        int rp0 = 0, rp1 = 0;
+        if (row) {
+            ICP_NN_COUNT(rows, 1);
+            rp0 = (int)tv.cstart[rowbase + xa];
+            rp1 = (int)tv.cstart[rowbase + xb + 1];
+            row = rp1 > rp0;            // nothing in the whole chord
+        }
+        const float qry = row ? nn_block_offset(Q.ty, yy) : 0.0f;
+        int xs = xa;
+        while (__any_sync(ICP_FULL_MASK, row)) {
+            // this lane's next segment: the part of its chord inside one 32-cell block
+            int p0 = 0, p1 = 0;
+            float qrx = 0.0f;
+            if (row) {
+                const int xe_blk = xs | (kNnBlockCells - 1);
+                const int xe = xe_blk < xb ? xe_blk : xb;
+                p0 = (xs == xa) ? rp0 : (int)tv.cstart[rowbase + xs];
+                p1 = (xe == xb) ? rp1 : (int)tv.cstart[rowbase + xe + 1];
+                qrx = nn_block_offset(Q.tx, xs);
+                ICP_NN_COUNT(spans, 1);
+                xs = xe + 1;
+                row = xs <= xb;
+            }
+#pragma unroll
+            for (int o = 0; o < G; ++o) {
+                const int sp0 = __shfl_sync(ICP_FULL_MASK, p0, gbase + o);
+                const int sp1 = __shfl_sync(ICP_FULL_MASK, p1, gbase + o);
+                if (!__any_sync(ICP_FULL_MASK, sp1 > sp0)) continue;
+                const float sqrx = __uint_as_float(__shfl_sync(ICP_FULL_MASK, __float_as_uint(qrx), gbase + o));
+                const float sqry = __uint_as_float(__shfl_sync(ICP_FULL_MASK, __float_as_uint(qry), gbase + o));
+                if (gl == 0) ICP_NN_COUNT(cand, sp1 - sp0);
+                // two candidates per lane and step; word w holds positions 2w and 2w + 1 (pf is 16-byte aligned)
+                for (int b = sp0 & ~1; __any_sync(ICP_FULL_MASK, b < sp1); b += 2 * G) {
+                    const int p = b + 2 * gl;
+                    if (p + 1 < sp1) {
+                        const float4 w = *reinterpret_cast<const float4*>(tv.pf + p);
+                        const float ex0 = sqrx - w.x, ey0 = sqry - w.y, ex1 = sqrx - w.z, ey1 = sqry - w.w;
+                        if (p >= sp0) visit(p, nn_fma(ex0, ex0, ey0 * ey0));
+                        visit(p + 1, nn_fma(ex1, ex1, ey1 * ey1));
+                    } else if (p < sp1 && p >= sp0) {
+                        const float2 v = tv.pf[p];
+                        const float ex = sqrx - v.x, ey = sqry - v.y;
+                        visit(p, nn_fma(ex, ex, ey * ey));
+                    }
+                }
+            }
+        }
+    }
+    // merge the lanes' filter states
+#pragma unroll
+    for (int d = G / 2; d >= 1; d >>= 1) {
+        const float om1 = __uint_as_float(__shfl_xor_sync(ICP_FULL_MASK, __float_as_uint(f.m1), d));
+        const float om2 = __uint_as_float(__shfl_xor_sync(ICP_FULL_MASK, __float_as_uint(f.m2), d));
+        const int opos = (int)__shfl_xor_sync(ICP_FULL_MASK, (uint32_t)f.pos, d);
+        f.m2 = fminf(fminf(f.m2, om2), fmaxf(f.m1, om1));
+        f.pos = (om1 < f.m1) ? opos : f.pos;
+        f.m1 = fminf(f.m1, om1);
+    }
+    int pos = -1;
+    if (active) {
+        const float thr = nn_filter_band(f.m1, Q.a);
+        if (walk && f.m2 > thr && f.m1 < 3.0e38f) pos = f.pos;          // a single candidate inside the band
+        else if (gl == 0) pos = walk ? nn_exact_pass(tv, Q, qx, qy, thr).pos : nn_ring_search(tv, qx, qy).pos;
+    }
+    return __shfl_sync(ICP_FULL_MASK, pos, gbase);
+}
+
 constexpr uint32_t kNnMaxPoints = 1u << 31;   // positions and original indices travel as int
 
 // ---------------------------------------------------------------------------------------------

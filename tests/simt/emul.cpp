@@ -259,6 +259,8 @@ extern "C" int simt_target_search(int dim, const double* pts, uint32_t m, long l
         tv.seed = bufs[cur]; tv.pf = pf.data();
     }
     if (dim == 2 && fast == 2) simt::launch(2, kNnWarpThreads, kNnWarpShared, [&] { nn_search_warp_kernel(tv, queries, nq, out_idx); });
+    else if (dim == 2 && fast == 4) simt::launch(2, kNnGroupThreads, 0, [&] { nn_search_group_kernel<4>(tv, queries, nq, out_idx); });
+    else if (dim == 2 && fast == 8) simt::launch(2, kNnGroupThreads, 0, [&] { nn_search_group_kernel<8>(tv, queries, nq, out_idx); });
     else if (dim == 2) simt::launch(2, 256, 0, [&] { nn_search_kernel<2>(tv, queries, nq, out_idx); });
     else simt::launch(2, 256, 0, [&] { nn_search_kernel<3>(tv, queries, nq, out_idx); });
     return 0;

@@ -141,7 +141,7 @@ def target_search(dst, queries, budget, fast=True):
     q = np.ascontiguousarray(queries, dtype=np.float64)
     out = np.full(q.shape[0], -1, dtype=np.int32)
     rc = lib().simt_target_search(C.c_int(d.shape[1]), d.ctypes.data_as(_dp), C.c_uint32(d.shape[0]),
-                                  C.c_longlong(int(budget)), C.c_int(2 if fast == "warp" else 1 if fast else 0), q.ctypes.data_as(_dp),
+                                  C.c_longlong(int(budget)), C.c_int({"warp": 2, "group4": 4, "group8": 8}.get(fast, 1 if fast else 0)), q.ctypes.data_as(_dp),
                                   C.c_uint64(q.shape[0]), out.ctypes.data_as(C.POINTER(C.c_int32)))
     assert rc == 0
     return out

@@ -243,7 +243,7 @@ def _map_queries(seed, count=6, beams=360):
     return np.concatenate(out)
 
 
-@pytest.mark.parametrize("cells_per_point,fast", [(2, True), (32, True), (200, True), (32, "warp")])
+@pytest.mark.parametrize("cells_per_point,fast", [(2, True), (32, True), (200, True), (32, "warp"), (32, "group4"), (8, "group8")])
 def test_target_search_fast_path_is_exact(cells_per_point, fast):
     """Seeded, binary32-filtered disc search == brute force on a map sampled densely along walls:
     near-ties (neighbours on a wall), exact duplicates, queries on target points, far outside."""
@@ -259,12 +259,12 @@ def test_target_search_fast_path_is_exact(cells_per_point, fast):
     got = E.target_search(m, q, budget=len(m) * cells_per_point, fast=fast)
     assert np.array_equal(got, exp)
     assert np.array_equal(E.target_search(m, q[:400], budget=len(m) * 2, fast=False), exp[:400])
-    if fast == "warp":      # a query count that is not a multiple of 32, and fewer than 32
+    if fast != True:      # a query count that is not a multiple of 32, and fewer than 32
         for cut in (len(q) - 7, 5, 1):
-            assert np.array_equal(E.target_search(m, q[:cut], budget=len(m) * cells_per_point, fast="warp"), exp[:cut])
+            assert np.array_equal(E.target_search(m, q[:cut], budget=len(m) * cells_per_point, fast=fast), exp[:cut])
 
 
-@pytest.mark.parametrize("fast", [True, "warp"])
+@pytest.mark.parametrize("fast", [True, "warp", "group4", "group8"])
 def test_target_search_fast_path_odd_geometries(fast):
     rng = np.random.default_rng(9)
     line = np.stack([np.linspace(-1.0, 1.0, 500), np.full(500, 3.25)], axis=1)       # flat in y
@@ -319,7 +319,7 @@ def test_seeded_disc_walk_is_exact_for_any_seed(dim):
         assert np.array_equal(got, exp), f"trial {trial} dim {dim} m {m} budget {budget}"
 
 
-@pytest.mark.parametrize("fast", [True, "warp"])
+@pytest.mark.parametrize("fast", [True, "warp", "group4", "group8"])
 def test_target_search_random_geometries(fast):
     """Seeded disc + binary32 filter on shared 2-D targets across scales, offsets and cell sizes."""
     rng = np.random.default_rng(77)

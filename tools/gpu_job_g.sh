@@ -1,13 +1,15 @@
 #!/bin/bash
+# round 2, job G: the group search kernel (4 / 8 lanes per query) against the private walk
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x -k "config4 or stream or 3d or final_cost or status" 2>&1 | tail -5 > gpurun_out/r02g_pytest.log
-tail -3 gpurun_out/r02g_pytest.log
-rm -f gpurun_out/r02g_config4_sweep.jsonl
-for cpp in 2 8 32; do
-  ICP_B200_STREAM_CELLS_PER_POINT=$cpp timeout 300 python tools/time_config4.py 296 8 >> gpurun_out/r02g_config4_sweep.jsonl 2>> gpurun_out/r02g_config4_sweep.err
+for g in 0 4 8; do
+ICP_B200_NN_GROUP=$g python - <<'PY'
+import os, sys, torch
+sys.path.insert(0,'.')
+import bench, icp_rust_b200 as icp
+dev=torch.device('cuda',0); ctx=icp.Context(0); st=torch.cuda.Stream(device=dev); torch.cuda.set_stream(st)
+r=bench.bench_nn_search(icp, ctx, torch, dev, st)
+print('group', os.environ["ICP_B200_NN_GROUP"], 'nn', r['value'], r['jittered_map_points']['value'], r['parity_sample_ok'])
+PY
 done
-for G in 4 16; do for cpp in 8; do
-  echo "G=$G" >> gpurun_out/r02g_config4_sweep.jsonl
-  ICP_B200_LIB_DIR=$PWD/icp_rust_b200/lib_g$G ICP_B200_STREAM_CELLS_PER_POINT=$cpp timeout 300 python tools/time_config4.py 296 8 >> gpurun_out/r02g_config4_sweep.jsonl 2>> gpurun_out/r02g_config4_sweep.err
-done; done
-cat gpurun_out/r02g_config4_sweep.jsonl | cut -c1-200
+ICP_B200_NN_GROUP=4 timeout 600 python -m pytest tests -m gpu -q -x -k "search" 2>&1 | tail -2
+ICP_B200_NN_GROUP=8 timeout 600 python -m pytest tests -m gpu -q -x -k "search" 2>&1 | tail -2
