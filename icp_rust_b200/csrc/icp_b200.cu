@@ -1086,7 +1086,9 @@ int icp_b200_target_search_device(icp_b200_target* t, const double* queries, uin
     // queries/s — consecutive beams are ~60 mm apart at 10 m, their discs barely overlap; kept for A/B runs)
     const int nn_group = (t->dim == 2 && tv.pf != nullptr) ? env_int("ICP_B200_NN_GROUP", 0) : 0;
     if (nn_group == 4 || nn_group == 8) {
-        // G lanes per query (target_nn_search2_group): a warp takes 32 / G consecutive queries at a time
+        // ICP_B200_NN_GROUP=4|8: G lanes per query (target_nn_search2_group), a warp takes 32 / G consecutive queries
+        // at a time.  Measured on the config-3 scan queries: 4.08 (G = 4) and 3.31 (G = 8) against 6.41 G queries/s
+        // for the private walk; kept for A/B runs.
         const long long chunks = (long long)((nq + (32 / nn_group) - 1) / (32 / nn_group));
         const long long wantg = (chunks + kNnGroupThreads / 32 - 1) / (kNnGroupThreads / 32);
         const int gridg = (int)std::max<long long>(1, std::min<long long>(wantg, (long long)ctx->sm_count * 32));

@@ -636,6 +636,8 @@ ICP_GLOBAL void ICP_LAUNCH_BOUNDS(THREADS, MINB) icp_lean_kernel(FusedParams p)
                     r2v[i] = q;
                 }
             }
+            // (a group of four lanes per query on a shared target — target_nn_search2_group — was measured in
+            // this loop: config 3 48.7k against 54.9k scans/s; the stand-alone kernel 4.1 against 6.4 G queries/s)
 #pragma unroll 1
             for (int i = tid; i < n; i += THREADS) {
                 const double2 q = r2v[i];
