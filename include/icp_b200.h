@@ -25,6 +25,12 @@
  *  - Host-pointer entries copy with cudaMemcpyAsync on two streams so that transfers overlap
  *    compute.  That overlap needs PINNED (page-locked) caller buffers (cudaHostAlloc /
  *    cudaHostRegister); pageable memory works but every copy then serialises.
+ *  - The reference's outer loop has no exit (src/lib.rs:112-128).  An inner solve that accepts no
+ *    update returns the identity, so the outer transform, the correspondences and the next solve
+ *    stay what they were: every later iteration is an exact repeat.  The kernels write those
+ *    iterations' outputs (same correspondences and iteration word per iteration, checksum advanced
+ *    per iteration) instead of recomputing them; all outputs keep the bits of the full computation.
+ *    ICP_B200_FIXED_POINT=0 in the environment computes every iteration.
  *  - Parity: results are checked against oracle/, a C restatement of the crate.  Its median is the
  *    mathematically exact order statistic ((b + c) / 2 of the true middle pair for even n);
  *    src/stats.rs:23-26 reads input[n/2 - 1] after a second select_nth_unstable_by, which the
