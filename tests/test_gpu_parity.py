@@ -735,3 +735,62 @@ def test_outer_fixed_point_exit_is_exact(icp, scans2d, frames3d_20):
         t.close()
     fast.close()
     full.close()
+
+
+def test_overlapping_calls_other_kernels(icp, frames3d_20):
+    """ICP_B200_FLAG_INDEPENDENT through the other kernels: asynchronous device-pointer calls on the
+    streaming kernel (3-D clouds beyond the fused instances), with ordered sums, and against a
+    shared target (icp_b200_target_estimate_batch_device) — queued back to back, twice over, the
+    results equal those of the synchronous host-pointer calls bit for bit.  max_iter 1 and 2: the
+    fixed-point exit at the edge of the loop."""
+    import torch
+    from icp_rust_b200.workloads import config4_init_transforms
+    c = icp.Context(0)
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.Stream(device=dev)
+    n3 = 3600
+    s3, o3 = _cat([frames3d_20[k + 1][:n3] for k in range(3)], 3)
+    d3, _ = _cat([frames3d_20[k][:n3] for k in range(3)], 3)
+    T3 = config4_init_transforms(3)
+    src, dst, off, _ = icp.synth_scan_pairs(40, beams=1080, first_pair=31000)
+    T2 = np.tile(I6, (40, 1))
+    m = icp.synth_map(20000, seed=7)
+    sm, om, Tm = icp.synth_map_scans(30, beams=360, seed=7)
+    tgt = icp.Target(m, c)
+
+    def to_dev(a, dtype=None):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return (t.to(dtype) if dtype else t).to(dev)
+
+    cases = []
+    for max_iter in (1, 2, 20):
+        cases.append(dict(name=f"stream3d/{max_iter}", dim=3, B=3, n=n3, max_iter=max_iter, ordered=False, target=None,
+                          want=c.estimate_batch(s3, o3, d3, o3, T3, max_iter, dim=3),
+                          bufs=dict(src=to_dev(s3), dst=to_dev(d3), off=to_dev(o3.astype(np.int32)), T0=to_dev(T3))))
+    cases.append(dict(name="ordered2d", dim=2, B=40, n=1080, max_iter=20, ordered=True, target=None,
+                      want=c.estimate_batch(src, off, dst, off, T2, 20, ordered=True),
+                      bufs=dict(src=to_dev(src), dst=to_dev(dst), off=to_dev(off.astype(np.int32)), T0=to_dev(T2))))
+    cases.append(dict(name="shared_map", dim=2, B=30, n=360, max_iter=20, ordered=False, target=tgt,
+                      want=tgt.estimate_batch(sm, om, Tm, 20),
+                      bufs=dict(src=to_dev(sm), dst=None, off=to_dev(om.astype(np.int32)), T0=to_dev(Tm))))
+    for cs in cases:
+        cs["out"] = torch.zeros((cs["B"], 6), dtype=torch.float64, device=dev)
+        cs["hash"] = torch.zeros(cs["B"], dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            for cs in cases:
+                b = cs["bufs"]
+                ptrs = dict(src=b["src"].data_ptr(), src_off=b["off"].data_ptr(), init_T=b["T0"].data_ptr(),
+                            out_T=cs["out"].data_ptr(), out_corr_hash=cs["hash"].data_ptr())
+                if cs["target"] is None:
+                    ptrs.update(dst=b["dst"].data_ptr(), dst_off=b["off"].data_ptr())
+                c.estimate_batch_device(ptrs, cs["B"], cs["max_iter"], dim=cs["dim"], max_src=cs["n"], max_dst=cs["n"],
+                                        stream=stream.cuda_stream, synchronize=False, target=cs["target"], ordered=cs["ordered"],
+                                        flags=icp.FLAG_INDEPENDENT)
+    torch.cuda.synchronize()
+    for cs in cases:
+        assert np.array_equal(cs["out"].cpu().numpy(), cs["want"]["T"]), cs["name"]
+        assert np.array_equal(cs["hash"].cpu().numpy().astype(np.uint64), cs["want"]["corr_hash"]), cs["name"]
+    tgt.close()
+    c.close()
