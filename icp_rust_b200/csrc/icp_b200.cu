@@ -854,7 +854,9 @@ static int target_build(icp_b200_target* t)
     // cell budget per point, bounded (cell tables stay L2-resident).  2-D targets search a seeded disc
     // (icp_target_nn.cuh): empty cells cost nothing there, so the cells are small; the ring search of
     // 3-D targets pays for every empty cell it crosses.
-    const int cells_per_point = env_int("ICP_B200_TARGET_CELLS_PER_POINT", dim == 2 ? 32 : 2);
+    // 2-D: swept with the round-2 kernel on the 100k-point map (16.8 M scan queries / jittered map points, G queries/s):
+    // 8: 6.66 / 9.00, 16: 6.61 / 9.75, 20: 6.74 / 10.27, 24: 6.60-6.67 / 10.5, 28: 6.06 / 9.89, 32: 6.30-6.36 / 10.1, 48: 5.49 / 9.58, 64: 4.87 / 9.32
+    const int cells_per_point = env_int("ICP_B200_TARGET_CELLS_PER_POINT", dim == 2 ? 24 : 2);
     long long budget = std::max<long long>(64, std::min<long long>((long long)m * cells_per_point, 1ll << 24));
     t->g = grid_make_geom(t->bbox[0], t->bbox[1], t->bbox[2], t->bbox[3], t->bbox[4], t->bbox[5], (int)dim, (int)budget);
     t->m_built = m;
