@@ -409,6 +409,37 @@ def run_gpu(args, rank, local_rank, world):
     e2e2_s = max_over_ranks(e2e2_s)
     e2e2_value = world * B * K / e2e2_s
     same2 = bool(all(np.array_equal(host[j]["out"].numpy(), dev_out[j].cpu().numpy()) for j in range(NBUF)))
+
+    # The same K steps from ONE thread through the two-half form of the call (icp_b200_estimate_batch_submit /
+    # _wait), alternating the two contexts: step j+1 is enqueued before step j is waited for.
+    def host_submit(j, c):
+        h = host[j % NBUF]
+        c.submit_host_ptrs(dict(src=h["src"].data_ptr(), src_off=h["off"].data_ptr(), dst=h["dst"].data_ptr(),
+                                dst_off=h["off"].data_ptr(), init_T=h["T0"].data_ptr(), out_T=h["out"].data_ptr(),
+                                out_status=h["status"].data_ptr()), B, MAX_ITER, dim=2, ordered=args.ordered)
+
+    def pipelined(n):
+        host_submit(0, callers[0])
+        for j in range(1, n):
+            host_submit(j, callers[j % 2])
+            callers[(j - 1) % 2].wait()
+        callers[(n - 1) % 2].wait()
+
+    for j in range(NBUF):
+        host[j]["out"].zero_()
+    pipelined(2)
+    torch.cuda.synchronize()
+    barrier()
+    w6 = time.time()
+    t0 = time.perf_counter()
+    pipelined(K)
+    torch.cuda.synchronize()
+    e2e3_s = time.perf_counter() - t0
+    barrier()
+    w7 = time.time()
+    e2e3_s = max_over_ranks(e2e3_s)
+    e2e3_value = world * B * K / e2e3_s
+    same3 = bool(all(np.array_equal(host[j]["out"].numpy(), dev_out[j].cpu().numpy()) for j in range(NBUF)))
     ctx_b.close()
     # device-resident and host paths ran the same two batches: results must agree bit for bit
     same = bool(all(np.array_equal(host[j]["out"].numpy(), dev_out[j].cpu().numpy()) for j in range(NBUF)))
@@ -418,7 +449,7 @@ def run_gpu(args, rank, local_rank, world):
     c3 = None
     c4 = None
     cpu = None
-    clocks = sampler.summary([(w0, w1), (w2, w3), (w4, w5)])
+    clocks = sampler.summary([(w0, w1), (w2, w3), (w4, w5), (w6, w7)])
     sampler.stop_flag = True
     # ---- BASELINE config 5 (strong scaling) when several GPUs run: every rank takes part
     c5 = None
@@ -473,7 +504,11 @@ def run_gpu(args, rank, local_rank, world):
                             "(include/icp_b200.h threading model), so that one call's copies and last pairs overlap the "
                             "other call's kernels; `one_caller` is the same K calls from a single thread",
                     "one_caller": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s / K * 1e3,
-                                   "bit_identical_to_device_path": same}},
+                                   "bit_identical_to_device_path": same},
+                    "one_caller_pipelined": {"value": e2e3_value, "unit": UNIT, "ms_per_step": e2e3_s / K * 1e3,
+                                             "bit_identical_to_device_path": same3,
+                                             "note": "one thread, icp_b200_estimate_batch_submit / _wait alternating two "
+                                                     "contexts: step j+1 is enqueued before step j is waited for"}},
             "gpu_launches": int(launches),
             "fixed_point_exit": fixed_point,
             "step_overlap": {"flag": None if args.no_overlap else "ICP_B200_FLAG_INDEPENDENT",

@@ -23,7 +23,7 @@ FLAG_ORDERED_SUMS = 1  # ICP_B200_FLAG_ORDERED_SUMS: reference-order sums, bit-i
 FLAG_SHARED_SOURCE = 2  # one source scan, `batch` initial transforms
 FLAG_NO_GUARD = 4  # default mode without the knife-edge guard / ordered re-run
 FLAG_INDEPENDENT = 8  # asynchronous device-pointer call that touches nothing the previous call writes: may overlap its tail
-ABI_VERSION = 3
+ABI_VERSION = 4
 BREAK_CAP, BREAK_NONE, BREAK_DELTA, BREAK_ERROR = 0, 1, 2, 3
 PAIR_OK, PAIR_EMPTY_TARGET, PAIR_TOO_LARGE, PAIR_NON_FINITE = 0, 1, 2, 3
 ERR_EMPTY_TARGET, ERR_NON_FINITE, ERR_TOO_LARGE = 4, 5, 6
@@ -48,6 +48,10 @@ class Transform:
 
     @staticmethod
     def new(param):  # transform.rs:13-16 -> se2::calc_rt (se2.rs:21-41)
+        # Host-side convenience only (building an initial guess): sin / cos come from the platform libm here,
+        # while the device kernels and the oracle evaluate the fdlibm restatement of icp_math.cuh — the two can
+        # differ in the last bit.  Nothing on the compute path calls this; transforms the device returns are
+        # passed around as their 6 doubles (from_array / to_array), never re-derived from parameters.
         vx, vy, theta = (float(v) for v in param)
         c, s = math.cos(theta), math.sin(theta)
         if theta == 0.0:
@@ -225,6 +229,29 @@ class Context:
         else:
             rc = self._L.icp_b200_target_estimate_batch(target._h, C.byref(b))
         return self._check(rc)
+
+    def submit_host_ptrs(self, ptrs: dict, B, max_iter, dim=2, corr_mode=CORR_NONE, target=None, ordered=False,
+                         flags=0):
+        """icp_b200_estimate_batch_submit: the first half of estimate_batch_host_ptrs — everything is enqueued,
+        nothing waited for.  The buffers (pinned) stay valid and untouched until wait().  One thread that
+        alternates two contexts keeps the device busy across batch boundaries."""
+        b = Batch()
+        b.dim, b.batch, b.max_iter, b.corr_mode = dim, B, max_iter, corr_mode
+        b.flags = (FLAG_ORDERED_SUMS if ordered else 0) | flags
+        for k in ("src", "src_off", "dst", "dst_off", "init_T", "out_T", "out_inner", "out_corr", "out_corr_hash",
+                  "out_status", "out_cost"):
+            v = ptrs.get(k)
+            setattr(b, k, v if v else None)
+        if target is None:
+            rc = self._L.icp_b200_estimate_batch_submit(self._h, C.byref(b))
+        else:
+            rc = self._L.icp_b200_target_estimate_batch_submit(target._h, C.byref(b))
+        return self._check(rc)
+
+    def wait(self, allow=()):
+        """icp_b200_estimate_batch_wait: completes the submitted batch; returns / raises what the one-call
+        form would."""
+        return self._check(self._L.icp_b200_estimate_batch_wait(self._h), allow)
 
     # ------------------------------------------------------------------ stats hook
     def calc_stddevs_batch(self, sets):

@@ -39,7 +39,8 @@ EXPORTS = [
     "icp_b200_estimate_batch_device", "icp_b200_icp2d_estimate", "icp_b200_icp3d_estimate",
     "icp_b200_target_create", "icp_b200_target_destroy", "icp_b200_target_estimate_batch",
     "icp_b200_target_estimate_batch_device", "icp_b200_target_search", "icp_b200_target_search_device",
-    "icp_b200_calc_stddevs_batch", "icp_b200_target_update",
+    "icp_b200_calc_stddevs_batch", "icp_b200_target_update", "icp_b200_estimate_batch_submit",
+    "icp_b200_estimate_batch_wait", "icp_b200_target_estimate_batch_submit",
 ]
 
 _cuda = None
@@ -64,6 +65,9 @@ def cuda_lib():
         L.icp_b200_last_call_info.argtypes = [C.c_void_p, C.POINTER(CallInfo)]
         L.icp_b200_estimate_batch.argtypes = [C.c_void_p, C.POINTER(Batch)]
         L.icp_b200_estimate_batch_device.argtypes = [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_int]
+        L.icp_b200_estimate_batch_submit.argtypes = [C.c_void_p, C.POINTER(Batch)]
+        L.icp_b200_estimate_batch_wait.argtypes = [C.c_void_p]
+        L.icp_b200_target_estimate_batch_submit.argtypes = [C.c_void_p, C.POINTER(Batch)]
         for f in (L.icp_b200_icp2d_estimate, L.icp_b200_icp3d_estimate):
             f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                           C.c_void_p]

@@ -72,7 +72,10 @@ int env_int(const char* name, int dflt)
 
 }  // namespace
 
+namespace { struct HostPending; }
+
 struct icp_b200_context {
+    HostPending* pending = nullptr;   // a submitted host-pointer batch that has not been waited for
     int device = 0;
     int sm_count = 0;
     int max_smem_optin = 0;
@@ -413,6 +416,7 @@ int estimate_device_impl(icp_b200_context* ctx, const icp_b200_target* tgt, cons
     const bool shared = tgt != nullptr;
     int rc = validate_batch(ctx, b, shared);
     if (rc != ICP_B200_OK || b->batch == 0) return rc;
+    if (ctx->pending) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "a submitted batch is waiting for icp_b200_estimate_batch_wait");
     ICP_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream[0];
     ctx->info = icp_b200_call_info{};
@@ -479,12 +483,27 @@ int estimate_device_impl(icp_b200_context* ctx, const icp_b200_target* tgt, cons
     return ICP_B200_OK;
 }
 
-// Host-pointer path: chunked H2D -> kernel -> D2H pipeline over two streams.
-int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b200_batch* hb)
+// What a submitted host-pointer batch leaves for its wait: everything the second half of the call needs.
+struct HostPending {
+    icp_b200_batch hb, db;
+    icp_b200_target* tgt = nullptr;
+    LaunchPlan redo;
+    bool use_redo = false, shared_src = false;
+    int used = 0;
+    uint64_t ncorr = 0, nsrc = 0;
+};
+
+int host_wait(icp_b200_context* ctx);
+
+// Host-pointer path: chunked H2D -> kernel -> D2H pipeline over two streams.  First half: everything is
+// ENQUEUED (copies in, kernels, copies out) and nothing waited for; host_wait is the second half.
+int host_submit(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b200_batch* hb)
 {
     const bool shared = tgt != nullptr;
     int rc = validate_batch(ctx, hb, shared);
-    if (rc != ICP_B200_OK || hb->batch == 0) return rc;
+    if (rc != ICP_B200_OK) return rc;
+    if (ctx->pending) return fail(ctx, ICP_B200_ERR_INVALID_ARGUMENT, "a submitted batch is waiting for icp_b200_estimate_batch_wait");
+    if (hb->batch == 0) return rc;
     ICP_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->info = icp_b200_call_info{};
     rc = ensure_events(ctx);
@@ -610,6 +629,32 @@ int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b2
         }
         used = c + 1;
     }
+    HostPending* P = new HostPending;
+    P->hb = *hb; P->db = db; P->tgt = tgt; P->redo = redo; P->use_redo = use_redo; P->shared_src = shared_src;
+    P->used = used; P->ncorr = ncorr; P->nsrc = nsrc;
+    ctx->pending = P;
+    return ICP_B200_OK;
+}
+
+// Second half: the guard's ordered re-run behind the last chunk, the status word, the results of re-run pairs.
+int host_wait(icp_b200_context* ctx)
+{
+    if (!ctx->pending) return ICP_B200_OK;
+    // the record is dropped however this ends: a failed wait leaves nothing pending
+    struct Drop { icp_b200_context* c; ~Drop() { delete c->pending; c->pending = nullptr; } } drop{ctx};
+    const HostPending& P = *ctx->pending;
+    const icp_b200_batch* hb = &P.hb;
+    const icp_b200_batch& db = P.db;
+    icp_b200_target* tgt = P.tgt;
+    const LaunchPlan& redo = P.redo;
+    const bool use_redo = P.use_redo, shared_src = P.shared_src;
+    const int used = P.used;
+    const uint64_t ncorr = P.ncorr, nsrc = P.nsrc;
+    const uint32_t B = hb->batch;
+    const uint32_t* so = hb->src_off;
+    cudaStream_t s0 = ctx->stream[0], s1 = ctx->stream[1];
+    int rc = ICP_B200_OK;
+    ICP_CUDA(ctx, cudaSetDevice(ctx->device));
     int32_t err = 0;
     uint32_t nredo = 0;
     ICP_CUDA(ctx, cudaStreamSynchronize(s1));
@@ -666,6 +711,12 @@ int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b2
     ctx->info.kernel_ms = total;
     if (err != 0) return fail(ctx, pair_status_to_error(err), "at least one scan pair was rejected (see out_status)");
     return ICP_B200_OK;
+}
+
+int estimate_host_impl(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b200_batch* hb)
+{
+    const int rc = host_submit(ctx, tgt, hb);
+    return rc != ICP_B200_OK ? rc : host_wait(ctx);
 }
 
 }  // namespace
@@ -747,6 +798,8 @@ void icp_b200_destroy(icp_b200_context* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    delete ctx->pending;   // a batch submitted and never waited for: its copies have landed by now
+    ctx->pending = nullptr;
     DevBuf* bufs[] = {&ctx->src, &ctx->dst, &ctx->src_off, &ctx->dst_off, &ctx->init_T, &ctx->out_T, &ctx->out_inner,
                       &ctx->out_corr, &ctx->out_hash, &ctx->out_status, &ctx->counters, &ctx->workspace[0],
                       &ctx->workspace[1], &ctx->stats_in, &ctx->stats_off, &ctx->stats_out, &ctx->out_cost,
@@ -775,6 +828,14 @@ int icp_b200_last_call_info(const icp_b200_context* ctx, icp_b200_call_info* inf
 const char* icp_b200_last_error(const icp_b200_context* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 
 int icp_b200_estimate_batch(icp_b200_context* ctx, const icp_b200_batch* batch) { return estimate_host_impl(ctx, nullptr, batch); }
+
+int icp_b200_estimate_batch_submit(icp_b200_context* ctx, const icp_b200_batch* batch) { return host_submit(ctx, nullptr, batch); }
+
+int icp_b200_estimate_batch_wait(icp_b200_context* ctx)
+{
+    if (!ctx) return ICP_B200_ERR_INVALID_ARGUMENT;
+    return host_wait(ctx);
+}
 
 int icp_b200_estimate_batch_device(icp_b200_context* ctx, const icp_b200_batch* batch, void* stream, int synchronize)
 {
@@ -1053,6 +1114,13 @@ int icp_b200_target_estimate_batch(icp_b200_target* t, const icp_b200_batch* bat
     if (!t) return ICP_B200_ERR_INVALID_ARGUMENT;
     if (batch && batch->dim != t->dim) return fail(t->ctx, ICP_B200_ERR_INVALID_ARGUMENT, "batch dim differs from target dim");
     return estimate_host_impl(t->ctx, t, batch);
+}
+
+int icp_b200_target_estimate_batch_submit(icp_b200_target* t, const icp_b200_batch* batch)
+{
+    if (!t) return ICP_B200_ERR_INVALID_ARGUMENT;
+    if (batch && batch->dim != t->dim) return fail(t->ctx, ICP_B200_ERR_INVALID_ARGUMENT, "batch dim differs from target dim");
+    return host_submit(t->ctx, t, batch);
 }
 
 int icp_b200_target_estimate_batch_device(icp_b200_target* t, const icp_b200_batch* batch, void* stream, int synchronize)

@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define ICP_B200_ABI_VERSION 3
+#define ICP_B200_ABI_VERSION 4
 
 typedef enum {
     ICP_B200_OK = 0,
@@ -166,6 +166,20 @@ const char *icp_b200_last_error(const icp_b200_context *ctx);
  * the call returns.  Replaces src/lib.rs:97-130 and src/lib.rs:139-173. */
 int icp_b200_estimate_batch(icp_b200_context *ctx, const icp_b200_batch *batch);
 
+/* The same call in two halves, for ONE host thread that streams batches (a scan front end calling
+ * Icp2d::estimate frame after frame, examples/scan2d.rs:84-90, batched): `submit` validates, enqueues every
+ * copy and kernel of the batch and returns without waiting; `wait` completes it (the guard's re-run, the
+ * status word, the last copies) and returns what icp_b200_estimate_batch would have returned.
+ * submit + wait IS icp_b200_estimate_batch.  Between the two, on that context: no other compute call
+ * (INVALID_ARGUMENT), and the batch's arrays — inputs, outputs and the offset tables, PINNED — stay valid and
+ * untouched; the icp_b200_batch struct itself is copied.  With two contexts a thread keeps the device busy
+ * across batch boundaries: submit(A, k) ... submit(B, k+1); wait(A); submit(A, k+2); wait(B) ... — batch
+ * k+1's copies and first pairs run under batch k's last pairs, as two threads calling
+ * icp_b200_estimate_batch on a context each would achieve (bench.py e2e).  wait without a submitted batch
+ * returns OK.  icp_b200_last_call_info is complete after wait. */
+int icp_b200_estimate_batch_submit(icp_b200_context *ctx, const icp_b200_batch *batch);
+int icp_b200_estimate_batch_wait(icp_b200_context *ctx);
+
 /* Same with DEVICE pointers (inputs resident in HBM, outputs written to HBM).  Enqueued on
  * `stream` (a cudaStream_t, NULL = the context's stream) and synchronised before returning
  * only if `synchronize` is non-zero.  The call's status word (worst pair status) is read back by
@@ -209,6 +223,8 @@ int icp_b200_target_update(icp_b200_target *target, const double *add, uint32_t 
 /* estimate() of every `src` scan against the one shared target; HOST pointers
  * (batch->dst / dst_off are ignored). */
 int icp_b200_target_estimate_batch(icp_b200_target *target, const icp_b200_batch *batch);
+/* submit half for a shared target; completed by icp_b200_estimate_batch_wait on the target's context */
+int icp_b200_target_estimate_batch_submit(icp_b200_target *target, const icp_b200_batch *batch);
 int icp_b200_target_estimate_batch_device(icp_b200_target *target, const icp_b200_batch *batch,
                                           void *stream, int synchronize);
 

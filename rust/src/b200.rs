@@ -13,7 +13,7 @@ use crate::types::{Matrix2, Rotation2, Vector2, Vector3};
 #[repr(C)] pub struct IcpB200Context { _p: [u8; 0] }
 #[repr(C)] pub struct IcpB200Target { _p: [u8; 0] }
 
-pub const ICP_B200_ABI_VERSION: c_int = 3;
+pub const ICP_B200_ABI_VERSION: c_int = 4;
 pub const ICP_B200_OK: c_int = 0;
 pub const ICP_B200_CORR_NONE: i32 = 0;
 pub const ICP_B200_CORR_LAST: i32 = 1;
@@ -71,6 +71,11 @@ extern "C" {
     pub fn icp_b200_target_update(target: *mut IcpB200Target, add: *const f64, n_add: u32,
                                   remove_idx: *const u32, n_remove: u32) -> c_int;
     pub fn icp_b200_target_estimate_batch(target: *mut IcpB200Target, batch: *const IcpB200Batch) -> c_int;
+    // the host-pointer call in two halves (one thread streaming batches through two contexts); the batch's
+    // arrays must outlive the wait
+    pub fn icp_b200_estimate_batch_submit(ctx: *mut IcpB200Context, batch: *const IcpB200Batch) -> c_int;
+    pub fn icp_b200_estimate_batch_wait(ctx: *mut IcpB200Context) -> c_int;
+    pub fn icp_b200_target_estimate_batch_submit(target: *mut IcpB200Target, batch: *const IcpB200Batch) -> c_int;
     pub fn icp_b200_target_estimate_batch_device(target: *mut IcpB200Target, batch: *const IcpB200Batch,
                                                  stream: *mut c_void, synchronize: c_int) -> c_int;
     // KdTree::search(&q).0 for every query (src/lib.rs:121,164)

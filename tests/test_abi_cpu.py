@@ -40,7 +40,7 @@ def test_exports_are_unmangled_c_symbols():
 
 def test_abi_version_and_status_strings():
     L = _lib.cuda_lib()
-    assert L.icp_b200_abi_version() == icp.ABI_VERSION == 3
+    assert L.icp_b200_abi_version() == icp.ABI_VERSION == 4
     m = re.search(r"#define ICP_B200_ABI_VERSION (\d+)", open(HEADER).read())
     assert int(m.group(1)) == icp.ABI_VERSION
     assert L.icp_b200_status_string(0) == b"ok"

@@ -794,3 +794,86 @@ def test_overlapping_calls_other_kernels(icp, frames3d_20):
         assert np.array_equal(cs["hash"].cpu().numpy().astype(np.uint64), cs["want"]["corr_hash"]), cs["name"]
     tgt.close()
     c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("forced_reruns", [False, True])
+def test_submit_wait_pipeline_one_thread(icp, forced_reruns):
+    """icp_b200_estimate_batch_submit / _wait: one thread streams batches of very different sizes
+    through two contexts, batch k+1 enqueued before batch k is waited for (pinned buffers).  Every
+    batch gives, bit for bit, what the one-call form gives; a context with a submitted batch refuses
+    other compute calls; wait without a submitted batch is a no-op; a rejected pair surfaces at wait.
+    With the guard bands forced wide every pair goes through the re-run that wait issues."""
+    import torch
+    sizes = [300, 5, 444, 1, 150, 37]
+    total = sum(sizes)
+    src, dst, off, _ = icp.synth_scan_pairs(total, beams=1080, first_pair=910000)
+    if forced_reruns:
+        os.environ["ICP_B200_GUARD_SCALE"] = "1e9"
+    try:
+        cs = [icp.Context(0), icp.Context(0)]
+    finally:
+        os.environ.pop("ICP_B200_GUARD_SCALE", None)
+    assert cs[0].wait() == 0
+    want, bufs, first = [], [], 0
+    for n in sizes:
+        s = src[first * 1080:(first + n) * 1080]
+        d = dst[first * 1080:(first + n) * 1080]
+        o = (off[first:first + n + 1] - off[first]).astype(np.uint32)
+        T0 = np.tile(I6, (n, 1))
+        want.append(cs[0].estimate_batch(s, o, d, o, T0, 20))
+        if forced_reruns:
+            assert want[-1]["redo_pairs"] == n
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        bufs.append(dict(src=pin(s), dst=pin(d), off=pin(o.astype(np.int32)), T0=pin(T0),
+                         out=torch.zeros((n, 6), dtype=torch.float64).pin_memory(),
+                         inner=torch.zeros((n, 20), dtype=torch.int32).pin_memory(),
+                         hash=torch.zeros(n, dtype=torch.int64).pin_memory(),
+                         status=torch.full((n,), -1, dtype=torch.int32).pin_memory()))
+        first += n
+
+    def ptrs(b):
+        return dict(src=b["src"].data_ptr(), src_off=b["off"].data_ptr(), dst=b["dst"].data_ptr(),
+                    dst_off=b["off"].data_ptr(), init_T=b["T0"].data_ptr(), out_T=b["out"].data_ptr(),
+                    out_inner=b["inner"].data_ptr(), out_corr_hash=b["hash"].data_ptr(), out_status=b["status"].data_ptr())
+
+    cs[0].submit_host_ptrs(ptrs(bufs[0]), sizes[0], 20)
+    # the context is taken until its wait
+    with pytest.raises(icp.IcpError):
+        cs[0].submit_host_ptrs(ptrs(bufs[1]), sizes[1], 20)
+    with pytest.raises(icp.IcpError):
+        cs[0].estimate_batch_host_ptrs(ptrs(bufs[1]), sizes[1], 20)
+    for k in range(1, len(sizes)):
+        cs[k % 2].submit_host_ptrs(ptrs(bufs[k]), sizes[k], 20)
+        cs[(k - 1) % 2].wait()
+        if forced_reruns:
+            assert cs[(k - 1) % 2].call_info()["redo_pairs"] == sizes[k - 1]
+    cs[(len(sizes) - 1) % 2].wait()
+    for k, n in enumerate(sizes):
+        b, w = bufs[k], want[k]
+        assert np.array_equal(b["out"].numpy(), w["T"]), k
+        assert np.array_equal(b["inner"].numpy().view(np.uint32), w["inner"]), k
+        assert np.array_equal(b["hash"].numpy().view(np.uint64), w["corr_hash"]), k
+        assert (b["status"].numpy() == 0).all()
+
+    # a rejected pair (NaN coordinate) is reported by wait, as the one-call form reports it
+    bad = bufs[1]
+    bad["src"][3, 0] = float("nan")
+    cs[0].submit_host_ptrs(ptrs(bad), sizes[1], 20)
+    assert cs[0].wait(allow=(icp.ERR_NON_FINITE,)) == icp.ERR_NON_FINITE
+    assert bad["status"].numpy()[0] == 3 and (bad["status"].numpy()[1:] == 0).all()
+    assert cs[0].wait() == 0
+    # shared target: submit on the target, wait on its context
+    m = icp.synth_map(20000, seed=11)
+    scans, soff, sT0 = icp.synth_map_scans(8, beams=360, seed=11)
+    tgt = icp.Target(m, cs[1])
+    w = tgt.estimate_batch(scans, soff, sT0, 10)
+    out = torch.zeros((8, 6), dtype=torch.float64).pin_memory()
+    sc, so, st = (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (scans, soff.astype(np.int32), sT0))
+    cs[1].submit_host_ptrs(dict(src=sc.data_ptr(), src_off=so.data_ptr(), init_T=st.data_ptr(), out_T=out.data_ptr()),
+                           8, 10, target=tgt)
+    cs[1].wait()
+    assert np.array_equal(out.numpy(), w["T"])
+    tgt.close()
+    for c in cs:
+        c.close()
