@@ -224,7 +224,7 @@ def run_gpu(args, rank, local_rank, world):
     for j in range(NBUF):
         hs = torch.empty((B * BEAMS, 2), dtype=torch.float64, pin_memory=True)
         hd = torch.empty((B * BEAMS, 2), dtype=torch.float64, pin_memory=True)
-        first = (rank * NBUF + j) * B
+        first = ((rank + args.as_rank) * NBUF + j) * B
         _, _, off, true_T = icp.synth_scan_pairs(B, beams=BEAMS, seed=SEED, first_pair=first,
                                                  out_src=hs.numpy(), out_dst=hd.numpy())
         hoff = torch.from_numpy(off.astype(np.int32)).pin_memory()
@@ -267,6 +267,14 @@ def run_gpu(args, rank, local_rank, world):
         if world > 1:
             dist.barrier()
 
+    def every_rank(x):
+        if world > 1:
+            t = torch.zeros(world, dtype=torch.float64, device=dev)
+            t[rank] = float(x)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return [float(v) for v in t.tolist()]
+        return [float(x)]
+
     def max_over_ranks(x):
         if world > 1:
             t = torch.tensor([x], dtype=torch.float64, device=dev)
@@ -291,6 +299,7 @@ def run_gpu(args, rank, local_rank, world):
     barrier()
     torch.cuda.synchronize()
     w1 = time.time()
+    dev_ranks = every_rank(evs[0].elapsed_time(evs[K]) / K)
     ms_total = max_over_ranks(evs[0].elapsed_time(evs[K]))
     # the same steps strictly one after the other, an event after each: the duration of ONE launch,
     # which the roofline figures are quoted on
@@ -406,6 +415,7 @@ def run_gpu(args, rank, local_rank, world):
     e2e2_s = time.perf_counter() - t0
     barrier()
     w5 = time.time()
+    e2e2_ranks = every_rank(e2e2_s / K * 1e3)
     e2e2_s = max_over_ranks(e2e2_s)
     e2e2_value = world * B * K / e2e2_s
     same2 = bool(all(np.array_equal(host[j]["out"].numpy(), dev_out[j].cpu().numpy()) for j in range(NBUF)))
@@ -437,6 +447,7 @@ def run_gpu(args, rank, local_rank, world):
     e2e3_s = time.perf_counter() - t0
     barrier()
     w7 = time.time()
+    e2e3_ranks = every_rank(e2e3_s / K * 1e3)
     e2e3_s = max_over_ranks(e2e3_s)
     e2e3_value = world * B * K / e2e3_s
     same3 = bool(all(np.array_equal(host[j]["out"].numpy(), dev_out[j].cpu().numpy()) for j in range(NBUF)))
@@ -490,7 +501,7 @@ def run_gpu(args, rank, local_rank, world):
         oT = host[0]["out"].numpy()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / K, "ms_per_step_every_rank": dev_ranks, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": bench_config(world, B),
             "kernel_shape": {"grid": info["grid_ctas"], "block": info["block_threads"], "smem": info["smem_bytes"],
@@ -498,7 +509,7 @@ def run_gpu(args, rank, local_rank, world):
                              "note": "one icp_lean_kernel launch + one (normally empty) ordered re-run launch of the knife-edge guard"},
             "e2e": {"value": e2e2_value, "unit": UNIT, "h2d_bytes_per_step": int(hinfo["h2d_bytes"]),
                     "d2h_bytes_per_step": int(hinfo["d2h_bytes"]), "ms_per_step": e2e2_s / K * 1e3,
-                    "callers": 2, "bit_identical_to_device_path": same2,
+                    "callers": 2, "bit_identical_to_device_path": same2, "ms_per_step_every_rank": e2e2_ranks,
                     "note": "K synchronous host-pointer calls (icp_b200_estimate_batch: pinned host buffers in, results "
                             "back in host memory when the call returns) issued from two host threads, one context each "
                             "(include/icp_b200.h threading model), so that one call's copies and last pairs overlap the "
@@ -506,7 +517,7 @@ def run_gpu(args, rank, local_rank, world):
                     "one_caller": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s / K * 1e3,
                                    "bit_identical_to_device_path": same},
                     "one_caller_pipelined": {"value": e2e3_value, "unit": UNIT, "ms_per_step": e2e3_s / K * 1e3,
-                                             "bit_identical_to_device_path": same3,
+                                             "bit_identical_to_device_path": same3, "ms_per_step_every_rank": e2e3_ranks,
                                              "note": "one thread, icp_b200_estimate_batch_submit / _wait alternating two "
                                                      "contexts: step j+1 is enqueued before step j is waited for"}},
             "gpu_launches": int(launches),
@@ -832,6 +843,8 @@ def main():
     ap.add_argument("--headline-only", action="store_true", help="skip the nn_search / config3 / config4 side measurements")
     ap.add_argument("--no-overlap", action="store_true",
                     help="time the device steps without ICP_B200_FLAG_INDEPENDENT (each waits for the previous one's last pair)")
+    ap.add_argument("--as-rank", type=int, default=0,
+                    help="diagnosis: a single-GPU run takes the input buffers rank R of a multi-GPU run would take")
     ap.add_argument("--no-config5", action="store_true", help="skip the 1M-pair strong-scaling leg of multi-GPU runs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -55,8 +55,10 @@ constexpr int kNumInstances = (int)(sizeof(kInstances) / sizeof(kInstances[0]));
 constexpr int kMaxChunks = 64;
 // device counter words of a context: per-chunk work counters | error word | work counter of the
 // ordered re-run | count of flagged pairs
-constexpr int kCtrWork = 0, kCtrErr = kMaxChunks, kCtrRedoWork = kMaxChunks + 1, kCtrRedoCount = kMaxChunks + 2;
-constexpr int kCtrWords = kMaxChunks + 3;
+// host-pointer calls: one work counter per chunk, the call's status word, and per chunk the work counter and the
+// count of the guard's re-run (a chunk's flagged pairs are listed at redo_list + the chunk's first pair)
+constexpr int kCtrWork = 0, kCtrErr = kMaxChunks, kCtrRedoWork = kMaxChunks + 1, kCtrRedoCount = 2 * kMaxChunks + 1;
+constexpr int kCtrWords = 3 * kMaxChunks + 1;
 // Counters of the device-pointer calls: two alternating sets (call parity) the kernels clean up
 // themselves (FusedParams::fin_counter), so back-to-back calls need no memset between them and may
 // overlap at their boundary (ICP_B200_FLAG_INDEPENDENT).  Words of set s at s * kDevSetWords.
@@ -80,6 +82,9 @@ struct icp_b200_context {
     int sm_count = 0;
     int max_smem_optin = 0;
     cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaStream_t redo_stream = nullptr;   // host-pointer path: the guard's re-runs, chunk by chunk, beside the later chunks
+    cudaEvent_t ev_cnt[kMaxChunks];       // chunk c's count of flagged pairs has landed in h_redo[c]
+    uint32_t* h_redo = nullptr;           // pinned, kMaxChunks words
     cudaEvent_t ev[kMaxChunks][2];
     cudaEvent_t ev_ready = nullptr;
     cudaEvent_t ev_redo[2] = {nullptr, nullptr};
@@ -92,6 +97,8 @@ struct icp_b200_context {
     DevBuf dev_counters, dev_workspace[2], dev_redo_list[2], dev_redo_workspace[2];
     uint64_t dev_calls = 0;
     bool dev_dirty = true;  // the counters need a memset (first call, or a call that failed midway)
+    int blocking_sync = 0;  // ICP_B200_BLOCKING_SYNC=1: the host-pointer path sleeps on a blocking event instead of spinning in cudaStreamSynchronize
+    cudaEvent_t ev_block = nullptr;
     int pdl = 1;            // ICP_B200_PDL=0: never overlap calls (ICP_B200_FLAG_INDEPENDENT is ignored)
     int fixed_point = 1;    // ICP_B200_FIXED_POINT=0: compute every outer iteration, also the ones that provably repeat
     int guard = 1;          // ICP_B200_GUARD=0: no knife-edge guard (as ICP_B200_FLAG_NO_GUARD on every call)
@@ -203,6 +210,15 @@ int plan_launch(icp_b200_context* ctx, uint32_t dim, bool shared_target, bool or
     if (!inst && !ordered && pairs < (uint32_t)ctx->sm_count) {
         static const int kLatencyOrder[] = {3, 5, 7, 6};
         for (int i : kLatencyOrder)
+            if (!inst && i < kNumInstances && fits(kInstances[i]) && shape(kInstances[i])) inst = kInstances[i];
+    }
+    // Ordered sums, fewer pairs than SMs: the 256-thread ordered instance takes 3.8 ms for a lone 1080-point pair
+    // (1.11 ms for the bundled 666-point pair), the 128-thread one 4.9 ms (1.40 ms).  Not for the guard's re-run of a
+    // large batch (plan_redo plans for the batch size): a 256-thread ordered CTA needs a whole SM's registers and
+    // would wait for one to drain, while the 128-thread one fits the hole a single retiring tree-mode CTA leaves.
+    if (!inst && ordered && pairs < (uint32_t)ctx->sm_count) {
+        static const int kOrderedLatency[] = {12, 13};
+        for (int i : kOrderedLatency)
             if (!inst && i < kNumInstances && fits(kInstances[i]) && shape(kInstances[i])) inst = kInstances[i];
     }
     for (int i = 0; !inst && i < kNumInstances; ++i)     // the first instance that holds the scan AND fits an SM
@@ -334,8 +350,8 @@ int launch_range(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_
     p.mcap = plan.mcap;
     p.ncap = plan.stream ? (int)plan.n_cap : plan.inst->capacity(plan.lean);
     if (guarded) {
-        p.redo_list = dev ? ctx->dev_redo_list[dev_set].as<uint32_t>() : ctx->redo_list.as<uint32_t>();
-        p.redo_count = dev ? dev + kDevRedoCount : ctx->counters.as<uint32_t>() + kCtrRedoCount;
+        p.redo_list = dev ? ctx->dev_redo_list[dev_set].as<uint32_t>() : ctx->redo_list.as<uint32_t>() + begin;
+        p.redo_count = dev ? dev + kDevRedoCount : ctx->counters.as<uint32_t>() + kCtrRedoCount + chunk_slot;
         p.guard.det = kGuardDet * ctx->guard_scale;
         p.guard.delta = kGuardDelta * ctx->guard_scale;
         p.guard.err = kGuardErr * ctx->guard_scale;
@@ -351,10 +367,13 @@ int launch_range(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_
 
 // The ordered re-run of the pairs the call's tree-mode launches flagged: one launch behind them on
 // `stream`, the flagged pairs spread over its CTAs (their indices and count never leave the device).
-// A lone 1080-point pair takes a few milliseconds in reference order (2n dependent additions per
-// evaluation), so the re-run is issued once per call, not once per chunk.
+// A lone 1080-point pair takes 4-5 ms in reference order (2n dependent additions per evaluation).  Device-pointer
+// calls issue the re-run once per call (it overlaps the next call).  Host-pointer calls learn each chunk's count of
+// flagged pairs as the chunk ends and re-run exactly those chunks on a stream of their own, beside the chunks
+// still to come (host_wait) — a flagged pair costs the call nothing unless it sits in the last chunk.
 int launch_redo(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_target* tgt, const LaunchPlan& redo,
-                cudaStream_t stream, int dev_set = -1, bool overlap = false)
+                cudaStream_t stream, int dev_set = -1, bool overlap = false, int chunk = 0, uint32_t chunk_begin = 0,
+                uint32_t flagged = 0)
 {
     FusedParams r{};
     fill_params(ctx, b, tgt, &r);
@@ -368,16 +387,19 @@ int launch_redo(icp_b200_context* ctx, const icp_b200_batch& b, const icp_b200_t
         r.out_error = ctx->dev_counters.as<int32_t>() + kDevErr;
         r.workspace = ctx->dev_redo_workspace[dev_set].as<unsigned char>();
     } else {
-        r.pair_list = ctx->redo_list.as<uint32_t>();
-        r.pair_count = ctx->counters.as<uint32_t>() + kCtrRedoCount;
-        r.work_counter = ctx->counters.as<uint32_t>() + kCtrRedoWork;
+        // host-pointer call: the re-run of ONE chunk's flagged pairs (their count is known to the host by now)
+        r.pair_list = ctx->redo_list.as<uint32_t>() + chunk_begin;
+        r.pair_count = ctx->counters.as<uint32_t>() + kCtrRedoCount + chunk;
+        r.work_counter = ctx->counters.as<uint32_t>() + kCtrRedoWork + chunk;
         r.workspace = ctx->redo_workspace.as<unsigned char>();
     }
     r.ws_stride = redo.ws_stride;
     r.pair_begin = 0; r.pair_end = b.batch;
     r.mcap = redo.mcap;
     r.ncap = redo.stream ? (int)redo.n_cap : redo.inst->capacity(false);
-    return launch_plan(ctx, redo, r, (int)std::min<uint32_t>((uint32_t)redo.grid, b.batch), stream, overlap);
+    uint32_t grid = std::min<uint32_t>((uint32_t)redo.grid, b.batch);
+    if (dev_set < 0) grid = std::max<uint32_t>(1u, std::min<uint32_t>(grid, flagged));
+    return launch_plan(ctx, redo, r, (int)grid, stream, overlap);
 }
 
 // The ordered plan that re-runs flagged pairs, when this call wants the guard.
@@ -406,7 +428,24 @@ int ensure_events(icp_b200_context* ctx)
         for (int j = 0; j < 2; ++j) ICP_CUDA(ctx, cudaEventCreate(&ctx->ev[i][j]));
     ICP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
     for (int j = 0; j < 2; ++j) ICP_CUDA(ctx, cudaEventCreate(&ctx->ev_redo[j]));
+    ICP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
+    for (int i = 0; i < kMaxChunks; ++i)
+        ICP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_cnt[i], cudaEventDisableTiming | (ctx->blocking_sync ? cudaEventBlockingSync : 0)));
+    ICP_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_redo), kMaxChunks * sizeof(uint32_t), cudaHostAllocDefault));
     ctx->events_ok = true;
+    return ICP_B200_OK;
+}
+
+// Wait of the host-pointer path for one of its streams.  Many ranks on few host cores: a thread that spins in
+// cudaStreamSynchronize for the 20+ ms of a batch takes a core from the ranks beside it; the blocking form sleeps.
+int host_sync(icp_b200_context* ctx, cudaStream_t st)
+{
+    if (ctx->blocking_sync) {
+        ICP_CUDA(ctx, cudaEventRecord(ctx->ev_block, st));
+        ICP_CUDA(ctx, cudaEventSynchronize(ctx->ev_block));
+        return ICP_B200_OK;
+    }
+    ICP_CUDA(ctx, cudaStreamSynchronize(st));
     return ICP_B200_OK;
 }
 
@@ -491,6 +530,7 @@ struct HostPending {
     bool use_redo = false, shared_src = false;
     int used = 0;
     uint64_t ncorr = 0, nsrc = 0;
+    uint32_t per = 0;    // pairs per chunk
 };
 
 int host_wait(icp_b200_context* ctx);
@@ -587,21 +627,29 @@ int host_submit(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b200_batc
         cudaStream_t st = (c & 1) ? s1 : s0;
         // SHARED_SOURCE: the one scan went up with the tables; sp0/sp1 then only place the correspondences
         const uint64_t sp0 = shared_src ? nsrc * b0 : so[b0], sp1 = shared_src ? nsrc * b1 : so[b1];
+        // (Measured and dropped: every chunk's inputs issued up front on a copy stream of their own, the kernels
+        // gated by events.  All kernels of the next batch are then runnable at once, two callers fall into lockstep
+        // and drain together: 169k against 179k pairs/s end to end with two callers, 178k against 179k pipelined.)
+        cudaStream_t cs = st;
         if (!shared_src) {
             if (sp1 > sp0)
-                ICP_CUDA(ctx, cudaMemcpyAsync(ctx->src.as<double>() + sp0 * dim, hb->src + sp0 * dim, (sp1 - sp0) * dim * 8, cudaMemcpyHostToDevice, st));
+                ICP_CUDA(ctx, cudaMemcpyAsync(ctx->src.as<double>() + sp0 * dim, hb->src + sp0 * dim, (sp1 - sp0) * dim * 8, cudaMemcpyHostToDevice, cs));
             ctx->info.h2d_bytes += (sp1 - sp0) * dim * 8;
         }
         if (!shared) {
             const uint64_t dp0 = doff[b0], dp1 = doff[b1];
             if (dp1 > dp0)
-                ICP_CUDA(ctx, cudaMemcpyAsync(ctx->dst.as<double>() + dp0 * dim, hb->dst + dp0 * dim, (dp1 - dp0) * dim * 8, cudaMemcpyHostToDevice, st));
+                ICP_CUDA(ctx, cudaMemcpyAsync(ctx->dst.as<double>() + dp0 * dim, hb->dst + dp0 * dim, (dp1 - dp0) * dim * 8, cudaMemcpyHostToDevice, cs));
             ctx->info.h2d_bytes += (dp1 - dp0) * dim * 8;
         }
         ICP_CUDA(ctx, cudaEventRecord(ctx->ev[c][0], st));
         rc = launch_range(ctx, db, tgt, plan, use_redo, b0, b1, c, c & 1, st);
         if (rc != ICP_B200_OK) return rc;
         ICP_CUDA(ctx, cudaEventRecord(ctx->ev[c][1], st));
+        if (use_redo) {
+            ICP_CUDA(ctx, cudaMemcpyAsync(ctx->h_redo + c, ctx->counters.as<uint32_t>() + kCtrRedoCount + c, 4, cudaMemcpyDeviceToHost, st));
+            ICP_CUDA(ctx, cudaEventRecord(ctx->ev_cnt[c], st));
+        }
         ICP_CUDA(ctx, cudaMemcpyAsync(hb->out_T + (size_t)b0 * 6, ctx->out_T.as<double>() + (size_t)b0 * 6, (size_t)(b1 - b0) * 48, cudaMemcpyDeviceToHost, st));
         ctx->info.d2h_bytes += (uint64_t)(b1 - b0) * 48;
         if (hb->out_inner && hb->max_iter) {
@@ -631,7 +679,7 @@ int host_submit(icp_b200_context* ctx, icp_b200_target* tgt, const icp_b200_batc
     }
     HostPending* P = new HostPending;
     P->hb = *hb; P->db = db; P->tgt = tgt; P->redo = redo; P->use_redo = use_redo; P->shared_src = shared_src;
-    P->used = used; P->ncorr = ncorr; P->nsrc = nsrc;
+    P->used = used; P->ncorr = ncorr; P->nsrc = nsrc; P->per = per;
     ctx->pending = P;
     return ICP_B200_OK;
 }
@@ -657,23 +705,45 @@ int host_wait(icp_b200_context* ctx)
     ICP_CUDA(ctx, cudaSetDevice(ctx->device));
     int32_t err = 0;
     uint32_t nredo = 0;
-    ICP_CUDA(ctx, cudaStreamSynchronize(s1));
+    std::vector<uint32_t> list;
     if (use_redo) {
-        // every chunk's kernel has been issued (s1's have finished): one ordered re-run of the pairs
-        // they flagged, behind s0's last chunk, then the results of exactly those pairs once more
-        ICP_CUDA(ctx, cudaEventRecord(ctx->ev_redo[0], s0));
-        rc = launch_redo(ctx, db, tgt, redo, s0);
-        if (rc != ICP_B200_OK) return rc;
-        ICP_CUDA(ctx, cudaEventRecord(ctx->ev_redo[1], s0));
-        ICP_CUDA(ctx, cudaMemcpyAsync(&nredo, ctx->counters.as<uint32_t>() + kCtrRedoCount, 4, cudaMemcpyDeviceToHost, s0));
+        // Chunk by chunk, as the chunks end: a chunk that flagged pairs gets its ordered re-run at once, on the
+        // re-run stream, beside the chunks still running (and beside the next batch of a pipelining caller), so the
+        // 4-5 ms of a lone ordered pair are off the call's critical path unless the pair sits in the last chunk.
+        bool any = false;
+        std::vector<std::pair<uint32_t, uint32_t>> seg;    // (first pair of the chunk, flagged pairs)
+        for (int c = 0; c < used; ++c) {
+            ICP_CUDA(ctx, cudaEventSynchronize(ctx->ev_cnt[c]));
+            const uint32_t n = ctx->h_redo[c];
+            if (n == 0) continue;
+            const uint32_t b0 = (uint32_t)c * P.per;
+            if (!any) ICP_CUDA(ctx, cudaEventRecord(ctx->ev_redo[0], ctx->redo_stream));
+            any = true;
+            rc = launch_redo(ctx, db, tgt, redo, ctx->redo_stream, -1, false, c, b0, n);
+            if (rc != ICP_B200_OK) return rc;
+            seg.push_back({b0, n});
+            nredo += n;
+        }
+        if (any) ICP_CUDA(ctx, cudaEventRecord(ctx->ev_redo[1], ctx->redo_stream));
+        if ((rc = host_sync(ctx, s1)) != ICP_B200_OK) return rc;
+        if ((rc = host_sync(ctx, s0)) != ICP_B200_OK) return rc;
+        if (any) {
+            list.resize(nredo);
+            uint32_t at = 0;
+            for (const auto& sg : seg) {
+                ICP_CUDA(ctx, cudaMemcpyAsync(list.data() + at, ctx->redo_list.as<uint32_t>() + sg.first, (size_t)sg.second * 4,
+                                              cudaMemcpyDeviceToHost, ctx->redo_stream));
+                at += sg.second;
+            }
+            if ((rc = host_sync(ctx, ctx->redo_stream)) != ICP_B200_OK) return rc;
+        }
+    } else {
+        if ((rc = host_sync(ctx, s1)) != ICP_B200_OK) return rc;
     }
     ICP_CUDA(ctx, cudaMemcpyAsync(&err, ctx->counters.as<int32_t>() + kCtrErr, 4, cudaMemcpyDeviceToHost, s0));
-    ICP_CUDA(ctx, cudaStreamSynchronize(s0));
+    if ((rc = host_sync(ctx, s0)) != ICP_B200_OK) return rc;
     ctx->info.redo_pairs = nredo;
     if (nredo > 0) {
-        std::vector<uint32_t> list(nredo);
-        ICP_CUDA(ctx, cudaMemcpyAsync(list.data(), ctx->redo_list.p, (size_t)nredo * 4, cudaMemcpyDeviceToHost, s0));
-        ICP_CUDA(ctx, cudaStreamSynchronize(s0));
         const bool all = nredo > 64;     // many (forced bands in tests): whole arrays again
         const size_t npairs = all ? 1 : nredo;
         for (size_t k = 0; k < npairs; ++k) {
@@ -695,7 +765,7 @@ int host_wait(icp_b200_context* ctx)
             }
             ctx->info.d2h_bytes += (uint64_t)cnt * (48 + (hb->out_inner ? hb->max_iter * 4 : 0) + (hb->out_corr_hash ? 8 : 0) + (hb->out_cost ? 8 : 0));
         }
-        ICP_CUDA(ctx, cudaStreamSynchronize(s0));
+        if ((rc = host_sync(ctx, s0)) != ICP_B200_OK) return rc;
     }
     float total = 0.f;
     for (int c = 0; c < used; ++c) {
@@ -703,7 +773,7 @@ int host_wait(icp_b200_context* ctx)
         ICP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[c][0], ctx->ev[c][1]));
         total += ms;
     }
-    if (use_redo) {
+    if (nredo > 0) {
         float ms = 0.f;
         ICP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_redo[0], ctx->ev_redo[1]));
         total += ms;
@@ -768,11 +838,15 @@ int icp_b200_create(int device, icp_b200_context** out)
     icp_b200_context* ctx = new (std::nothrow) icp_b200_context();
     if (!ctx) return ICP_B200_ERR_OUT_OF_MEMORY;
     ctx->device = device;
+    int prio_lo = 0, prio_hi = 0;
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
         cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream[0], cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream[1], cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ctx->stream[1], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess ||
+        // highest priority: a re-run CTA is placed ahead of the pending tree-mode CTAs when a slot frees up
+        cudaStreamCreateWithPriority(&ctx->redo_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
         cudaGetLastError();
         delete ctx;
         return ICP_B200_ERR_CUDA;
@@ -787,6 +861,7 @@ int icp_b200_create(int device, icp_b200_context** out)
     ctx->use_lean = env_int("ICP_B200_LEAN", 1);
     ctx->guard = env_int("ICP_B200_GUARD", 1);
     ctx->pdl = env_int("ICP_B200_PDL", 1);
+    ctx->blocking_sync = env_int("ICP_B200_BLOCKING_SYNC", 0);
     ctx->fixed_point = env_int("ICP_B200_FIXED_POINT", 1);
     if (const char* gs = getenv("ICP_B200_GUARD_SCALE")) ctx->guard_scale = std::max(0.0, atof(gs));
     *out = ctx;
@@ -811,10 +886,14 @@ void icp_b200_destroy(icp_b200_context* ctx)
         for (int i = 0; i < kMaxChunks; ++i)
             for (int j = 0; j < 2; ++j) cudaEventDestroy(ctx->ev[i][j]);
         cudaEventDestroy(ctx->ev_ready);
+        cudaEventDestroy(ctx->ev_block);
+        for (int i = 0; i < kMaxChunks; ++i) cudaEventDestroy(ctx->ev_cnt[i]);
+        cudaFreeHost(ctx->h_redo);
         for (int j = 0; j < 2; ++j) cudaEventDestroy(ctx->ev_redo[j]);
     }
     for (int s = 0; s < 2; ++s)
         if (ctx->stream[s]) cudaStreamDestroy(ctx->stream[s]);
+    if (ctx->redo_stream) cudaStreamDestroy(ctx->redo_stream);
     delete ctx;
 }
 

@@ -87,7 +87,8 @@ typedef enum {
  * re-run by the library, inside the same call, with ORDERED_SUMS.  Iteration counts and
  * correspondences therefore equal the ordered mode's: a pair either took every decision with a
  * margin the summation order cannot bridge, or was recomputed in the reference's order.
- * icp_b200_call_info.redo_pairs counts the re-runs (about 1 pair in 1000 on BASELINE config 2).
+ * icp_b200_call_info.redo_pairs counts the re-runs (about 1 pair in 40000 on BASELINE config 2; a lone
+ * 1080-point pair takes ~5 ms in reference order, which host-pointer calls hide beside their later chunks).
  * Results are deterministic (independent of scheduling) but, for unflagged pairs, depend in their
  * last bits on the kernel instance chosen for the scan size.
  * ORDERED_SUMS: every sum is accumulated in the reference's own order (src/lib.rs:242-255,45-50):
