@@ -846,7 +846,7 @@ int icp_b200_create(int device, icp_b200_context** out)
         cudaStreamCreateWithFlags(&ctx->stream[1], cudaStreamNonBlocking) != cudaSuccess ||
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess ||
         // highest priority: a re-run CTA is placed ahead of the pending tree-mode CTAs when a slot frees up
-        cudaStreamCreateWithPriority(&ctx->redo_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
+        cudaStreamCreateWithPriority(&ctx->redo_stream, cudaStreamNonBlocking, env_int("ICP_B200_REDO_PRIORITY", 1) ? prio_hi : prio_lo) != cudaSuccess) {
         cudaGetLastError();
         delete ctx;
         return ICP_B200_ERR_CUDA;
