@@ -193,3 +193,87 @@ pub fn estimate_batch_2d(pairs: &[(&[Vector2], &[Vector2], Transform)], max_iter
     check(unsafe { icp_b200_estimate_batch(ctx.0, &batch) });
     out.chunks_exact(6).map(|a| from6(a.try_into().unwrap())).collect()
 }
+
+/// Streaming batches from one thread: `push` enqueues a batch (icp_b200_estimate_batch_submit) on the next of
+/// `DEPTH` contexts and returns the transforms of the batch pushed `DEPTH - 1` calls earlier, once it has been
+/// waited for (icp_b200_estimate_batch_wait); `finish` drains.  The queue entry OWNS every array the batch points
+/// to, so they outlive the wait as the header requires.  (For copies that overlap compute the Vecs should be
+/// page-locked — cudaHostRegister on their buffers; left out of this sketch.)  DEPTH = 3: a batch that holds a
+/// pair the knife-edge guard re-runs comes back about a batch time late, and two further batches in flight keep
+/// the device busy meanwhile.
+pub struct Pipeline {
+    ctx: Vec<*mut IcpB200Context>,
+    inflight: std::collections::VecDeque<InFlight>,
+    next: usize,
+    max_iter: u32,
+}
+
+struct InFlight {
+    slot: usize,
+    _src: Vec<f64>, _dst: Vec<f64>, _so: Vec<u32>, _dof: Vec<u32>, _t0: Vec<f64>,
+    out: Vec<f64>,
+}
+
+impl Pipeline {
+    pub const DEPTH: usize = 3;
+
+    pub fn new(max_iter: usize) -> Self {
+        let ctx = (0..Self::DEPTH).map(|_| {
+            let mut c = core::ptr::null_mut();
+            check(unsafe { icp_b200_create(0, &mut c) });
+            c
+        }).collect();
+        Pipeline { ctx, inflight: Default::default(), next: 0, max_iter: max_iter as u32 }
+    }
+
+    fn retire(&mut self) -> Vec<Transform> {
+        let f = self.inflight.pop_front().unwrap();
+        check(unsafe { icp_b200_estimate_batch_wait(self.ctx[f.slot]) });
+        f.out.chunks_exact(6).map(|a| from6(a.try_into().unwrap())).collect()
+    }
+
+    /// Enqueues `pairs`; returns the results of the oldest batch when DEPTH batches are in flight.
+    pub fn push(&mut self, pairs: &[(&[Vector2], &[Vector2], Transform)]) -> Option<Vec<Transform>> {
+        let b = pairs.len();
+        let (mut src, mut dst) = (Vec::<f64>::new(), Vec::<f64>::new());
+        let (mut so, mut dof) = (vec![0u32; b + 1], vec![0u32; b + 1]);
+        let mut t0 = Vec::<f64>::with_capacity(6 * b);
+        for (k, (s, d, init)) in pairs.iter().enumerate() {
+            for p in s.iter() { src.extend_from_slice(&[p[0], p[1]]); }
+            for p in d.iter() { dst.extend_from_slice(&[p[0], p[1]]); }
+            so[k + 1] = so[k] + s.len() as u32;
+            dof[k + 1] = dof[k] + d.len() as u32;
+            t0.extend_from_slice(&to6(init));
+        }
+        let mut out = vec![0f64; 6 * b];
+        let slot = self.next;
+        self.next = (self.next + 1) % Self::DEPTH;
+        let batch = IcpB200Batch {
+            dim: 2, batch: b as u32, max_iter: self.max_iter, corr_mode: ICP_B200_CORR_NONE,
+            max_src_points: 0, max_dst_points: 0,
+            src: src.as_ptr(), src_off: so.as_ptr(), dst: dst.as_ptr(), dst_off: dof.as_ptr(),
+            init_t: t0.as_ptr(), out_t: out.as_mut_ptr(),
+            out_inner: core::ptr::null_mut(), out_corr: core::ptr::null_mut(),
+            out_corr_hash: core::ptr::null_mut(), out_status: core::ptr::null_mut(),
+            flags: 0, out_cost: core::ptr::null_mut(),
+        };
+        // the Vecs' heap buffers do not move when the Vecs are moved into the queue entry
+        check(unsafe { icp_b200_estimate_batch_submit(self.ctx[slot], &batch) });
+        self.inflight.push_back(InFlight { slot, _src: src, _dst: dst, _so: so, _dof: dof, _t0: t0, out });
+        if self.inflight.len() == Self::DEPTH { Some(self.retire()) } else { None }
+    }
+
+    /// Waits for everything still in flight, oldest first.
+    pub fn finish(&mut self) -> Vec<Vec<Transform>> {
+        let mut all = Vec::new();
+        while !self.inflight.is_empty() { all.push(self.retire()); }
+        all
+    }
+}
+
+impl Drop for Pipeline {
+    fn drop(&mut self) {
+        let _ = self.finish();
+        for c in self.ctx.drain(..) { unsafe { icp_b200_destroy(c) }; }
+    }
+}
