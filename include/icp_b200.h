@@ -176,8 +176,11 @@ int icp_b200_estimate_batch(icp_b200_context *ctx, const icp_b200_batch *batch);
  * untouched; the icp_b200_batch struct itself is copied.  With two contexts a thread keeps the device busy
  * across batch boundaries: submit(A, k) ... submit(B, k+1); wait(A); submit(A, k+2); wait(B) ... — batch
  * k+1's copies and first pairs run under batch k's last pairs, as two threads calling
- * icp_b200_estimate_batch on a context each would achieve (bench.py e2e).  wait without a submitted batch
- * returns OK.  icp_b200_last_call_info is complete after wait. */
+ * icp_b200_estimate_batch on a context each would achieve.  A batch that holds a pair the knife-edge guard
+ * re-runs is waited for about a batch time longer (the ordered re-run shares its SM with the next batch); with
+ * THREE contexts in rotation (submit k+2 before wait k) the device stays busy through that as well — the form
+ * bench.py's e2e figure uses.  wait without a submitted batch returns OK.  icp_b200_last_call_info is complete
+ * after wait. */
 int icp_b200_estimate_batch_submit(icp_b200_context *ctx, const icp_b200_batch *batch);
 int icp_b200_estimate_batch_wait(icp_b200_context *ctx);
 
