@@ -86,6 +86,9 @@ def test_null_arguments_are_rejected():
     assert L.icp_b200_create(0, None) == 1   # ICP_B200_ERR_INVALID_ARGUMENT
     assert L.icp_b200_estimate_batch(None, None) == 1
     assert L.icp_b200_last_error(None) == b"null context"
+    assert L.icp_b200_estimate_batch_submit(None, None) == 1
+    assert L.icp_b200_estimate_batch_wait(None) == 1
+    assert L.icp_b200_target_estimate_batch_submit(None, None) == 1
     L.icp_b200_destroy(None)                 # no-op
     L.icp_b200_target_destroy(None)
 
